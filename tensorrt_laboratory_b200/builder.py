@@ -1,0 +1,199 @@
+"""Plan builder: lowered graph (+ folded weights) -> B2ENGINE blob.
+
+This is the offline step the reference performs with ``trtexec`` (reference ``models/setup.py:32-56``,
+``examples/ONNX/resnet50/build.py:35-67``): it fixes precision and max batch, lays weights out in the
+kernel-native format and writes one self-contained file that ``Runtime::DeserializeEngine`` loads
+(reference ``trtlab/tensorrt/src/runtime.cc:62-95``).  Binary layout: ``csrc/plan_format.h``.
+"""
+from __future__ import annotations
+
+import struct
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import graph as G
+
+PREC_FP32, PREC_FP16 = 0, 1
+OP_INPUT_CAST, OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_FC, OP_SOFTMAX, OP_OUTPUT_CAST = range(7)
+T_ACT, T_VEC = 0, 1
+MAGIC = b"B2ENGINE"
+VERSION = 1
+
+_HEADER = struct.Struct("<8sIIIIIIQQ64s16x")
+_TENSOR = struct.Struct("<64sIIIIIi8x")
+_OP = struct.Struct("<64sIiiiiIIIIIIIIIIIQQQQ16x")
+_BINDING = struct.Struct("<64sIIiI8i16x")
+assert _HEADER.size == 128 and _TENSOR.size == 96 and _OP.size == 176 and _BINDING.size == 128
+
+
+def _roundup(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def phys_channels(c: int, precision: int) -> int:
+    """Channel padding policy of activation tensors.  fp16/tcgen05: 8 (one 16-byte TMA element row,
+    un-swizzled K-chunks) for thin inputs, otherwise a multiple of 64 (one 128-byte swizzle row)."""
+    if precision == PREC_FP32:
+        return c
+    return 8 if c <= 8 else _roundup(c, 64)
+
+
+def _name(s: str) -> bytes:
+    b = s.encode()
+    if len(b) > 63:
+        b = b[:63]
+    return b
+
+
+def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
+               outputs: Optional[Sequence[str]] = None, name: Optional[str] = None) -> bytes:
+    """Serialize ``lowered`` (from :func:`graph.lower` with weights) into a plan blob.
+
+    ``outputs``: tensor names to expose as output bindings (default: the graph output).  4-D activation
+    outputs get an ``OUTPUT_CAST`` to fp32 NCHW; vector outputs (fc / softmax) are written in place.
+    """
+    if precision not in (PREC_FP32, PREC_FP16):
+        raise ValueError("precision must be PREC_FP32 or PREC_FP16")
+    wdtype = np.float16 if precision == PREC_FP16 else np.float32
+    outputs = list(outputs) if outputs else [lowered["output"]]
+    shapes: Dict[str, tuple] = dict(lowered["tensors"])
+    vec_tensors = {op["output"] for op in lowered["ops"] if op["type"] in (G.OP_FC, G.OP_SOFTMAX)}
+
+    tensors: List[dict] = []
+    tindex: Dict[str, int] = {}
+
+    def add_tensor(tname: str) -> int:
+        if tname in tindex:
+            return tindex[tname]
+        c, h, w = shapes[tname]
+        if tname in vec_tensors:
+            rec = dict(name=tname, kind=T_VEC, h=1, w=1, c=c * h * w, c_phys=c * h * w, binding=-1)
+        else:
+            rec = dict(name=tname, kind=T_ACT, h=h, w=w, c=c, c_phys=phys_channels(c, precision), binding=-1)
+        tindex[tname] = len(tensors)
+        tensors.append(rec)
+        return tindex[tname]
+
+    bindings: List[dict] = []
+    ops: List[dict] = []
+    payload = bytearray()
+
+    def add_payload(arr: np.ndarray):
+        while len(payload) % 256:
+            payload.append(0)
+        off = len(payload)
+        raw = np.ascontiguousarray(arr).tobytes()
+        payload.extend(raw)
+        return off, len(raw)
+
+    # input binding + cast
+    cin, hin, win = lowered["input_shape"]
+    t_in = add_tensor(lowered["input"])
+    bindings.append(dict(name=lowered["input"], is_input=1, dtype=0, tensor=t_in, dims=[cin, hin, win]))
+    ops.append(dict(name="cast:" + lowered["input"], type=OP_INPUT_CAST, inp=-1, res=-1, out=t_in, binding=0))
+
+    for op in lowered["ops"]:
+        t = op["type"]
+        ti = add_tensor(op["input"])
+        to = add_tensor(op["output"])
+        rec = dict(name=op["name"], inp=ti, res=-1, out=to, binding=-1)
+        if t == G.OP_CONV:
+            if "W" not in op:
+                raise ValueError(f"conv {op['name']}: lowered graph carries no weights")
+            cin_phys = tensors[ti]["c_phys"]
+            cout_phys = tensors[to]["c_phys"]
+            k = op["k"]
+            taps = k * k
+            taps_phys = _roundup(taps, 2) if (precision == PREC_FP16 and cin_phys == 8) else taps
+            W = np.zeros((cout_phys, taps_phys, cin_phys), dtype=np.float32)
+            W[:op["cout"], :taps, :op["cin"]] = op["W"].reshape(op["cout"], taps, op["cin"])
+            bias = np.zeros(cout_phys, dtype=np.float32)
+            bias[:op["cout"]] = op["bias"]
+            w_off, w_bytes = add_payload(W.astype(wdtype))
+            b_off, b_bytes = add_payload(bias)
+            rec.update(type=OP_CONV, k=k, stride=op["stride"], pad=op["pad"], relu=int(op["relu"]),
+                       cin=op["cin"], cout=op["cout"], cin_phys=cin_phys, cout_phys=cout_phys,
+                       taps=taps, taps_phys=taps_phys, w_off=w_off, w_bytes=w_bytes, b_off=b_off, b_bytes=b_bytes)
+            if op["residual"] is not None:
+                rec["res"] = add_tensor(op["residual"])
+        elif t == G.OP_MAXPOOL:
+            rec.update(type=OP_MAXPOOL, k=op["k"], stride=op["stride"], pad=op["pad"], ceil_mode=int(op["ceil_mode"]))
+        elif t == G.OP_AVGPOOL:
+            rec.update(type=OP_AVGPOOL, k=op["k"], stride=op["stride"])
+        elif t == G.OP_FC:
+            c, h, w = op["in_chw"]
+            c_phys = tensors[ti]["c_phys"]
+            Wf = np.zeros((op["cout"], h * w, c_phys), dtype=np.float32)
+            Wf[:, :, :c] = op["W"].reshape(op["cout"], h * w, c)
+            w_off, w_bytes = add_payload(Wf.astype(wdtype))
+            b_off, b_bytes = add_payload(op["bias"].astype(np.float32))
+            rec.update(type=OP_FC, cin=op["cin"], cout=op["cout"], cin_phys=h * w * c_phys, cout_phys=op["cout"],
+                       w_off=w_off, w_bytes=w_bytes, b_off=b_off, b_bytes=b_bytes)
+        elif t == G.OP_SOFTMAX:
+            rec.update(type=OP_SOFTMAX)
+        else:
+            raise ValueError(f"unsupported lowered op {t}")
+        ops.append(rec)
+
+    for oname in outputs:
+        if oname not in tindex:
+            raise ValueError(f"output tensor {oname!r} is not produced by the graph")
+        ti = tindex[oname]
+        trec = tensors[ti]
+        bidx = len(bindings)
+        if trec["kind"] == T_VEC:
+            if trec["binding"] >= 0:
+                raise ValueError(f"tensor {oname} bound twice")
+            trec["binding"] = bidx
+            bindings.append(dict(name=oname, is_input=0, dtype=0, tensor=ti, dims=[trec["c"]]))
+        else:
+            bindings.append(dict(name=oname, is_input=0, dtype=0, tensor=ti, dims=[trec["c"], trec["h"], trec["w"]]))
+            ops.append(dict(name="cast:" + oname, type=OP_OUTPUT_CAST, inp=ti, res=-1, out=-1, binding=bidx))
+
+    tables = _HEADER.size + len(tensors) * _TENSOR.size + len(ops) * _OP.size + len(bindings) * _BINDING.size
+    payload_offset = _roundup(tables, 256)
+    blob = bytearray()
+    blob += _HEADER.pack(MAGIC, VERSION, precision, max_batch, len(tensors), len(ops), len(bindings),
+                         payload_offset, len(payload), _name(name or lowered["name"]))
+    for t in tensors:
+        blob += _TENSOR.pack(_name(t["name"]), t["kind"], t["h"], t["w"], t["c"], t["c_phys"], t["binding"])
+    for o in ops:
+        blob += _OP.pack(_name(o["name"]), o["type"], o["inp"], o["res"], o["out"], o["binding"],
+                         o.get("k", 0), o.get("stride", 0), o.get("pad", 0), o.get("relu", 0), o.get("ceil_mode", 0),
+                         o.get("cin", 0), o.get("cout", 0), o.get("cin_phys", 0), o.get("cout_phys", 0),
+                         o.get("taps", 0), o.get("taps_phys", 0),
+                         o.get("w_off", 0), o.get("w_bytes", 0), o.get("b_off", 0), o.get("b_bytes", 0))
+    for b in bindings:
+        dims = list(b["dims"]) + [0] * (8 - len(b["dims"]))
+        blob += _BINDING.pack(_name(b["name"]), b["is_input"], b["dtype"], b["tensor"], len(b["dims"]), *dims)
+    blob += b"\0" * (payload_offset - len(blob))
+    blob += payload
+    return bytes(blob)
+
+
+def build_resnet_plan(depth: int = 50, precision: int = PREC_FP16, max_batch: int = 8, seed: int = 0) -> bytes:
+    """Convenience: generated Caffe-v1 ResNet + deterministic weights -> plan."""
+    from . import weights as Wt
+    net = G.resnet_caffe(depth)
+    return build_plan(G.lower(net, Wt.random_weights(net, seed)), precision, max_batch)
+
+
+def single_conv_net(cin: int, h: int, w: int, cout: int, k: int, stride: int, pad: int, relu: bool = True,
+                    residual: bool = False, bias: bool = True) -> dict:
+    """Raw layer list of a one-convolution network (kernel-level parity tests go through the public ABI).
+    With ``residual`` the net is  y = relu(conv_b(x) + conv_a(x))  so the fused add path is exercised."""
+    L = []
+    if residual:
+        L.append(dict(name="short", type="Convolution", bottoms=["data"], tops=["short"], num_output=cout,
+                      kernel_size=k, pad=pad, stride=stride, bias_term=bias))
+    L.append(dict(name="conv", type="Convolution", bottoms=["data"], tops=["conv"], num_output=cout,
+                  kernel_size=k, pad=pad, stride=stride, bias_term=bias))
+    top = "conv"
+    if residual:
+        L.append(dict(name="sum", type="Eltwise", bottoms=["short", "conv"], tops=["sum"], operation="SUM"))
+        top = "sum"
+    if relu:
+        L.append(dict(name="relu", type="ReLU", bottoms=[top], tops=[top]))
+    return {"name": f"conv{k}x{k}s{stride}_{cin}x{h}x{w}_{cout}", "input": "data", "input_dims": [1, cin, h, w],
+            "layers": L}

@@ -1,0 +1,367 @@
+"""ctypes binding of the C ABI (``include/b200infer.h`` + ``include/b200cuda.h``).
+
+The shared library is built in-tree by ``__graft_entry__.build()``.  Loading fails LOUDLY when it is
+missing -- there is no Python/CPU fallback for any compute entry point.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200infer.so")
+
+_lib = None
+
+# (name, restype, argtypes) -- every symbol declared in include/b200infer.h and include/b200cuda.h
+_VP, _I, _SZ, _D, _S = C.c_void_p, C.c_int, C.c_size_t, C.c_double, C.c_char_p
+_PVP = C.POINTER(C.c_void_p)
+SYMBOLS = [
+    ("b2_abi_version", _I, []),
+    ("b2_last_error", _S, []),
+    ("b2_runtime_create", _I, [_PVP]),
+    ("b2_runtime_destroy", None, [_VP]),
+    ("b2_runtime_set_allocator", _I, [_VP, _VP, _VP, _VP]),
+    ("b2_engine_deserialize", _I, [_VP, _VP, _SZ, _PVP]),
+    ("b2_engine_inspect", _I, [_VP, _SZ, _PVP]),
+    ("b2_engine_destroy", None, [_VP]),
+    ("b2_engine_nb_bindings", _I, [_VP]),
+    ("b2_engine_binding_name", _S, [_VP, _I]),
+    ("b2_engine_binding_index", _I, [_VP, _S]),
+    ("b2_engine_binding_is_input", _I, [_VP, _I]),
+    ("b2_engine_binding_dtype", _I, [_VP, _I]),
+    ("b2_engine_binding_dims", _I, [_VP, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int)]),
+    ("b2_engine_max_batch", _I, [_VP]),
+    ("b2_engine_precision", _I, [_VP]),
+    ("b2_engine_name", _S, [_VP]),
+    ("b2_engine_device_memory_size", _SZ, [_VP]),
+    ("b2_engine_weights_size", _SZ, [_VP]),
+    ("b2_engine_flops", _D, [_VP, _I]),
+    ("b2_engine_nb_layers", _I, [_VP]),
+    ("b2_context_create", _I, [_VP, _PVP]),
+    ("b2_context_destroy", None, [_VP]),
+    ("b2_context_set_device_memory", _I, [_VP, _VP]),
+    ("b2_context_enqueue", _I, [_VP, _I, _PVP, _VP, _VP]),
+    ("b2_context_nb_launches", _I, [_VP, _I]),
+    ("b2_context_set_option", _I, [_VP, _S, _I]),
+    ("b2_context_profile", _I, [_VP, _I, _PVP, _VP, C.POINTER(C.c_float), _I]),
+    ("b2_context_launch_name", _S, [_VP, _I, _I]),
+    ("b2_context_launch_flops", _D, [_VP, _I, _I]),
+    ("b2_context_launch_bytes", _D, [_VP, _I, _I]),
+    # b200cuda.h
+    ("b2_device_count", _I, []),
+    ("b2_device_set", _I, [_I]),
+    ("b2_device_get", _I, []),
+    ("b2_device_info", _I, [_I, _S, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_SZ), C.POINTER(_SZ)]),
+    ("b2_malloc_device", _I, [_PVP, _SZ]),
+    ("b2_free_device", _I, [_VP]),
+    ("b2_malloc_host", _I, [_PVP, _SZ]),
+    ("b2_free_host", _I, [_VP]),
+    ("b2_memset_device", _I, [_VP, _I, _SZ, _VP]),
+    ("b2_stream_create", _I, [_PVP]),
+    ("b2_stream_destroy", _I, [_VP]),
+    ("b2_stream_sync", _I, [_VP]),
+    ("b2_stream_query", _I, [_VP]),
+    ("b2_event_create", _I, [_PVP, _I]),
+    ("b2_event_destroy", _I, [_VP]),
+    ("b2_event_record", _I, [_VP, _VP]),
+    ("b2_event_sync", _I, [_VP]),
+    ("b2_event_query", _I, [_VP]),
+    ("b2_event_elapsed_ms", _I, [_VP, _VP, C.POINTER(C.c_float)]),
+    ("b2_stream_wait_event", _I, [_VP, _VP]),
+    ("b2_memcpy_h2d", _I, [_VP, _VP, _SZ, _VP]),
+    ("b2_memcpy_d2h", _I, [_VP, _VP, _SZ, _VP]),
+    ("b2_memcpy_d2d", _I, [_VP, _VP, _SZ, _VP]),
+    ("b2_device_sync", _I, []),
+]
+
+
+class B2Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200infer error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    """dlopen the in-tree library and bind every declared symbol (raises if anything is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built (run `python __graft_entry__.py`). "
+            "There is no CPU fallback for this package.")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise B2Error(rc, (load().b2_last_error() or b"").decode(errors="replace"))
+
+
+def device_count() -> int:
+    return load().b2_device_count()
+
+
+def device_info(device: int = 0) -> dict:
+    lib = load()
+    name = C.create_string_buffer(256)
+    maj, mnr, sms = _I(), _I(), _I()
+    mem, l2 = _SZ(), _SZ()
+    check(lib.b2_device_info(device, name, 256, C.byref(maj), C.byref(mnr), C.byref(sms), C.byref(mem), C.byref(l2)))
+    return dict(name=name.value.decode(), cc=(maj.value, mnr.value), sm_count=sms.value, total_mem=mem.value,
+                l2_bytes=l2.value)
+
+
+class DeviceBuffer:
+    """RAII device allocation (cuda_malloc)."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        p = _VP()
+        check(load().b2_malloc_device(C.byref(p), self.nbytes))
+        self.ptr = p.value
+
+    def free(self):
+        if self.ptr:
+            load().b2_free_device(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """RAII pinned host allocation (cuda_malloc_host) exposed as a numpy array."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        p = _VP()
+        check(load().b2_malloc_host(C.byref(p), max(self.nbytes, 1)))
+        self.ptr = p.value
+        self._raw = (C.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr)
+
+    def array(self, dtype, shape) -> np.ndarray:
+        a = np.frombuffer(self._raw, dtype=dtype, count=int(np.prod(shape)))
+        return a.reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self._raw = None
+            load().b2_free_host(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Stream:
+    def __init__(self):
+        p = _VP()
+        check(load().b2_stream_create(C.byref(p)))
+        self.handle = p.value
+
+    def sync(self):
+        check(load().b2_stream_sync(self.handle))
+
+    def destroy(self):
+        if self.handle:
+            load().b2_stream_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Event:
+    def __init__(self, timing: bool = True):
+        p = _VP()
+        check(load().b2_event_create(C.byref(p), 1 if timing else 0))
+        self.handle = p.value
+
+    def record(self, stream: "Stream"):
+        check(load().b2_event_record(self.handle, stream.handle))
+
+    def sync(self):
+        check(load().b2_event_sync(self.handle))
+
+    def elapsed_ms(self, stop: "Event") -> float:
+        ms = C.c_float()
+        check(load().b2_event_elapsed_ms(self.handle, stop.handle, C.byref(ms)))
+        return ms.value
+
+    def __del__(self):
+        try:
+            if self.handle:
+                load().b2_event_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Engine:
+    """Deserialized plan on the current device (replaces nvinfer1::ICudaEngine)."""
+
+    def __init__(self, blob: bytes, inspect_only: bool = False):
+        lib = load()
+        self._lib = lib
+        self._blob = blob
+        self._rt = _VP()
+        self.handle = _VP()
+        if inspect_only:
+            check(lib.b2_engine_inspect(blob, len(blob), C.byref(self.handle)))
+        else:
+            check(lib.b2_runtime_create(C.byref(self._rt)))
+            check(lib.b2_engine_deserialize(self._rt, blob, len(blob), C.byref(self.handle)))
+        self.name = lib.b2_engine_name(self.handle).decode()
+        self.max_batch = lib.b2_engine_max_batch(self.handle)
+        self.precision = lib.b2_engine_precision(self.handle)
+        self.bindings: List[dict] = []
+        for i in range(lib.b2_engine_nb_bindings(self.handle)):
+            dims = (C.c_int32 * 8)()
+            nd = _I()
+            check(lib.b2_engine_binding_dims(self.handle, i, dims, C.byref(nd)))
+            shape = tuple(int(dims[d]) for d in range(nd.value))
+            self.bindings.append(dict(
+                name=lib.b2_engine_binding_name(self.handle, i).decode(),
+                is_input=bool(lib.b2_engine_binding_is_input(self.handle, i)),
+                dtype=lib.b2_engine_binding_dtype(self.handle, i),
+                shape=shape,
+                item_bytes=int(np.prod(shape)) * 4,
+            ))
+
+    @property
+    def device_memory_size(self) -> int:
+        return self._lib.b2_engine_device_memory_size(self.handle)
+
+    @property
+    def weights_size(self) -> int:
+        return self._lib.b2_engine_weights_size(self.handle)
+
+    def flops(self, batch: int) -> float:
+        return self._lib.b2_engine_flops(self.handle, batch)
+
+    def destroy(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self._lib.b2_engine_destroy(self.handle)
+            self.handle = _VP()
+        if getattr(self, "_rt", None) and self._rt.value:
+            self._lib.b2_runtime_destroy(self._rt)
+            self._rt = _VP()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Session:
+    """One ExecutionContext + its activation arena + device/pinned binding buffers + a stream:
+    the Python-side analogue of the reference's BenchmarkWorkspace (workspace.cc:90-124)."""
+
+    def __init__(self, engine: Engine, options: Optional[Dict[str, int]] = None):
+        lib = load()
+        self._lib = lib
+        self.engine = engine
+        self.ctx = _VP()
+        check(lib.b2_context_create(engine.handle, C.byref(self.ctx)))
+        self.scratch = DeviceBuffer(engine.device_memory_size)
+        check(lib.b2_context_set_device_memory(self.ctx, self.scratch.ptr))
+        for k, v in (options or {}).items():
+            check(lib.b2_context_set_option(self.ctx, k.encode(), int(v)))
+        self.stream = Stream()
+        self.dev = [DeviceBuffer(b["item_bytes"] * engine.max_batch) for b in engine.bindings]
+        self.host = [PinnedBuffer(b["item_bytes"] * engine.max_batch) for b in engine.bindings]
+        self._ptrs = (C.c_void_p * len(self.dev))(*[d.ptr for d in self.dev])
+
+    def set_option(self, key: str, value: int):
+        check(self._lib.b2_context_set_option(self.ctx, key.encode(), int(value)))
+
+    def host_array(self, i: int, batch: Optional[int] = None) -> np.ndarray:
+        b = self.engine.bindings[i]
+        n = batch or self.engine.max_batch
+        return self.host[i].array(np.float32, (n,) + b["shape"])
+
+    def h2d(self, batch: int):
+        for i, b in enumerate(self.engine.bindings):
+            if b["is_input"]:
+                check(self._lib.b2_memcpy_h2d(self.dev[i].ptr, self.host[i].ptr, b["item_bytes"] * batch, self.stream.handle))
+
+    def d2h(self, batch: int):
+        for i, b in enumerate(self.engine.bindings):
+            if not b["is_input"]:
+                check(self._lib.b2_memcpy_d2h(self.host[i].ptr, self.dev[i].ptr, b["item_bytes"] * batch, self.stream.handle))
+
+    def enqueue(self, batch: int):
+        check(self._lib.b2_context_enqueue(self.ctx, batch, self._ptrs, self.stream.handle, None))
+
+    def infer(self, x: np.ndarray) -> Dict[str, np.ndarray]:
+        """Synchronous convenience: pinned H2D -> forward -> D2H.  ``x``: [batch, C, H, W] fp32."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        batch = x.shape[0]
+        inputs = [i for i, b in enumerate(self.engine.bindings) if b["is_input"]]
+        if len(inputs) != 1:
+            raise ValueError("infer() handles single-input engines")
+        self.host_array(inputs[0], batch)[...] = x
+        self.h2d(batch)
+        self.enqueue(batch)
+        self.d2h(batch)
+        self.stream.sync()
+        return {b["name"]: self.host_array(i, batch).copy()
+                for i, b in enumerate(self.engine.bindings) if not b["is_input"]}
+
+    def profile(self, batch: int) -> List[dict]:
+        """Per-launch device times of one (serialised) forward pass."""
+        n = self._lib.b2_context_nb_launches(self.ctx, batch)
+        if n < 0:
+            check(3)
+        ms = (C.c_float * n)()
+        got = self._lib.b2_context_profile(self.ctx, batch, self._ptrs, self.stream.handle, ms, n)
+        if got < 0:
+            raise B2Error(3, (self._lib.b2_last_error() or b"").decode())
+        return [dict(name=self._lib.b2_context_launch_name(self.ctx, batch, i).decode(), ms=float(ms[i]),
+                     flops=self._lib.b2_context_launch_flops(self.ctx, batch, i),
+                     bytes=self._lib.b2_context_launch_bytes(self.ctx, batch, i)) for i in range(n)]
+
+    def nb_launches(self, batch: int) -> int:
+        return self._lib.b2_context_nb_launches(self.ctx, batch)
+
+    def close(self):
+        if self.ctx and self.ctx.value:
+            try:
+                self.stream.sync()
+            except Exception:
+                pass
+            self._lib.b2_context_destroy(self.ctx)
+            self.ctx = _VP()
+        for b in self.dev:
+            b.free()
+        for b in self.host:
+            b.free()
+        self.scratch.free()
+        self.stream.destroy()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

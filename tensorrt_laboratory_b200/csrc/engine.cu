@@ -1,0 +1,839 @@
+// C ABI implementation (include/b200infer.h): plan loader, activation-arena planner, per-batch launch
+// plans (TMA tensor maps, tile selection), CUDA-graph-cached enqueue.
+//
+// Reference counterparts: trtlab/tensorrt/src/runtime.cc:62-143 (deserialize + weight allocation through
+// the IGpuAllocator hook), src/model.cc:76-116 (binding metadata), src/execution_context.cc:9-27,
+// src/workspace.cc:36-57 (setDeviceMemory, enqueueV2, graph capture).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200infer.h"
+#include "kernels.h"
+#include "plan_format.h"
+
+#include "b2_internal.h"
+
+namespace b2i {
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+}  // namespace b2i
+
+namespace {
+using b2i::fail;
+using b2i::g_err;
+
+#define B2_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(B2_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- driver entry points for tensor-map encoding (no link-time libcuda dependency) ------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+int g_driver_version = 0;
+std::once_flag g_driver_once;
+int g_driver_status = 0;
+
+int load_driver_entry_points() {
+    std::call_once(g_driver_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            g_driver_status = 1;
+            return;
+        }
+        g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+        fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            g_driver_status = 2;
+            return;
+        }
+        g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+        cudaDriverGetVersion(&g_driver_version);
+    });
+    return g_driver_status;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+struct Tensor {
+    std::string name;
+    uint32_t kind, h, w, c, c_phys;
+    int binding;
+    size_t item_bytes = 0;  // bytes per batch item
+    size_t offset = 0;      // arena offset (binding < 0)
+    int def = -1, last_use = -1;
+};
+
+struct Op {
+    b2plan::OpRec r;
+    std::string name;
+};
+
+struct Binding {
+    std::string name;
+    bool is_input;
+    int dtype;
+    int tensor;
+    int nd;
+    int32_t dims[8];
+    size_t item_bytes;
+};
+
+enum LKind { L_INPUT_CAST, L_CONV_TC, L_CONV_SIMT, L_MAXPOOL, L_AVGPOOL, L_FC, L_SOFTMAX, L_OUTPUT_CAST };
+
+struct Launch {
+    LKind kind;
+    std::string name;
+    double flops = 0, bytes = 0;
+    b2k::ConvLaunch conv;
+    b2k::SimtConvArgs simt;
+    const void* in = nullptr;
+    void* out = nullptr;
+    const void* w = nullptr;
+    const float* bias = nullptr;
+    int in_binding = -1, out_binding = -1;
+    int N = 0, C = 0, H = 0, W = 0, C_phys = 0, Ho = 0, Wo = 0, k = 0, stride = 0, pad = 0, K = 0, Cout = 0;
+};
+
+struct Plan {
+    int batch = 0;
+    std::vector<Launch> launches;
+};
+
+}  // namespace
+
+struct b2_runtime {
+    b2_alloc_fn alloc = nullptr;
+    b2_free_fn free_ = nullptr;
+    void* user = nullptr;
+};
+
+struct b2_engine {
+    b2_runtime* rt = nullptr;
+    b2_alloc_fn alloc = nullptr;  // snapshot of the runtime's allocator at deserialize time
+    b2_free_fn free_ = nullptr;
+    void* alloc_user = nullptr;
+    std::string name;
+    int precision = 0, max_batch = 0;
+    std::vector<Tensor> tensors;
+    std::vector<Op> ops;
+    std::vector<Binding> bindings;
+    uint8_t* d_payload = nullptr;
+    size_t payload_bytes = 0;
+    size_t arena_bytes = 0;
+    int device = -1;
+    bool inspect_only = false;
+    double flops_per_item = 0;
+    bool half() const { return precision == B2_PREC_FP16; }
+};
+
+struct b2_context {
+    b2_engine* e = nullptr;
+    uint8_t* scratch = nullptr;
+    std::map<int, std::unique_ptr<Plan>> plans;
+    struct GraphKey {
+        int batch;
+        std::vector<void*> ptrs;
+        bool operator<(const GraphKey& o) const { return batch != o.batch ? batch < o.batch : ptrs < o.ptrs; }
+    };
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+    int use_graph = 1;
+    int force_simt = 0;
+    int force_im2col = 0;
+    int force_bn = 0;
+};
+
+namespace {
+
+// ---- plan parsing -----------------------------------------------------------------------------
+std::string fixed_str(const char* p, size_t n) {
+    size_t len = 0;
+    while (len < n && p[len]) ++len;
+    return std::string(p, len);
+}
+
+int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** payload) {
+    using namespace b2plan;
+    if (!blob || nbytes < sizeof(Header)) return fail(B2_EINVAL, "plan: blob too small (%zu bytes)", nbytes);
+    const uint8_t* base = static_cast<const uint8_t*>(blob);
+    Header h;
+    memcpy(&h, base, sizeof h);
+    if (memcmp(h.magic, kMagic, 8) != 0) return fail(B2_EINVAL, "plan: bad magic (not a B2ENGINE blob)");
+    if (h.version != kVersion) return fail(B2_EINVAL, "plan: version %u, this library reads %u", h.version, kVersion);
+    if (h.precision > 1) return fail(B2_EINVAL, "plan: unknown precision %u", h.precision);
+    if (h.max_batch == 0 || h.max_batch > 4096) return fail(B2_EINVAL, "plan: bad max_batch %u", h.max_batch);
+    const size_t tbl = sizeof(Header) + size_t(h.n_tensors) * sizeof(TensorRec) + size_t(h.n_ops) * sizeof(OpRec) +
+                       size_t(h.n_bindings) * sizeof(BindingRec);
+    if (tbl > nbytes || h.payload_offset < tbl || h.payload_offset + h.payload_bytes > nbytes)
+        return fail(B2_EINVAL, "plan: truncated (tables %zu, payload %llu+%llu, blob %zu)", tbl,
+                    (unsigned long long)h.payload_offset, (unsigned long long)h.payload_bytes, nbytes);
+    e->name = fixed_str(h.name, 64);
+    e->precision = h.precision;
+    e->max_batch = h.max_batch;
+    e->payload_bytes = h.payload_bytes;
+    const size_t elt = h.precision == B2_PREC_FP16 ? 2 : 4;
+    const uint8_t* p = base + sizeof(Header);
+    for (uint32_t i = 0; i < h.n_tensors; ++i, p += sizeof(TensorRec)) {
+        TensorRec r;
+        memcpy(&r, p, sizeof r);
+        Tensor t;
+        t.name = fixed_str(r.name, 64);
+        t.kind = r.kind;
+        t.h = r.h, t.w = r.w, t.c = r.c, t.c_phys = r.c_phys;
+        t.binding = r.binding;
+        if (r.kind == T_ACT) {
+            if (r.c_phys < r.c || r.h == 0 || r.w == 0) return fail(B2_EINVAL, "plan: tensor %s has bad dims", t.name.c_str());
+            t.item_bytes = size_t(r.h) * r.w * r.c_phys * elt;
+        } else if (r.kind == T_VEC) {
+            t.item_bytes = size_t(r.c) * 4;
+        } else {
+            return fail(B2_EINVAL, "plan: tensor %s has unknown kind %u", t.name.c_str(), r.kind);
+        }
+        if (t.binding >= int(h.n_bindings)) return fail(B2_EINVAL, "plan: tensor %s binding out of range", t.name.c_str());
+        e->tensors.push_back(t);
+    }
+    auto tensor_ok = [&](int idx, bool optional) { return (optional && idx == -1) || (idx >= 0 && idx < int(h.n_tensors)); };
+    for (uint32_t i = 0; i < h.n_ops; ++i, p += sizeof(OpRec)) {
+        Op op;
+        memcpy(&op.r, p, sizeof(OpRec));
+        op.name = fixed_str(op.r.name, 64);
+        const OpRec& r = op.r;
+        if (r.type > OP_OUTPUT_CAST) return fail(B2_EINVAL, "plan: op %s has unknown type %u", op.name.c_str(), r.type);
+        const bool in_opt = r.type == OP_INPUT_CAST, out_opt = r.type == OP_OUTPUT_CAST;
+        if (!tensor_ok(r.in, in_opt) || !tensor_ok(r.out, out_opt) || !tensor_ok(r.res, true))
+            return fail(B2_EINVAL, "plan: op %s references a missing tensor", op.name.c_str());
+        if ((r.type == OP_INPUT_CAST || r.type == OP_OUTPUT_CAST) && (r.binding < 0 || r.binding >= int(h.n_bindings)))
+            return fail(B2_EINVAL, "plan: cast op %s has a bad binding", op.name.c_str());
+        if (r.w_off + r.w_bytes > h.payload_bytes || r.b_off + r.b_bytes > h.payload_bytes)
+            return fail(B2_EINVAL, "plan: op %s weights outside payload", op.name.c_str());
+        if (r.type == OP_CONV) {
+            if (r.k == 0 || r.stride == 0 || r.taps != r.k * r.k || r.taps_phys < r.taps)
+                return fail(B2_EINVAL, "plan: conv %s has bad geometry", op.name.c_str());
+            if (r.w_bytes != size_t(r.cout_phys) * r.taps_phys * r.cin_phys * elt || r.b_bytes != size_t(r.cout_phys) * 4)
+                return fail(B2_EINVAL, "plan: conv %s weight size mismatch", op.name.c_str());
+            const Tensor& ti = e->tensors[r.in];
+            const Tensor& to = e->tensors[r.out];
+            if (ti.c_phys != r.cin_phys || to.c_phys != r.cout_phys || ti.c != r.cin || to.c != r.cout)
+                return fail(B2_EINVAL, "plan: conv %s channel mismatch with its tensors", op.name.c_str());
+            const uint32_t ho = (ti.h + 2 * r.pad_ - r.k) / r.stride + 1, wo = (ti.w + 2 * r.pad_ - r.k) / r.stride + 1;
+            if (to.h != ho || to.w != wo) return fail(B2_EINVAL, "plan: conv %s output dims mismatch", op.name.c_str());
+            e->flops_per_item += 2.0 * ho * wo * r.cout * r.cin * r.taps;
+        } else if (r.type == OP_FC) {
+            const Tensor& ti = e->tensors[r.in];
+            const size_t K = size_t(ti.h) * ti.w * ti.c_phys;
+            if (r.w_bytes != size_t(r.cout) * K * elt || r.b_bytes != size_t(r.cout) * 4)
+                return fail(B2_EINVAL, "plan: fc %s weight size mismatch", op.name.c_str());
+            e->flops_per_item += 2.0 * ti.h * ti.w * ti.c * r.cout;
+        }
+        e->ops.push_back(op);
+    }
+    for (uint32_t i = 0; i < h.n_bindings; ++i, p += sizeof(BindingRec)) {
+        BindingRec r;
+        memcpy(&r, p, sizeof r);
+        Binding b;
+        b.name = fixed_str(r.name, 64);
+        b.is_input = r.is_input != 0;
+        b.dtype = r.dtype;
+        b.tensor = r.tensor;
+        b.nd = r.nd;
+        if (r.nd == 0 || r.nd > 8) return fail(B2_EINVAL, "plan: binding %s has bad rank", b.name.c_str());
+        if (r.dtype != B2_DT_FLOAT) return fail(B2_EINVAL, "plan: binding %s: only fp32 bindings are supported", b.name.c_str());
+        size_t n = 1;
+        for (uint32_t d = 0; d < 8; ++d) {
+            b.dims[d] = d < r.nd ? r.dims[d] : 0;
+            if (d < r.nd) n *= size_t(r.dims[d]);
+        }
+        b.item_bytes = n * 4;
+        e->bindings.push_back(b);
+    }
+    *payload = base + h.payload_offset;
+    return B2_OK;
+}
+
+// ---- activation arena: first-fit over live intervals ------------------------------------------
+void plan_arena(b2_engine* e) {
+    for (size_t i = 0; i < e->ops.size(); ++i) {
+        const auto& r = e->ops[i].r;
+        if (r.out >= 0 && e->tensors[r.out].def < 0) e->tensors[r.out].def = int(i);
+        for (int t : {r.in, r.res})
+            if (t >= 0) e->tensors[t].last_use = std::max(e->tensors[t].last_use, int(i));
+    }
+    struct Live {
+        size_t off, size;
+        int last;
+    };
+    std::vector<Live> live;
+    size_t top = 0;
+    std::vector<int> order;
+    for (size_t i = 0; i < e->tensors.size(); ++i)
+        if (e->tensors[i].binding < 0 && e->tensors[i].def >= 0) order.push_back(int(i));
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return e->tensors[a].def < e->tensors[b].def; });
+    for (int ti : order) {
+        Tensor& t = e->tensors[ti];
+        if (t.last_use < t.def) t.last_use = t.def;
+        const size_t size = align_up(t.item_bytes * e->max_batch, 1024);
+        // a buffer may be reused once its last reader has been launched BEFORE the new producer
+        live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.last < t.def; }), live.end());
+        std::sort(live.begin(), live.end(), [](const Live& a, const Live& b) { return a.off < b.off; });
+        size_t off = 0;
+        for (const Live& l : live) {
+            if (off + size <= l.off) break;
+            off = std::max(off, l.off + l.size);
+        }
+        t.offset = off;
+        live.push_back({off, size, t.last_use});
+        top = std::max(top, off + size);
+    }
+    e->arena_bytes = align_up(std::max<size_t>(top, 1024), 1024);
+}
+
+// ---- tensor maps ------------------------------------------------------------------------------
+int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                uint32_t box_outer, CUtensorMapSwizzle swz) {
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {inner * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(B2_ECUDA, "cuTensorMapEncodeTiled failed (%d) dims=%llu,%llu box=%u,%u", int(r),
+                    (unsigned long long)inner, (unsigned long long)outer, box_inner, box_outer);
+    return B2_OK;
+}
+
+int make_map_im2col(CUtensorMap* map, const void* base, int C, int W, int H, int N, int k, int stride, int pad,
+                    uint32_t channels_per_pixel, uint32_t pixels_per_column, CUtensorMapSwizzle swz) {
+    cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
+    cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
+    // fprop bounding box: base pixel positions run over [-pad, dim - 1 + pad - (k-1)] (dilation 1)
+    int lower[2] = {-pad, -pad};
+    int upper[2] = {pad - (k - 1), pad - (k - 1)};
+    cuuint32_t estr[4] = {1, cuuint32_t(stride), cuuint32_t(stride), 1};
+    CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
+                                 upper, channels_per_pixel, pixels_per_column, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(B2_ECUDA, "cuTensorMapEncodeIm2col failed (%d) C=%d W=%d H=%d N=%d k=%d s=%d p=%d", int(r), C, W, H,
+                    N, k, stride, pad);
+    // Driver workaround mirrored from CUTLASS (cute/atom/copy_traits_sm90_im2col.hpp): drivers <= 13.1 set a
+    // descriptor bit that misbehaves for tensors smaller than 128 KiB.
+    if (g_driver_version <= 13010 && size_t(C) * W * H * N * 2 < 131072)
+        reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+    return B2_OK;
+}
+
+int pick_bn(int m_tiles, int cout_phys, int forced) {
+    const int cands[4] = {256, 128, 64, 32};
+    if (forced && cout_phys % forced == 0) return forced;
+    for (int bn : cands)
+        if (cout_phys % bn == 0 && m_tiles * (cout_phys / bn) >= 148) return bn;
+    for (int i = 3; i >= 0; --i)
+        if (cout_phys % cands[i] == 0) return cands[i];
+    return 0;
+}
+
+// ---- per-batch launch plan ---------------------------------------------------------------------
+int build_plan(b2_context* c, int batch, Plan** out) {
+    b2_engine* e = c->e;
+    auto it = c->plans.find(batch);
+    if (it != c->plans.end()) {
+        *out = it->second.get();
+        return B2_OK;
+    }
+    if (!c->scratch) return fail(B2_ESTATE, "b2_context_set_device_memory has not been called");
+    if (load_driver_entry_points() != 0) return fail(B2_ECUDA, "cuTensorMapEncode* driver entry points unavailable");
+    auto plan = std::make_unique<Plan>();
+    plan->batch = batch;
+    const bool half = e->half();
+    const size_t elt = half ? 2 : 4;
+    auto tptr = [&](int ti) -> uint8_t* {
+        const Tensor& t = e->tensors[ti];
+        return t.binding >= 0 ? nullptr : c->scratch + t.offset;
+    };
+    for (const Op& op : e->ops) {
+        const b2plan::OpRec& r = op.r;
+        Launch L;
+        L.name = op.name;
+        L.N = batch;
+        switch (r.type) {
+            case b2plan::OP_INPUT_CAST: {
+                const Tensor& t = e->tensors[r.out];
+                L.kind = L_INPUT_CAST;
+                L.in_binding = r.binding;
+                L.out = tptr(r.out);
+                L.C = t.c, L.H = t.h, L.W = t.w, L.C_phys = t.c_phys;
+                L.bytes = double(batch) * t.h * t.w * (t.c * 4.0 + t.c_phys * elt);
+                break;
+            }
+            case b2plan::OP_OUTPUT_CAST: {
+                const Tensor& t = e->tensors[r.in];
+                L.kind = L_OUTPUT_CAST;
+                L.in = tptr(r.in);
+                L.out_binding = r.binding;
+                L.C = t.c, L.H = t.h, L.W = t.w, L.C_phys = t.c_phys;
+                L.bytes = double(batch) * t.h * t.w * (t.c * 4.0 + t.c_phys * elt);
+                break;
+            }
+            case b2plan::OP_CONV: {
+                const Tensor& ti = e->tensors[r.in];
+                const Tensor& to = e->tensors[r.out];
+                const uint8_t* w = e->d_payload + r.w_off;
+                const float* bias = reinterpret_cast<const float*>(e->d_payload + r.b_off);
+                const int M = batch * int(to.h) * int(to.w);
+                L.flops = 2.0 * M * r.cout * r.cin * r.taps;
+                L.bytes = double(batch) * (ti.item_bytes + to.item_bytes * (r.res >= 0 ? 2 : 1)) + double(r.w_bytes);
+                const bool kb64 = r.cin_phys % 64 == 0;
+                const bool kb8 = r.cin_phys == 8;
+                const bool tc_ok = half && !c->force_simt && (kb64 || kb8) && r.cout_phys % 32 == 0 &&
+                                   (kb64 || r.taps_phys % 2 == 0);
+                if (tc_ok) {
+                    L.kind = L_CONV_TC;
+                    b2k::ConvLaunch& cl = L.conv;
+                    memset(&cl, 0, sizeof cl);
+                    cl.kb = kb64 ? 64 : 8;
+                    cl.grid_m = (M + 127) / 128;
+                    cl.bn = pick_bn(cl.grid_m, int(r.cout_phys), c->force_bn);
+                    cl.grid_n = int(r.cout_phys) / cl.bn;
+                    b2k::ConvArgs& a = cl.args;
+                    a.bias = bias;
+                    a.residual = r.res >= 0 ? reinterpret_cast<const __half*>(tptr(r.res)) : nullptr;
+                    a.out = reinterpret_cast<__half*>(tptr(r.out));
+                    a.M = M;
+                    a.Cout = int(r.cout_phys);
+                    a.taps = int(r.taps);
+                    a.taps_phys = int(r.taps_phys);
+                    a.kw = int(r.k);
+                    a.cblocks = kb64 ? int(r.cin_phys) / 64 : 1;
+                    a.num_kblocks = kb64 ? int(r.taps) * a.cblocks : (int(r.taps_phys) + 7) / 8;
+                    a.HoWo = int(to.h * to.w);
+                    a.Wo = int(to.w);
+                    a.stride = int(r.stride);
+                    a.pad = int(r.pad_);
+                    a.relu = int(r.relu);
+                    a.split_k = 1;
+                    const bool tiled = r.k == 1 && r.stride == 1 && r.pad_ == 0 && kb64 && !c->force_im2col;
+                    a.a_mode = tiled ? b2k::A_TILED : b2k::A_IM2COL;
+                    const CUtensorMapSwizzle swz = kb64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+                    int rc;
+                    if (tiled)
+                        rc = make_map_2d(&cl.mapA, tptr(r.in), r.cin_phys, uint64_t(M), 64, 128, swz);
+                    else
+                        rc = make_map_im2col(&cl.mapA, tptr(r.in), int(r.cin_phys), int(ti.w), int(ti.h), batch, int(r.k),
+                                             int(r.stride), int(r.pad_), uint32_t(cl.kb), 128, swz);
+                    if (rc) return rc;
+                    rc = make_map_2d(&cl.mapB, w, uint64_t(r.taps_phys) * r.cin_phys, r.cout_phys, uint32_t(cl.kb),
+                                     uint32_t(cl.bn), swz);
+                    if (rc) return rc;
+                } else {
+                    L.kind = L_CONV_SIMT;
+                    b2k::SimtConvArgs& a = L.simt;
+                    memset(&a, 0, sizeof a);
+                    a.in = tptr(r.in), a.w = w, a.bias = bias;
+                    a.residual = r.res >= 0 ? tptr(r.res) : nullptr;
+                    a.out = tptr(r.out);
+                    a.N = batch, a.H = int(ti.h), a.W = int(ti.w), a.Cin = int(r.cin), a.Cin_phys = int(r.cin_phys);
+                    a.Ho = int(to.h), a.Wo = int(to.w), a.Cout = int(r.cout), a.Cout_phys = int(r.cout_phys);
+                    a.k = int(r.k), a.taps_phys = int(r.taps_phys), a.stride = int(r.stride), a.pad = int(r.pad_);
+                    a.relu = int(r.relu);
+                }
+                break;
+            }
+            case b2plan::OP_MAXPOOL: {
+                const Tensor& ti = e->tensors[r.in];
+                const Tensor& to = e->tensors[r.out];
+                L.kind = L_MAXPOOL;
+                L.in = tptr(r.in), L.out = tptr(r.out);
+                L.H = ti.h, L.W = ti.w, L.C_phys = ti.c_phys, L.Ho = to.h, L.Wo = to.w;
+                L.k = r.k, L.stride = r.stride, L.pad = r.pad_;
+                L.bytes = double(batch) * (ti.item_bytes + to.item_bytes);
+                break;
+            }
+            case b2plan::OP_AVGPOOL: {
+                const Tensor& ti = e->tensors[r.in];
+                L.kind = L_AVGPOOL;
+                L.in = tptr(r.in), L.out = tptr(r.out);
+                L.H = ti.h, L.W = ti.w, L.C_phys = ti.c_phys;
+                L.bytes = double(batch) * ti.item_bytes;
+                break;
+            }
+            case b2plan::OP_FC: {
+                const Tensor& ti = e->tensors[r.in];
+                const Tensor& to = e->tensors[r.out];
+                L.kind = L_FC;
+                L.in = tptr(r.in);
+                L.out = tptr(r.out);
+                L.out_binding = to.binding;
+                L.w = e->d_payload + r.w_off;
+                L.bias = reinterpret_cast<const float*>(e->d_payload + r.b_off);
+                L.K = int(ti.h * ti.w * ti.c_phys);
+                L.Cout = int(r.cout);
+                L.flops = 2.0 * batch * ti.h * ti.w * ti.c * r.cout;
+                L.bytes = double(r.w_bytes) + double(batch) * (ti.item_bytes + to.item_bytes);
+                break;
+            }
+            case b2plan::OP_SOFTMAX: {
+                const Tensor& ti = e->tensors[r.in];
+                const Tensor& to = e->tensors[r.out];
+                L.kind = L_SOFTMAX;
+                L.in = tptr(r.in);
+                L.in_binding = ti.binding;
+                L.out = tptr(r.out);
+                L.out_binding = to.binding;
+                L.C = int(ti.c);
+                L.bytes = double(batch) * ti.c * 8.0;
+                break;
+            }
+            default:
+                return fail(B2_EINVAL, "op %s: unknown type", op.name.c_str());
+        }
+        plan->launches.push_back(std::move(L));
+    }
+    *out = plan.get();
+    c->plans[batch] = std::move(plan);
+    return B2_OK;
+}
+
+int run_launch(const b2_engine* e, const Launch& L, void* const* bindings, cudaStream_t s) {
+    const bool half = e->half();
+    const void* in = L.in_binding >= 0 ? bindings[L.in_binding] : L.in;
+    void* out = L.out_binding >= 0 ? bindings[L.out_binding] : L.out;
+    switch (L.kind) {
+        case L_INPUT_CAST:
+            return b2k::launch_input_cast(static_cast<const float*>(in), out, L.N, L.C, L.H, L.W, L.C_phys, half, s);
+        case L_OUTPUT_CAST:
+            return b2k::launch_output_cast(in, static_cast<float*>(out), L.N, L.C, L.H, L.W, L.C_phys, half, s);
+        case L_CONV_TC:
+            return b2k::launch_conv_f16_tcgen05(L.conv, s);
+        case L_CONV_SIMT:
+            return b2k::launch_conv_simt(L.simt, half, s);
+        case L_MAXPOOL:
+            return b2k::launch_maxpool(in, out, L.N, L.H, L.W, L.C_phys, L.Ho, L.Wo, L.k, L.stride, L.pad, half, s);
+        case L_AVGPOOL:
+            return b2k::launch_avgpool(in, out, L.N, L.H * L.W, L.C_phys, half, s);
+        case L_FC:
+            return b2k::launch_fc(in, L.w, L.bias, static_cast<float*>(out), L.N, L.K, L.Cout, half, s);
+        case L_SOFTMAX:
+            return b2k::launch_softmax(static_cast<const float*>(in), static_cast<float*>(out), L.N, L.C, s);
+    }
+    return int(cudaErrorInvalidValue);
+}
+
+int run_all(const b2_engine* e, const Plan& plan, void* const* bindings, cudaStream_t s) {
+    for (const Launch& L : plan.launches) {
+        const int rc = run_launch(e, L, bindings, s);
+        if (rc != 0)
+            return fail(B2_ECUDA, "launch of %s failed: %s", L.name.c_str(), cudaGetErrorString(cudaError_t(rc)));
+    }
+    return B2_OK;
+}
+
+int check_args(b2_context* c, int batch, void* const* bindings) {
+    if (!c || !bindings) return fail(B2_EINVAL, "null context or bindings");
+    if (batch < 1 || batch > c->e->max_batch) return fail(B2_EINVAL, "batch %d outside [1, %d]", batch, c->e->max_batch);
+    for (size_t i = 0; i < c->e->bindings.size(); ++i)
+        if (!bindings[i]) return fail(B2_EINVAL, "binding %zu (%s) is null", i, c->e->bindings[i].name.c_str());
+    return B2_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int b2_abi_version(void) { return B2_ABI_VERSION; }
+const char* b2_last_error(void) { return g_err.c_str(); }
+
+int b2_runtime_create(b2_runtime** out) {
+    if (!out) return fail(B2_EINVAL, "null out");
+    *out = new b2_runtime();
+    return B2_OK;
+}
+void b2_runtime_destroy(b2_runtime* rt) { delete rt; }
+
+int b2_runtime_set_allocator(b2_runtime* rt, b2_alloc_fn alloc, b2_free_fn free_, void* user) {
+    if (!rt) return fail(B2_EINVAL, "null runtime");
+    if ((alloc == nullptr) != (free_ == nullptr)) return fail(B2_EINVAL, "alloc and free must be set together");
+    rt->alloc = alloc, rt->free_ = free_, rt->user = user;
+    return B2_OK;
+}
+
+static int deserialize_impl(b2_runtime* rt, const void* blob, size_t nbytes, bool inspect_only, b2_engine** out) {
+    if (!out) return fail(B2_EINVAL, "null out");
+    *out = nullptr;
+    std::unique_ptr<b2_engine> e(new b2_engine());
+    e->rt = rt;
+    e->inspect_only = inspect_only;
+    const uint8_t* payload = nullptr;
+    int rc = parse_blob(blob, nbytes, e.get(), &payload);
+    if (rc) return rc;
+    plan_arena(e.get());
+    if (!inspect_only) {
+        int dev = -1;
+        if (cudaGetDevice(&dev) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B2_ENODEVICE, "no CUDA device available (this engine has no CPU fallback)");
+        }
+        cudaDeviceProp prop;
+        B2_CUDA(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major != 10)
+            return fail(B2_ENODEVICE, "device %d is sm_%d%d; this library only carries sm_100a code", dev, prop.major, prop.minor);
+        e->device = dev;
+        rc = b2k::init_conv_kernels();
+        if (rc) return fail(B2_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaError_t(rc)));
+        const size_t bytes = std::max<size_t>(e->payload_bytes, 256);
+        if (rt && rt->alloc) {
+            e->alloc = rt->alloc, e->free_ = rt->free_, e->alloc_user = rt->user;
+            e->d_payload = static_cast<uint8_t*>(rt->alloc(rt->user, bytes, 256, 0));
+            if (!e->d_payload) return fail(B2_ENOMEM, "user allocator returned null for %zu weight bytes", bytes);
+        } else {
+            void* p = nullptr;
+            if (cudaMalloc(&p, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(B2_ENOMEM, "cudaMalloc(%zu) for weights failed", bytes);
+            }
+            e->d_payload = static_cast<uint8_t*>(p);
+        }
+        if (e->payload_bytes) B2_CUDA(cudaMemcpy(e->d_payload, payload, e->payload_bytes, cudaMemcpyHostToDevice));
+    }
+    *out = e.release();
+    return B2_OK;
+}
+
+int b2_engine_deserialize(b2_runtime* rt, const void* blob, size_t nbytes, b2_engine** out) {
+    return deserialize_impl(rt, blob, nbytes, false, out);
+}
+
+// metadata-only load (no device, no weights); contexts cannot be created from it
+int b2_engine_inspect(const void* blob, size_t nbytes, b2_engine** out) {
+    return deserialize_impl(nullptr, blob, nbytes, true, out);
+}
+
+void b2_engine_destroy(b2_engine* e) {
+    if (!e) return;
+    if (e->d_payload) {
+        if (e->free_)
+            e->free_(e->alloc_user, e->d_payload);
+        else
+            cudaFree(e->d_payload);
+    }
+    delete e;
+}
+
+int b2_engine_nb_bindings(const b2_engine* e) { return e ? int(e->bindings.size()) : 0; }
+const char* b2_engine_binding_name(const b2_engine* e, int i) {
+    return (e && i >= 0 && i < int(e->bindings.size())) ? e->bindings[i].name.c_str() : nullptr;
+}
+int b2_engine_binding_index(const b2_engine* e, const char* name) {
+    if (!e || !name) return -1;
+    for (size_t i = 0; i < e->bindings.size(); ++i)
+        if (e->bindings[i].name == name) return int(i);
+    return -1;
+}
+int b2_engine_binding_is_input(const b2_engine* e, int i) {
+    return (e && i >= 0 && i < int(e->bindings.size())) ? int(e->bindings[i].is_input) : 0;
+}
+int b2_engine_binding_dtype(const b2_engine* e, int i) {
+    return (e && i >= 0 && i < int(e->bindings.size())) ? e->bindings[i].dtype : -1;
+}
+int b2_engine_binding_dims(const b2_engine* e, int i, int32_t* dims, int* nd) {
+    if (!e || i < 0 || i >= int(e->bindings.size()) || !dims || !nd) return fail(B2_EINVAL, "bad binding query");
+    *nd = e->bindings[i].nd;
+    for (int d = 0; d < 8; ++d) dims[d] = e->bindings[i].dims[d];
+    return B2_OK;
+}
+int b2_engine_max_batch(const b2_engine* e) { return e ? e->max_batch : 0; }
+int b2_engine_precision(const b2_engine* e) { return e ? e->precision : -1; }
+const char* b2_engine_name(const b2_engine* e) { return e ? e->name.c_str() : nullptr; }
+size_t b2_engine_device_memory_size(const b2_engine* e) { return e ? e->arena_bytes : 0; }
+size_t b2_engine_weights_size(const b2_engine* e) { return e ? e->payload_bytes : 0; }
+double b2_engine_flops(const b2_engine* e, int batch) { return e ? e->flops_per_item * batch : 0.0; }
+int b2_engine_nb_layers(const b2_engine* e) { return e ? int(e->ops.size()) : 0; }
+
+int b2_context_create(b2_engine* e, b2_context** out) {
+    if (!e || !out) return fail(B2_EINVAL, "null engine or out");
+    if (e->inspect_only) return fail(B2_ESTATE, "engine was loaded with b2_engine_inspect (no device resources)");
+    b2_context* c = new b2_context();
+    c->e = e;
+    c->use_graph = env_int("B2_GRAPH", 1);
+    c->force_simt = env_int("B2_FORCE_SIMT", 0);
+    c->force_im2col = env_int("B2_FORCE_IM2COL", 0);
+    c->force_bn = env_int("B2_FORCE_BN", 0);
+    *out = c;
+    return B2_OK;
+}
+
+static void drop_cached(b2_context* c) {
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    c->graphs.clear();
+    c->plans.clear();
+}
+
+void b2_context_destroy(b2_context* c) {
+    if (!c) return;
+    drop_cached(c);
+    delete c;
+}
+
+int b2_context_set_device_memory(b2_context* c, void* scratch) {
+    if (!c || !scratch) return fail(B2_EINVAL, "null context or scratch");
+    if (reinterpret_cast<uintptr_t>(scratch) % 1024 != 0) return fail(B2_EINVAL, "scratch must be 1024-byte aligned");
+    if (c->scratch != scratch) drop_cached(c);
+    c->scratch = static_cast<uint8_t*>(scratch);
+    return B2_OK;
+}
+
+int b2_context_set_option(b2_context* c, const char* key, int value) {
+    if (!c || !key) return fail(B2_EINVAL, "null context or key");
+    const std::string k(key);
+    if (k == "graph") {
+        c->use_graph = value;
+        return B2_OK;
+    }
+    if (k == "simt") c->force_simt = value;
+    else if (k == "im2col") c->force_im2col = value;
+    else if (k == "bn") c->force_bn = value;
+    else return fail(B2_EINVAL, "unknown option '%s'", key);
+    drop_cached(c);
+    return B2_OK;
+}
+
+int b2_context_nb_launches(b2_context* c, int batch) {
+    if (!c) return -1;
+    Plan* plan = nullptr;
+    if (build_plan(c, batch, &plan)) return -1;
+    return int(plan->launches.size());
+}
+
+int b2_context_enqueue(b2_context* c, int batch, void* const* bindings, b2_stream_t stream_, b2_event_t consumed) {
+    int rc = check_args(c, batch, bindings);
+    if (rc) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Plan* plan = nullptr;
+    if ((rc = build_plan(c, batch, &plan))) return rc;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    B2_CUDA(cudaStreamIsCapturing(stream, &cap));
+    if (cap != cudaStreamCaptureStatusNone || !c->use_graph) {
+        if ((rc = run_all(c->e, *plan, bindings, stream))) return rc;
+    } else {
+        b2_context::GraphKey key;
+        key.batch = batch;
+        key.ptrs.assign(bindings, bindings + c->e->bindings.size());
+        auto it = c->graphs.find(key);
+        if (it == c->graphs.end()) {
+            if (c->graphs.size() >= 256) {  // bound the cache; callers normally cycle through a small Buffers pool
+                for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+                c->graphs.clear();
+            }
+            cudaGraph_t graph = nullptr;
+            B2_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            rc = run_all(c->e, *plan, bindings, stream);
+            cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+            if (rc) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            if (ce != cudaSuccess) return fail(B2_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+            cudaGraphExec_t exec = nullptr;
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(B2_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+            it = c->graphs.emplace(std::move(key), exec).first;
+        }
+        B2_CUDA(cudaGraphLaunch(it->second, stream));
+    }
+    if (consumed) B2_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(consumed), stream));
+    return B2_OK;
+}
+
+int b2_context_profile(b2_context* c, int batch, void* const* bindings, b2_stream_t stream_, float* ms, int cap) {
+    if (check_args(c, batch, bindings)) return -1;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    Plan* plan = nullptr;
+    if (build_plan(c, batch, &plan)) return -1;
+    const int n = int(plan->launches.size());
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+    int rc = 0;
+    cudaEventRecord(ev[0], stream);
+    for (int i = 0; i < n && !rc; ++i) {
+        rc = run_launch(c->e, plan->launches[i], bindings, stream);
+        cudaEventRecord(ev[i + 1], stream);
+    }
+    cudaError_t se = cudaStreamSynchronize(stream);
+    if (rc || se != cudaSuccess) {
+        fail(B2_ECUDA, "profile run failed: %s", cudaGetErrorString(rc ? cudaError_t(rc) : se));
+        n > 0 ? (void)0 : (void)0;
+    } else {
+        for (int i = 0; i < n && i < cap; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return (rc || se != cudaSuccess) ? -1 : n;
+}
+
+static const Launch* get_launch(b2_context* c, int batch, int i) {
+    if (!c) return nullptr;
+    Plan* plan = nullptr;
+    if (build_plan(c, batch, &plan)) return nullptr;
+    if (i < 0 || i >= int(plan->launches.size())) return nullptr;
+    return &plan->launches[i];
+}
+const char* b2_context_launch_name(b2_context* c, int batch, int i) {
+    static thread_local std::string s;
+    const Launch* L = get_launch(c, batch, i);
+    if (!L) return nullptr;
+    static const char* kinds[] = {"input_cast", "conv_tcgen05", "conv_simt", "maxpool", "avgpool", "fc", "softmax", "output_cast"};
+    s = std::string(kinds[L->kind]) + ":" + L->name;
+    if (L->kind == L_CONV_TC)
+        s += " bn=" + std::to_string(L->conv.bn) + " kb=" + std::to_string(L->conv.kb) +
+             (L->conv.args.a_mode == b2k::A_TILED ? " tiled" : " im2col") + " grid=" + std::to_string(L->conv.grid_n) +
+             "x" + std::to_string(L->conv.grid_m) + " kblk=" + std::to_string(L->conv.args.num_kblocks);
+    return s.c_str();
+}
+double b2_context_launch_flops(b2_context* c, int batch, int i) {
+    const Launch* L = get_launch(c, batch, i);
+    return L ? L->flops : 0.0;
+}
+double b2_context_launch_bytes(b2_context* c, int batch, int i) {
+    const Launch* L = get_launch(c, batch, i);
+    return L ? L->bytes : 0.0;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// Host-visible launch API of the sm_100a kernels (implemented in kernels.cu).
+// Internal to libb200infer.so -- the public boundary is include/b200infer.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2k {
+
+// ---------------------------------------------------------------------------------------------
+// implicit-GEMM convolution on tcgen05 tensor cores
+//   D[M = batch*Ho*Wo, N = Cout] = A[M, K = taps*Cin] * B[N, K]^T,  fp16 in, fp32 accumulate in TMEM,
+//   epilogue: + bias[n] (+ residual[m][n]) -> relu -> fp16 -> NHWC store.
+// ---------------------------------------------------------------------------------------------
+enum { A_TILED = 0, A_IM2COL = 1 };
+
+struct ConvArgs {
+    const float* bias;       // [Cout_phys] fp32 (BN/Scale folded)
+    const __half* residual;  // [M][Cout_phys] or nullptr
+    __half* out;             // [M][Cout_phys]
+    int M;                   // valid output pixels (batch*Ho*Wo)
+    int Cout;                // physical output channels = row pitch of out/residual
+    int num_kblocks;         // k-blocks of 64 K-elements
+    int cblocks;             // KB==64: Cin_phys/64 channel blocks per tap
+    int taps;                // real filter taps (kh*kw)
+    int taps_phys;           // taps incl. zero-weight padding (even for KB==8)
+    int kw;                  // filter width (tap -> (r, s))
+    int HoWo, Wo;            // output plane, output width (m -> (img, p, q))
+    int stride, pad;
+    int relu;
+    int a_mode;              // A_TILED (1x1 stride-1: plain 2-D TMA) or A_IM2COL (TMA im2col mode)
+    int split_k;             // reserved (1)
+};
+
+struct ConvLaunch {
+    CUtensorMap mapA;  // activations: 2-D tiled [M, Cin] or 4-D im2col (C, W, H, N)
+    CUtensorMap mapB;  // weights: 2-D tiled [Cout_phys, Ktot]
+    ConvArgs args;
+    int bn;            // N tile: 16..256
+    int kb;            // K elements per TMA sub-tile: 64 (SWIZZLE_128B) or 8 (no swizzle, Cin_phys == 8)
+    int grid_m, grid_n;
+};
+
+// returns 0 or a cudaError_t
+int launch_conv_f16_tcgen05(const ConvLaunch& L, cudaStream_t stream);
+// one-time: opt in to large dynamic shared memory for every instantiation
+int init_conv_kernels();
+// smallest supported N tile that divides cout_phys given a preferred tile
+bool conv_tile_supported(int bn, int kb);
+
+// ---------------------------------------------------------------------------------------------
+// SIMT kernels (reference/fp32 engine path, and the non-GEMM operators of the fp16 path)
+// ---------------------------------------------------------------------------------------------
+struct SimtConvArgs {
+    const void* in;        // NHWC [N,H,W,Cin_phys]
+    const void* w;         // [Cout_phys][taps_phys][Cin_phys]
+    const float* bias;     // [Cout_phys]
+    const void* residual;  // NHWC out-shaped or nullptr
+    void* out;             // NHWC [N,Ho,Wo,Cout_phys]
+    int N, H, W, Cin, Cin_phys, Ho, Wo, Cout, Cout_phys;
+    int k, taps_phys, stride, pad, relu;
+};
+int launch_conv_simt(const SimtConvArgs& a, bool half_storage, cudaStream_t stream);
+
+// fp32 NCHW binding -> NHWC activations (zero-filled channel padding)
+int launch_input_cast(const float* src, void* dst, int N, int C, int H, int W, int C_phys,
+                      bool half_storage, cudaStream_t stream);
+// NHWC activations -> fp32 NCHW binding
+int launch_output_cast(const void* src, float* dst, int N, int C, int H, int W, int C_phys,
+                       bool half_storage, cudaStream_t stream);
+int launch_maxpool(const void* src, void* dst, int N, int H, int W, int C_phys, int Ho, int Wo, int k,
+                   int stride, int pad, bool half_storage, cudaStream_t stream);
+// global average pool: NHWC [N,HW,C] -> [N,1,1,C]
+int launch_avgpool(const void* src, void* dst, int N, int HW, int C_phys, bool half_storage,
+                   cudaStream_t stream);
+// out[n][j] = bias[j] + sum_k in[n][k]*w[j][k]   (in: activations, K = HW*C_phys; out fp32 [N][Cout])
+int launch_fc(const void* in, const void* w, const float* bias, float* out, int N, int K, int Cout,
+              bool half_storage, cudaStream_t stream);
+int launch_softmax(const float* in, float* out, int N, int C, cudaStream_t stream);
+
+}  // namespace b2k

@@ -1,0 +1,72 @@
+// On-disk / in-memory layout of a B2ENGINE plan ("serialized engine").
+// Written by tensorrt_laboratory_b200/builder.py, read by engine.cu.  Little-endian, fixed-size records.
+// It plays the role of the TensorRT plan file the reference reads in
+// trtlab/tensorrt/src/runtime.cc:62-95 (file -> deserializeCudaEngine).
+#pragma once
+#include <stdint.h>
+
+namespace b2plan {
+
+constexpr char kMagic[8] = {'B', '2', 'E', 'N', 'G', 'I', 'N', 'E'};
+constexpr uint32_t kVersion = 1;
+
+enum OpType : uint32_t {
+    OP_INPUT_CAST = 0,   // fp32 NCHW binding -> NHWC activation tensor
+    OP_CONV = 1,         // conv + folded BN/Scale bias (+ residual) (+ ReLU)
+    OP_MAXPOOL = 2,
+    OP_AVGPOOL = 3,      // global average pool
+    OP_FC = 4,           // inner product -> fp32 vector
+    OP_SOFTMAX = 5,      // fp32 vector -> fp32 vector
+    OP_OUTPUT_CAST = 6,  // NHWC activation tensor -> fp32 NCHW binding
+};
+
+enum TensorKind : uint32_t { T_ACT = 0 /* NHWC, engine precision */, T_VEC = 1 /* [N, c] fp32 */ };
+
+#pragma pack(push, 1)
+struct Header {  // 128 bytes
+    char magic[8];
+    uint32_t version;
+    uint32_t precision;  // B2_PREC_*
+    uint32_t max_batch;
+    uint32_t n_tensors;
+    uint32_t n_ops;
+    uint32_t n_bindings;
+    uint64_t payload_offset;  // from blob start, 256-byte aligned
+    uint64_t payload_bytes;
+    char name[64];
+    uint8_t pad[16];
+};
+struct TensorRec {  // 96 bytes
+    char name[64];
+    uint32_t kind;
+    uint32_t h, w, c, c_phys;
+    int32_t binding;  // >= 0: storage is bindings[binding] (T_VEC only), -1: activation arena
+    uint8_t pad[8];
+};
+struct OpRec {  // 176 bytes
+    char name[64];
+    uint32_t type;
+    int32_t in, res, out;  // tensor indices (-1 = none)
+    int32_t binding;       // cast ops: binding index
+    uint32_t k, stride, pad_, relu, ceil_mode;
+    uint32_t cin, cout, cin_phys, cout_phys, taps, taps_phys;
+    uint64_t w_off, w_bytes, b_off, b_bytes;  // payload-relative
+    uint8_t pad[16];
+};
+struct BindingRec {  // 128 bytes
+    char name[64];
+    uint32_t is_input;
+    uint32_t dtype;   // B2_DT_*
+    int32_t tensor;   // tensor it feeds / is fed by
+    uint32_t nd;
+    int32_t dims[8];  // per batch item
+    uint8_t pad[16];
+};
+#pragma pack(pop)
+
+static_assert(sizeof(Header) == 128, "Header size");
+static_assert(sizeof(TensorRec) == 96, "TensorRec size");
+static_assert(sizeof(OpRec) == 176, "OpRec size");
+static_assert(sizeof(BindingRec) == 128, "BindingRec size");
+
+}  // namespace b2plan
