@@ -94,7 +94,7 @@ int b2_engine_nb_layers(const b2_engine* e);
 int b2_context_create(b2_engine* e, b2_context** out);
 void b2_context_destroy(b2_context* c);
 /* replaces IExecutionContext::setDeviceMemory (workspace.cc:41); `scratch` must hold
- * b2_engine_device_memory_size() bytes, 1024-byte aligned, and outlive every enqueue */
+ * b2_engine_device_memory_size() bytes, 256-byte aligned, and outlive every enqueue */
 int b2_context_set_device_memory(b2_context* c, void* scratch);
 /* replaces IExecutionContext::enqueue / enqueueV2 (workspace.cc:47,52).  `bindings[i]` are DEVICE
  * pointers in binding order.  Asynchronous on `stream`; legal inside cudaStreamBeginCapture

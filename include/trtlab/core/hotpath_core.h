@@ -1,0 +1,319 @@
+// Minimal stand-ins for the parts of trtlab/core that the inference hot path consumes.
+//
+// trtlab/core is a "kept as-is" collaborator of the path but cannot be
+// built in this image (it needs Boost.Fiber 1.72, cpuaff, glog).  The path only uses four of its
+// facilities; they are re-stated here, std-thread only, with the reference's names and call shapes so
+// the trtlab/tensorrt classes read the same:
+//   ThreadPool::enqueue          trtlab/core/include/trtlab/core/thread_pool.h:142-145
+//   Pool<T>::Create/Push/EmplacePush/Pop(onReturn)   trtlab/core/include/trtlab/core/pool.h:145-245
+//   AsyncComputeWrapper / async_compute<void(Args...)>::wrap   .../async_compute.h:38-118
+//   Resources                    trtlab/core/include/trtlab/core/resources.h:33-42
+//   BytesToString / StringToBytes trtlab/core/src/utils.cc:44-76
+// When integrating into a real trtlab tree define B2_USE_TRTLAB_CORE and these are replaced by the
+// reference's own headers.
+#pragma once
+
+#ifdef B2_USE_TRTLAB_CORE
+#include "trtlab/core/async_compute.h"
+#include "trtlab/core/pool.h"
+#include "trtlab/core/resources.h"
+#include "trtlab/core/thread_pool.h"
+#include "trtlab/core/utils.h"
+#else
+
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <deque>
+#include <functional>
+#include <future>
+#include <iostream>
+#include <memory>
+#include <mutex>
+#include <queue>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <type_traits>
+#include <vector>
+
+namespace trtlab {
+
+// ---- logging / checks (glog-shaped, stderr) ---------------------------------------------------
+namespace detail {
+struct LogLine {
+    std::ostringstream os;
+    bool fatal;
+    bool enabled;
+    LogLine(const char* sev, const char* file, int line, bool fatal_, bool enabled_) : fatal(fatal_), enabled(enabled_) {
+        os << sev << " " << file << ":" << line << "] ";
+    }
+    ~LogLine() noexcept(false) {
+        if (enabled || fatal) std::cerr << os.str() << std::endl;
+        if (fatal) std::abort();
+    }
+    template <typename T>
+    LogLine& operator<<(const T& v) {
+        os << v;
+        return *this;
+    }
+};
+inline int verbosity() {
+    static int v = [] {
+        const char* e = std::getenv("TRTLAB_VERBOSE");
+        return e ? std::atoi(e) : 0;
+    }();
+    return v;
+}
+}  // namespace detail
+
+#define TRTLAB_LOG_INFO ::trtlab::detail::LogLine("I", __FILE__, __LINE__, false, ::trtlab::detail::verbosity() >= 1)
+#define TRTLAB_LOG_WARNING ::trtlab::detail::LogLine("W", __FILE__, __LINE__, false, true)
+#define TRTLAB_LOG_ERROR ::trtlab::detail::LogLine("E", __FILE__, __LINE__, false, true)
+#define TRTLAB_LOG_FATAL ::trtlab::detail::LogLine("F", __FILE__, __LINE__, true, true)
+#define TRTLAB_CHECK(cond) \
+    if (!(cond)) ::trtlab::detail::LogLine("F", __FILE__, __LINE__, true, true) << "Check failed: " #cond " "
+#define TRTLAB_CHECK_OP(a, op, b) \
+    if (!((a)op(b)))              \
+    ::trtlab::detail::LogLine("F", __FILE__, __LINE__, true, true) << "Check failed: " #a " " #op " " #b " (" << (a) << " vs " << (b) << ") "
+
+// ---- utils -------------------------------------------------------------------------------------
+inline std::string BytesToString(size_t bytes) {
+    char buf[64];
+    const char prefixes[] = "KMGTPE";
+    if (bytes < 1024) {
+        snprintf(buf, sizeof buf, "%zu B", bytes);
+        return buf;
+    }
+    int e = 0;
+    double v = double(bytes);
+    while (v >= 1024.0 && e < 6) {
+        v /= 1024.0;
+        ++e;
+    }
+    snprintf(buf, sizeof buf, "%.1f %ciB", v, prefixes[e - 1]);
+    return buf;
+}
+
+// "10b", "1024B", "1KiB", "10MB", "2.4gb": an 'i' selects powers of 1024, otherwise powers of 1000
+inline std::uint64_t StringToBytes(const std::string& s) {
+    size_t pos = 0;
+    double val = 0;
+    try {
+        val = std::stod(s, &pos);
+    } catch (...) {
+        throw std::invalid_argument("StringToBytes: cannot parse \"" + s + "\"");
+    }
+    std::string unit = s.substr(pos);
+    while (!unit.empty() && unit.front() == ' ') unit.erase(unit.begin());
+    if (unit.empty() || (unit.back() != 'b' && unit.back() != 'B'))
+        throw std::invalid_argument("StringToBytes: expected a unit ending in b/B in \"" + s + "\"");
+    unit.pop_back();
+    bool binary = false;
+    if (!unit.empty() && unit.back() == 'i') {
+        binary = true;
+        unit.pop_back();
+    }
+    int exp = 0;
+    if (!unit.empty()) {
+        switch (unit[0]) {
+            case 'k': case 'K': exp = 1; break;
+            case 'm': case 'M': exp = 2; break;
+            case 'g': case 'G': exp = 3; break;
+            case 't': case 'T': exp = 4; break;
+            default: throw std::invalid_argument("StringToBytes: unknown prefix in \"" + s + "\"");
+        }
+        if (unit.size() != 1) throw std::invalid_argument("StringToBytes: bad unit in \"" + s + "\"");
+    }
+    return static_cast<std::uint64_t>(val * std::pow(binary ? 1024.0 : 1000.0, exp));
+}
+
+inline size_t Align(size_t size, size_t alignment) { return (size + alignment - 1) / alignment * alignment; }
+
+// ---- Resources ---------------------------------------------------------------------------------
+struct Resources : public std::enable_shared_from_this<Resources> {
+    virtual ~Resources() {}
+    template <class Target>
+    std::shared_ptr<Target> casted_shared_from_this() {
+        return std::dynamic_pointer_cast<Target>(Resources::shared_from_this());
+    }
+};
+
+// ---- ThreadPool --------------------------------------------------------------------------------
+class ThreadPool {
+  public:
+    explicit ThreadPool(size_t nthreads) {
+        if (nthreads == 0) nthreads = 1;
+        for (size_t i = 0; i < nthreads; ++i) m_Workers.emplace_back([this] { Loop(); });
+    }
+    ThreadPool(const ThreadPool&) = delete;
+    ThreadPool& operator=(const ThreadPool&) = delete;
+    ~ThreadPool() {
+        {
+            std::lock_guard<std::mutex> l(m_Mutex);
+            m_Stop = true;
+        }
+        m_Cv.notify_all();
+        for (auto& t : m_Workers) t.join();
+    }
+
+    template <class F, class... Args>
+    auto enqueue(F&& f, Args&&... args) -> std::future<typename std::invoke_result<F, Args...>::type> {
+        using R = typename std::invoke_result<F, Args...>::type;
+        auto task = std::make_shared<std::packaged_task<R()>>(std::bind(std::forward<F>(f), std::forward<Args>(args)...));
+        std::future<R> fut = task->get_future();
+        enqueue(std::function<void()>([task] { (*task)(); }));
+        return fut;
+    }
+
+    void enqueue(std::function<void()> task) {
+        {
+            std::lock_guard<std::mutex> l(m_Mutex);
+            if (m_Stop) throw std::runtime_error("enqueue on stopped ThreadPool");
+            m_Tasks.push_back(std::move(task));
+        }
+        m_Cv.notify_one();
+    }
+
+    int Size() const { return int(m_Workers.size()); }
+
+  private:
+    void Loop() {
+        for (;;) {
+            std::function<void()> task;
+            {
+                std::unique_lock<std::mutex> l(m_Mutex);
+                m_Cv.wait(l, [this] { return m_Stop || !m_Tasks.empty(); });
+                if (m_Tasks.empty()) return;  // stop requested and drained
+                task = std::move(m_Tasks.front());
+                m_Tasks.pop_front();
+            }
+            task();
+        }
+    }
+    std::vector<std::thread> m_Workers;
+    std::deque<std::function<void()>> m_Tasks;
+    std::mutex m_Mutex;
+    std::condition_variable m_Cv;
+    bool m_Stop = false;
+};
+
+// ---- Pool<T>: blocking pool of shared resources; Pop() hands out a shared_ptr whose deleter returns
+//      the resource (after onReturn) instead of destroying it -------------------------------------
+template <typename T>
+class Pool : public std::enable_shared_from_this<Pool<T>> {
+  public:
+    static std::shared_ptr<Pool<T>> Create() { return std::shared_ptr<Pool<T>>(new Pool<T>()); }
+
+    void Push(std::shared_ptr<T> obj) {
+        {
+            std::lock_guard<std::mutex> l(m_Mutex);
+            m_Items.push(std::move(obj));
+        }
+        m_Cv.notify_one();
+    }
+    void EmplacePush(T* raw) { Push(std::shared_ptr<T>(raw)); }
+    template <typename... Args>
+    void EmplacePush(Args&&... args) {
+        EmplacePush(new T(std::forward<Args>(args)...));
+    }
+
+    std::shared_ptr<T> Pop() {
+        return Pop([](T*) {});
+    }
+    // blocks until a resource is available
+    std::shared_ptr<T> Pop(std::function<void(T*)> onReturn) {
+        std::shared_ptr<T> held = PopWithoutReturn();
+        T* raw = held.get();
+        auto self = this->shared_from_this();
+        return std::shared_ptr<T>(raw, [held, self, onReturn](T* p) mutable {
+            onReturn(p);
+            self->Push(std::move(held));
+            self.reset();
+        });
+    }
+    std::shared_ptr<T> PopWithoutReturn() {
+        std::unique_lock<std::mutex> l(m_Mutex);
+        m_Cv.wait(l, [this] { return !m_Items.empty(); });
+        std::shared_ptr<T> v = std::move(m_Items.front());
+        m_Items.pop();
+        return v;
+    }
+    size_t Size() {
+        std::lock_guard<std::mutex> l(m_Mutex);
+        return m_Items.size();
+    }
+
+  private:
+    Pool() = default;
+    std::queue<std::shared_ptr<T>> m_Items;
+    std::mutex m_Mutex;
+    std::condition_variable m_Cv;
+};
+
+// ---- AsyncCompute: user completion function + promise of its result ----------------------------
+template <typename Signature>
+class AsyncCompute;
+
+template <typename R, typename... Args>
+class AsyncCompute<R(Args...)> {
+  public:
+    using Fn = std::function<R(Args...)>;
+    explicit AsyncCompute(Fn fn) : m_Fn(std::move(fn)) {}
+    std::future<R> Future() { return m_Promise.get_future(); }
+    std::future<R> get_future() { return m_Promise.get_future(); }
+    void operator()(Args... args) {
+        try {
+            if constexpr (std::is_void<R>::value) {
+                m_Fn(args...);
+                m_Promise.set_value();
+            } else {
+                m_Promise.set_value(m_Fn(args...));
+            }
+        } catch (...) {
+            m_Promise.set_exception(std::current_exception());
+        }
+    }
+
+  private:
+    Fn m_Fn;
+    std::promise<R> m_Promise;
+};
+
+template <typename Signature>
+struct AsyncComputeWrapper;
+
+template <typename... Args>
+struct AsyncComputeWrapper<void(Args...)> {
+    template <typename F>
+    static auto Wrap(F&& f) {
+        using R = typename std::invoke_result<F, Args...>::type;
+        return std::make_shared<AsyncCompute<R(Args...)>>(std::forward<F>(f));
+    }
+};
+
+template <typename Signature>
+struct async_compute;
+template <typename... Args>
+struct async_compute<void(Args...)> {
+    template <typename F>
+    static auto wrap(F&& f) {
+        return AsyncComputeWrapper<void(Args...)>::Wrap(std::forward<F>(f));
+    }
+};
+
+}  // namespace trtlab
+
+#ifndef DELETE_COPYABILITY
+#define DELETE_COPYABILITY(T) \
+    T(const T&) = delete;     \
+    T& operator=(const T&) = delete;
+#define DELETE_MOVEABILITY(T) \
+    T(T&&) = delete;          \
+    T& operator=(T&&) = delete;
+#endif
+
+#endif  // B2_USE_TRTLAB_CORE

@@ -1,0 +1,3 @@
+// Forwarding header: keeps the reference's include path (trtlab/tensorrt/include/trtlab/tensorrt/buffers.h).
+#pragma once
+#include "trtlab/tensorrt/tensorrt.h"

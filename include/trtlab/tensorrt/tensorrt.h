@@ -1,0 +1,537 @@
+// trtlab::TensorRT -- the reference's C++ surface for the per-request inference hot path, re-hosted on
+// the B200-native engine (include/b200infer.h) instead of nvinfer1.  No NvInfer.h is included anywhere.
+//
+// v1 ("legacy", the drop-in contract named by the north star; reference include root
+// tensorrt/laboratory/*.h):  Runtime/StandardRuntime/ManagedRuntime, Model, Buffers/FixedBuffers,
+// Bindings, ExecutionContext, InferenceManager, InferRunner, InferBench.
+//   reference: trtlab/tensorrt/src/{inference_manager,buffers,bindings,infer_bench}.cc,
+//              trtlab/tensorrt/include/trtlab/tensorrt/{infer_runner,infer_bench,bindings,buffers}.h
+// v2 (what the reference tree links today): Runtime::deserialize_engine, Model::binding_*,
+//   StaticSingleModelGraphWorkspace / BenchmarkWorkspace / TimedBenchmarkWorkspace.
+//   reference: trtlab/tensorrt/src/{runtime,model,execution_context,workspace}.cc
+#pragma once
+
+#include <chrono>
+#include <functional>
+#include <future>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "b200cuda.h"
+#include "b200infer.h"
+#include "trtlab/core/hotpath_core.h"
+
+// CUDA handle aliases: when the CUDA runtime header is present use its types, otherwise opaque pointers
+#if defined(__CUDACC__) || defined(__CUDA_RUNTIME_H__) || defined(B2_WITH_CUDA_RUNTIME)
+#include <cuda_runtime.h>
+#else
+typedef struct CUstream_st* cudaStream_t;
+typedef struct CUevent_st* cudaEvent_t;
+#endif
+
+namespace trtlab {
+namespace TensorRT {
+
+class Model;
+class Buffers;
+class Bindings;
+class Runtime;
+class InferenceManager;
+
+// ------------------------------------------------------------------------------------------------
+// memory tags used by FixedBuffers<Host, Device> (reference trtlab/cuda memory types:
+// trtlab/cuda/include/trtlab/cuda/memory/device_memory.h:36-84)
+// ------------------------------------------------------------------------------------------------
+struct CudaPinnedHostMemory {
+    static const char* TypeName() { return "CudaPinnedHostMemory"; }
+    static constexpr size_t DefaultAlignment() { return 64; }
+    static void* Allocate(size_t bytes);
+    static void Free(void* ptr);
+};
+struct CudaDeviceMemory {
+    static const char* TypeName() { return "CudaDeviceMemory"; }
+    static constexpr size_t DefaultAlignment() { return 256; }
+    static void* Allocate(size_t bytes);
+    static void Free(void* ptr);
+};
+
+// bump allocator over one allocation; Reset() rewinds (legacy MemoryStack semantics, see
+// examples/10_Internals/README.md:41-48)
+template <typename MemoryType>
+class MemoryStack {
+  public:
+    explicit MemoryStack(size_t size) : m_Size(size), m_Used(0) {
+        m_Base = static_cast<char*>(MemoryType::Allocate(size));
+        if (!m_Base) throw std::bad_alloc();
+    }
+    ~MemoryStack() { MemoryType::Free(m_Base); }
+    DELETE_COPYABILITY(MemoryStack);
+    void* Allocate(size_t size) {
+        const size_t start = Align(m_Used, MemoryType::DefaultAlignment());
+        if (start + size > m_Size) throw std::bad_alloc();
+        m_Used = start + size;
+        return m_Base + start;
+    }
+    void Reset() { m_Used = 0; }
+    size_t Size() const { return m_Size; }
+    size_t Allocated() const { return m_Used; }
+    size_t Available() const { return m_Size - m_Used; }
+
+  private:
+    char* m_Base;
+    size_t m_Size, m_Used;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Model  (v1 method names observed at the reference's call sites: inference_manager.cc:112-154,
+// bindings.cc:58,167,173, pybind/trtlab/infer.cc:214-269; v2: model.h:17-47, model.cc:76-117)
+// ------------------------------------------------------------------------------------------------
+struct IExecutionContext {  // stands in for nvinfer1::IExecutionContext (created without device memory)
+    explicit IExecutionContext(b2_context* c) : handle(c) {}
+    ~IExecutionContext() { b2_context_destroy(handle); }
+    DELETE_COPYABILITY(IExecutionContext);
+    b2_context* handle;
+};
+
+class Model {
+  public:
+    struct TensorBindingInfo {
+        std::string name;
+        bool isInput;
+        int dtype;  // B2_DT_*
+        size_t dtypeSize;
+        std::vector<int> dims;
+        size_t elementsPerBatchItem;
+        size_t bytesPerBatchItem;
+    };
+
+    Model(b2_engine* engine, std::shared_ptr<Runtime> runtime);
+    virtual ~Model();
+    DELETE_COPYABILITY(Model);
+
+    const std::string& Name() const { return m_Name; }
+    void SetName(const std::string& name) { m_Name = name; }
+
+    virtual int GetMaxBatchSize() const;
+    uint32_t GetBindingsCount() const { return uint32_t(m_Bindings.size()); }
+    const TensorBindingInfo& GetBinding(uint32_t id) const;
+    const TensorBindingInfo& GetBinding(const std::string& name) const;
+    uint32_t BindingId(const std::string& name) const;
+    const std::vector<uint32_t>& GetInputBindingIds() const { return m_Inputs; }
+    const std::vector<uint32_t>& GetOutputBindingIds() const { return m_Outputs; }
+    size_t GetBindingMemorySize() const;      // sum over bindings at max batch
+    size_t GetActivationsMemorySize() const;  // replaces ICudaEngine::getDeviceMemorySize
+    size_t GetWeightsMemorySize() const;
+    std::shared_ptr<IExecutionContext> CreateExecutionContext() const;
+
+    // v2 spellings
+    std::size_t binding_element_count(std::uint32_t id) const { return GetBinding(id).elementsPerBatchItem * GetMaxBatchSize(); }
+    std::size_t binding_size_in_bytes(std::uint32_t id) const { return GetBinding(id).bytesPerBatchItem * GetMaxBatchSize(); }
+    std::string bindings_info() const;
+    std::string binding_info(std::uint32_t id) const;
+    b2_engine* engine() const { return m_Engine; }
+    double flops(int batch) const { return b2_engine_flops(m_Engine, batch); }
+
+  private:
+    b2_engine* m_Engine;
+    std::shared_ptr<Runtime> m_Runtime;  // an engine keeps its Runtime alive (runtime.cc:138-141)
+    std::string m_Name;
+    std::vector<TensorBindingInfo> m_Bindings;
+    std::vector<uint32_t> m_Inputs, m_Outputs;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Runtime  (runtime.h:43-110, runtime.cc:47-143)
+// ------------------------------------------------------------------------------------------------
+class Runtime : public std::enable_shared_from_this<Runtime> {
+  public:
+    virtual ~Runtime();
+    DELETE_COPYABILITY(Runtime);
+
+    std::shared_ptr<Model> DeserializeEngine(const std::string& plan_file);
+    std::shared_ptr<Model> DeserializeEngine(const void* data, size_t size);
+    std::shared_ptr<Model> deserialize_engine(const std::string& plan_file) { return DeserializeEngine(plan_file); }
+    std::shared_ptr<Model> deserialize_engine(const void* data, size_t size) { return DeserializeEngine(data, size); }
+
+    // {address, size} of every weight allocation made while deserializing (NvAllocator::use_weights_allocator)
+    struct Pointer {
+        void* addr;
+        size_t size;
+    };
+    const std::vector<Pointer>& weight_pointers() const { return m_Weights; }
+
+  protected:
+    Runtime();
+    std::vector<char> ReadEngineFile(const std::string&) const;
+    virtual void* AllocateDevice(uint64_t size, uint64_t alignment, uint32_t flags) = 0;
+    virtual void FreeDevice(void* ptr) = 0;
+
+  private:
+    static void* AllocThunk(void* user, uint64_t size, uint64_t alignment, uint32_t flags);
+    static void FreeThunk(void* user, void* ptr);
+    b2_runtime* m_Runtime;
+    std::vector<Pointer> m_Weights;
+};
+
+// cudaMalloc-backed weights (reference StandardAllocator, allocator.cc:61-70)
+class StandardRuntime : public Runtime {
+  public:
+    StandardRuntime() = default;
+  protected:
+    void* AllocateDevice(uint64_t size, uint64_t alignment, uint32_t flags) override;
+    void FreeDevice(void* ptr) override;
+};
+// cudaMallocManaged + ReadMostly advice (reference ManagedAllocator, allocator.cc:72-77)
+class ManagedRuntime : public Runtime {
+  public:
+    ManagedRuntime() = default;
+  protected:
+    void* AllocateDevice(uint64_t size, uint64_t alignment, uint32_t flags) override;
+    void FreeDevice(void* ptr) override;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Buffers / FixedBuffers / Bindings  (buffers.h:52-121, buffers.cc:42-78, bindings.h:60-120,
+// bindings.cc:55-175)
+// ------------------------------------------------------------------------------------------------
+class Buffers : public std::enable_shared_from_this<Buffers> {
+  public:
+    Buffers();
+    virtual ~Buffers();
+    DELETE_COPYABILITY(Buffers);
+
+    auto CreateBindings(const std::shared_ptr<Model>&) -> std::shared_ptr<Bindings>;
+    inline cudaStream_t Stream() { return m_Stream; }
+    void Synchronize();
+
+  protected:
+    virtual void Reset() = 0;
+    void ConfigureBindings(const std::shared_ptr<Model>& model, std::shared_ptr<Bindings>);
+    virtual void* AllocateHost(size_t size) = 0;
+    virtual void* AllocateDevice(size_t size) = 0;
+
+  private:
+    cudaStream_t m_Stream;
+    friend class InferenceManager;
+};
+
+template <typename HostMemoryType, typename DeviceMemoryType>
+class FixedBuffers : public Buffers {
+  public:
+    FixedBuffers(size_t host_size, size_t device_size)
+        : m_HostStack(new MemoryStack<HostMemoryType>(host_size)), m_DeviceStack(new MemoryStack<DeviceMemoryType>(device_size)) {}
+    ~FixedBuffers() override {}
+
+  protected:
+    void* AllocateHost(size_t size) final override { return m_HostStack->Allocate(size); }
+    void* AllocateDevice(size_t size) final override { return m_DeviceStack->Allocate(size); }
+    void Reset() final override {
+        m_HostStack->Reset();
+        m_DeviceStack->Reset();
+    }
+
+  private:
+    std::unique_ptr<MemoryStack<HostMemoryType>> m_HostStack;
+    std::unique_ptr<MemoryStack<DeviceMemoryType>> m_DeviceStack;
+};
+
+class Bindings {
+  public:
+    virtual ~Bindings();
+
+    void* HostAddress(uint32_t binding_id);
+    void* DeviceAddress(uint32_t binding_id);
+    void** DeviceAddresses();
+    void SetHostAddress(int binding_id, void* addr);
+    void SetDeviceAddress(int binding_id, void* addr);
+
+    void* ActivationsAddress() { return m_ActivationsAddress; }
+    void SetActivationsAddress(void* addr) { m_ActivationsAddress = addr; }
+
+    void CopyToDevice(uint32_t);
+    void CopyToDevice(const std::vector<uint32_t>&);
+    void CopyToDevice(uint32_t, void*, size_t);
+    void CopyFromDevice(uint32_t);
+    void CopyFromDevice(const std::vector<uint32_t>&);
+    void CopyFromDevice(uint32_t, void*, size_t);
+
+    const std::vector<uint32_t>& InputBindings() const { return m_Model->GetInputBindingIds(); }
+    const std::vector<uint32_t>& OutputBindings() const { return m_Model->GetOutputBindingIds(); }
+
+    auto GetModel() -> const std::shared_ptr<Model>& { return m_Model; }
+    auto BatchSize() const { return m_BatchSize; }
+    void SetBatchSize(uint32_t);
+
+    inline cudaStream_t Stream() const { return m_Buffers->Stream(); }
+    void Synchronize() const { m_Buffers->Synchronize(); }
+    size_t BindingSize(uint32_t binding_id) const;
+
+  private:
+    Bindings(const std::shared_ptr<Model>, const std::shared_ptr<Buffers>);
+    const std::shared_ptr<Model> m_Model;
+    const std::shared_ptr<Buffers> m_Buffers;  // a Bindings keeps its Buffers alive (bindings.h:107-108)
+    uint32_t m_BatchSize;
+    std::vector<void*> m_HostAddresses;
+    std::vector<void*> m_DeviceAddresses;
+    void* m_ActivationsAddress;
+    friend class Buffers;
+};
+
+// ------------------------------------------------------------------------------------------------
+// ExecutionContext  -- v1: the global concurrency token that owns the activation scratch
+// (inference_manager.cc:200-204,254-273; contract examples/10_Internals/README.md:50-52)
+// ------------------------------------------------------------------------------------------------
+class ExecutionContext {
+  public:
+    explicit ExecutionContext(size_t workspace_bytes);
+    virtual ~ExecutionContext();
+    DELETE_COPYABILITY(ExecutionContext);
+
+    void SetContext(std::shared_ptr<IExecutionContext> context);
+    // async forward pass on bindings->Stream(); records the completion event
+    void Infer(const std::shared_ptr<Bindings>&);
+    // waits for the completion event, returns the GPU compute time in seconds
+    double Synchronize();
+    // fiber-friendly variant: 0 when done, 1 while running (cuda_sync<userspace_threads>, sync.h:19-47)
+    int Query();
+    void Reset();
+
+  private:
+    std::shared_ptr<IExecutionContext> m_Context;
+    void* m_Workspace;
+    size_t m_WorkspaceBytes;
+    cudaEvent_t m_Start, m_Done;
+};
+
+// ------------------------------------------------------------------------------------------------
+// InferenceManager (inference_manager.cc:59-327)
+// ------------------------------------------------------------------------------------------------
+class InferenceManager : public ::trtlab::Resources {
+  public:
+    InferenceManager(int max_executions, int max_buffers);
+    virtual ~InferenceManager();
+    DELETE_COPYABILITY(InferenceManager);
+
+    void RegisterModel(const std::string& name, std::shared_ptr<Model> model);
+    void RegisterModel(const std::string& name, std::shared_ptr<Model> model, uint32_t max_concurrency);
+    void AllocateResources();
+
+    auto GetModel(std::string model_name) -> std::shared_ptr<Model>;
+    auto GetBuffers() -> std::shared_ptr<Buffers>;
+    auto GetExecutionContext(const Model* model) -> std::shared_ptr<ExecutionContext>;
+    auto GetExecutionContext(const std::shared_ptr<Model>& model) -> std::shared_ptr<ExecutionContext>;
+
+    auto AcquireThreadPool(const std::string&) -> ThreadPool&;
+    void RegisterThreadPool(const std::string&, std::unique_ptr<ThreadPool> threads);
+    bool HasThreadPool(const std::string&) const;
+    void JoinAllThreads();
+
+    void RegisterRuntime(const std::string&, std::shared_ptr<Runtime>);
+    void SetActiveRuntime(const std::string&);
+    Runtime& ActiveRuntime();
+
+    void ForEachModel(std::function<void(const Model&)>);
+
+    int MaxExecConcurrency() const;
+    int MaxCopyConcurrency() const;
+
+  private:
+    int m_MaxExecutions;
+    int m_MaxBuffers;
+    size_t m_HostStackSize;
+    size_t m_DeviceStackSize;
+    size_t m_ActivationsSize;
+    std::shared_ptr<Pool<Buffers>> m_Buffers;
+    std::shared_ptr<Pool<ExecutionContext>> m_ExecutionContexts;
+    std::map<std::string, std::shared_ptr<Runtime>> m_Runtimes;
+    Runtime* m_ActiveRuntime;
+    std::map<std::string, std::unique_ptr<ThreadPool>> m_ThreadPools;
+    std::map<std::string, std::shared_ptr<Model>> m_Models;
+    std::map<const Model*, std::shared_ptr<Pool<IExecutionContext>>> m_ModelExecutionContexts;
+};
+
+// ------------------------------------------------------------------------------------------------
+// InferRunner: pre -> cuda -> post pipeline over the manager's thread pools (infer_runner.h:37-157)
+// ------------------------------------------------------------------------------------------------
+struct InferRunner : public AsyncComputeWrapper<void(std::shared_ptr<Bindings>&)> {
+    InferRunner(std::shared_ptr<Model> model, std::shared_ptr<InferenceManager> resources)
+        : m_Model{model}, m_Resources{resources} {}
+    InferRunner(InferRunner&&) = delete;
+    InferRunner& operator=(InferRunner&&) = delete;
+    InferRunner(const InferRunner&) = delete;
+    InferRunner& operator=(const InferRunner&) = delete;
+    virtual ~InferRunner() {}
+
+    using BindingsHandle = std::shared_ptr<Bindings>;
+    using PreFn = std::function<void(Bindings&)>;
+
+    template <typename Post>
+    auto Infer(PreFn pre, Post post) {
+        auto compute = Wrap(post);
+        auto future = compute->Future();
+        Enqueue(pre, compute);
+        return future.share();
+    }
+
+    template <typename Post>
+    auto Infer(std::shared_ptr<Bindings> bindings, Post post) {
+        auto compute = Wrap(post);
+        auto future = compute->Future();
+        Enqueue(bindings, compute);
+        return future.share();
+    }
+
+  protected:
+    template <typename T>
+    void Enqueue(PreFn Pre, std::shared_ptr<AsyncCompute<T>> Post) {
+        auto model = m_Model;
+        auto resources = m_Resources;
+        Workers("pre").enqueue([model, resources, Pre, Post]() mutable {
+            auto buffers = resources->GetBuffers();
+            auto bindings = buffers->CreateBindings(model);
+            Pre(*bindings);
+            EnqueueStatic(resources, bindings, Post);
+        });
+    }
+
+    template <typename T>
+    void Enqueue(std::shared_ptr<Bindings> bindings, std::shared_ptr<AsyncCompute<T>> Post) {
+        EnqueueStatic(m_Resources, bindings, Post);
+    }
+
+    // the pipeline stages only capture shared_ptrs, so the InferRunner may die before they run
+    template <typename T>
+    static void EnqueueStatic(std::shared_ptr<InferenceManager> resources, std::shared_ptr<Bindings> bindings,
+                              std::shared_ptr<AsyncCompute<T>> Post) {
+        resources->AcquireThreadPool("cuda").enqueue([resources, bindings, Post]() mutable {
+            bindings->CopyToDevice(bindings->InputBindings());                     // H2D
+            auto trt_ctx = resources->GetExecutionContext(bindings->GetModel());   // may block on 2 pools
+            trt_ctx->Infer(bindings);                                              // forward, async
+            bindings->CopyFromDevice(bindings->OutputBindings());                  // D2H
+            resources->AcquireThreadPool("post").enqueue([bindings, trt_ctx, Post]() mutable {
+                trt_ctx->Synchronize();
+                trt_ctx.reset();  // returns both pool tokens
+                bindings->Synchronize();
+                (*Post)(bindings);
+                bindings.reset();  // returns the Buffers
+            });
+        });
+    }
+
+    inline ThreadPool& Workers(std::string name) { return m_Resources->AcquireThreadPool(name); }
+
+  public:
+    int MaxBatchSize() const { return m_Model->GetMaxBatchSize(); }
+    const Model& GetModel() const { return *m_Model; }
+    const std::shared_ptr<Model> GetModelSmartPtr() const { return m_Model; }
+    InferenceManager& Resources() { return *m_Resources; }
+
+  private:
+    std::shared_ptr<Model> m_Model;
+    std::shared_ptr<InferenceManager> m_Resources;
+};
+
+// ------------------------------------------------------------------------------------------------
+// InferBench (infer_bench.h:35-66, infer_bench.cc:39-110)
+// ------------------------------------------------------------------------------------------------
+enum InferBenchKey {
+    kMaxExecConcurrency = 0,
+    kMaxCopyConcurrency,
+    kBatchSize,
+    kWalltime,
+    kBatchesComputed,
+    kBatchesPerSecond,
+    kInferencesPerSecond,
+    kSecondsPerBatch,
+    kExecutionTimePerBatch,
+    // extensions (not in the reference): request latency percentiles, seconds
+    kLatencyP50,
+    kLatencyP90,
+    kLatencyP99,
+    kLatencyMax
+};
+
+class InferBench {
+  public:
+    InferBench(std::shared_ptr<InferenceManager>);
+    virtual ~InferBench();
+
+    using ModelsList = std::vector<std::shared_ptr<Model>>;
+    using Results = std::map<InferBenchKey, double>;
+
+    std::unique_ptr<Results> Run(const std::shared_ptr<Model> model, uint32_t batch_size, double seconds = 5.0);
+    std::unique_ptr<Results> Run(const ModelsList& models, uint32_t batch_size, double seconds = 5.0);
+    // extension: stop after exactly `max_batches` requests (0 = time-bound only); per-request latencies
+    // (Infer() call -> future ready) are appended to *latencies_s when non-null
+    std::unique_ptr<Results> Run(const ModelsList& models, uint32_t batch_size, double seconds, size_t max_batches,
+                                 std::vector<double>* latencies_s);
+
+  protected:
+    InferenceManager& InferResources() { return *m_Resources; }
+
+  private:
+    std::shared_ptr<InferenceManager> m_Resources;
+};
+
+// ------------------------------------------------------------------------------------------------
+// v2 workspaces (workspace.h:29-106, workspace.cc:21-164)
+// ------------------------------------------------------------------------------------------------
+class StaticSingleModelGraphWorkspace {
+  public:
+    explicit StaticSingleModelGraphWorkspace(std::shared_ptr<Model>);
+    virtual ~StaticSingleModelGraphWorkspace();
+    DELETE_COPYABILITY(StaticSingleModelGraphWorkspace);
+    DELETE_MOVEABILITY(StaticSingleModelGraphWorkspace);
+
+    void enqueue();  // cudaGraphLaunch of the captured forward pass
+    void* binding(std::uint32_t binding_id);
+    std::size_t binding_bytes(std::uint32_t binding_id) const;
+    cudaStream_t stream() { return m_Stream; }
+    std::size_t batch_size();
+    std::string name() const { return m_Name; }
+    const Model& model() const { return *m_Model; }
+
+  private:
+    std::shared_ptr<Model> m_Model;
+    std::shared_ptr<IExecutionContext> m_Context;
+    std::vector<void*> m_Bindings;
+    std::vector<size_t> m_BindingBytes;
+    void* m_DeviceMemory;
+    cudaStream_t m_Stream;
+    void* m_Graph;          // cudaGraph_t
+    void* m_GraphExecutor;  // cudaGraphExec_t
+    std::string m_Name;
+};
+
+class BenchmarkWorkspace : public StaticSingleModelGraphWorkspace {
+  public:
+    explicit BenchmarkWorkspace(std::shared_ptr<Model>);
+    ~BenchmarkWorkspace() override;
+    void* host_binding(std::uint32_t binding_id);
+    void async_h2d();
+    void async_d2h();
+
+  private:
+    std::vector<void*> m_HostBindings;
+};
+
+class TimedBenchmarkWorkspace : private BenchmarkWorkspace {
+  public:
+    explicit TimedBenchmarkWorkspace(std::shared_ptr<Model>);
+    ~TimedBenchmarkWorkspace() override;
+    void enqueue_pipeline();
+    float get_compute_time_ms();
+    float get_h2d_time_ms();
+    float get_d2h_time_ms();
+    using BenchmarkWorkspace::binding;
+    using BenchmarkWorkspace::host_binding;
+    using BenchmarkWorkspace::stream;
+
+  private:
+    cudaEvent_t m_Start, m_CompleteAsyncH2D, m_CompleteCompute, m_CompleteAsyncD2H;
+};
+
+}  // namespace TensorRT
+}  // namespace trtlab

@@ -1,0 +1,43 @@
+/*
+ * trtlab_host.h -- extern "C" handles onto the C++ host layer (trtlab::TensorRT::InferenceManager,
+ * InferRunner, InferBench, TimedBenchmarkWorkspace) so that Python (ctypes) tests and bench.py drive the
+ * SAME pipeline a C++ trtlab application uses.  Not needed by C++ callers, who include
+ * the trtlab/tensorrt headers directly.  Return codes / b2_last_error() as in b200infer.h.
+ */
+#ifndef TRTLAB_HOST_H_
+#define TRTLAB_HOST_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct trt_manager trt_manager;
+
+/* InferenceManager(max_exec, max_buffers /0 -> 2x/) + "pre"/"cuda"/"post" pools + StandardRuntime;
+ * mirrors the setup in reference examples/00_TensorRT/infer.cc:88-114 */
+int trt_manager_create(int max_exec, int max_buffers, int pre_threads, int cuda_threads, int post_threads,
+                       trt_manager** out);
+void trt_manager_destroy(trt_manager* m);
+/* Runtime::DeserializeEngine + InferenceManager::RegisterModel (max_concurrency <= 0: manager default) */
+int trt_manager_register_model(trt_manager* m, const char* name, const void* blob, size_t nbytes, int max_concurrency);
+int trt_manager_allocate(trt_manager* m); /* InferenceManager::AllocateResources */
+/* one request through InferRunner::Infer(pre, post): pinned H2D -> forward -> D2H, blocking */
+int trt_manager_infer(trt_manager* m, const char* model, int batch, const float* input, size_t input_bytes,
+                      float* output, size_t output_bytes, double* compute_seconds);
+/* write a distinct batch from `ring` into the pinned input region of every pooled Buffers */
+int trt_manager_prefill_inputs(trt_manager* m, const char* model, const float* ring, size_t ring_batches);
+/* InferBench::Run closed loop; results16[InferBenchKey]; optional per-request latencies (seconds) */
+int trt_manager_bench(trt_manager* m, const char* model, int batch, double seconds, size_t max_batches,
+                      double* results16, double* latencies, size_t lat_cap, size_t* lat_count);
+/* TimedBenchmarkWorkspace::enqueue_pipeline averaged over iters */
+int trt_timed_pipeline(const void* blob, size_t nbytes, int iters, float* h2d_ms, float* compute_ms, float* d2h_ms);
+/* device-resident throughput of `contexts` concurrent execution contexts (inputs cycled through a device ring) */
+int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int batch, int steps, int warmup,
+                          const float* host_ring, int ring_batches, double* elapsed_ms, int* launches_per_step);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRTLAB_HOST_H_ */

@@ -116,15 +116,16 @@ def caffe_forward(net: dict, weights: Dict[str, dict], x: np.ndarray, dtype=torc
 # fp16-rounding emulation of the ENGINE's numerics plan (separates kernel bugs from rounding)
 # ------------------------------------------------------------------------------------------------
 
-def lowered_forward_f16emu(lowered: dict, x: np.ndarray, keep: Optional[list] = None):
+def lowered_forward_f16emu(lowered: dict, x: np.ndarray, keep: Optional[list] = None, round16: bool = True):
     """Execute *lowered* ops (folded fp32 W in OHWI, bias) with the rounding points of the fp16 engine:
 
     input -> fp16; weights -> fp16; conv accumulates in fp32 (here fp64, i.e. exact) then
     ``+bias (+residual) -> relu -> fp16``; max-pool exact in fp16; global avg-pool fp32 sum / HW -> fp16;
     FC fp16 weights, fp32 accumulate + fp32 bias -> fp32 logits; softmax fp32.
+    ``round16=False`` evaluates the same fused graph exactly (fp64): used to check BN/Scale folding.
     """
     def r16(t):
-        return t.to(torch.float16).to(torch.float64)
+        return t.to(torch.float16).to(torch.float64) if round16 else t.to(torch.float64)
 
     blobs = {lowered["input"]: r16(torch.from_numpy(np.ascontiguousarray(x)).double())}
     snap = {}

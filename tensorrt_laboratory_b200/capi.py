@@ -76,7 +76,21 @@ SYMBOLS = [
     ("b2_memcpy_d2h", _I, [_VP, _VP, _SZ, _VP]),
     ("b2_memcpy_d2d", _I, [_VP, _VP, _SZ, _VP]),
     ("b2_device_sync", _I, []),
+    # trtlab_host.h
+    ("trt_manager_create", _I, [_I, _I, _I, _I, _I, _PVP]),
+    ("trt_manager_destroy", None, [_VP]),
+    ("trt_manager_register_model", _I, [_VP, _S, _VP, _SZ, _I]),
+    ("trt_manager_allocate", _I, [_VP]),
+    ("trt_manager_infer", _I, [_VP, _S, _I, _VP, _SZ, _VP, _SZ, C.POINTER(_D)]),
+    ("trt_manager_prefill_inputs", _I, [_VP, _S, _VP, _SZ]),
+    ("trt_manager_bench", _I, [_VP, _S, _I, _D, _SZ, C.POINTER(_D), C.POINTER(_D), _SZ, C.POINTER(_SZ)]),
+    ("trt_timed_pipeline", _I, [_VP, _SZ, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    ("trt_device_throughput", _I, [_VP, _SZ, _I, _I, _I, _I, _VP, _I, C.POINTER(_D), C.POINTER(_I)]),
 ]
+
+BENCH_KEYS = ["kMaxExecConcurrency", "kMaxCopyConcurrency", "kBatchSize", "kWalltime", "kBatchesComputed",
+              "kBatchesPerSecond", "kInferencesPerSecond", "kSecondsPerBatch", "kExecutionTimePerBatch",
+              "kLatencyP50", "kLatencyP90", "kLatencyP99", "kLatencyMax"]
 
 
 class B2Error(RuntimeError):
@@ -365,3 +379,82 @@ class Session:
             self.close()
         except Exception:
             pass
+
+
+class InferenceManager:
+    """Python handle on the C++ ``trtlab::TensorRT::InferenceManager`` pipeline (pools of Buffers and
+    ExecutionContexts + pre/cuda/post thread pools), the reference's v1 surface
+    (trtlab/tensorrt/src/inference_manager.cc:59-327; python flavour: trtlab/pybind/trtlab/infer.cc:683-694)."""
+
+    def __init__(self, max_exec_concurrency: int = 1, max_copy_concurrency: int = 0, pre_threads: int = 1,
+                 cuda_threads: int = 1, post_threads: int = 3):
+        self._lib = load()
+        self.handle = _VP()
+        check(self._lib.trt_manager_create(max_exec_concurrency, max_copy_concurrency, pre_threads, cuda_threads,
+                                           post_threads, C.byref(self.handle)))
+        self._blobs = []
+        self.models: Dict[str, Engine] = {}
+
+    def register_model(self, name: str, blob: bytes, max_concurrency: int = 0):
+        check(self._lib.trt_manager_register_model(self.handle, name.encode(), blob, len(blob), max_concurrency))
+        self._blobs.append(blob)
+        self.models[name] = Engine(blob, inspect_only=True)
+
+    def update_resources(self):
+        check(self._lib.trt_manager_allocate(self.handle))
+
+    allocate_resources = update_resources
+
+    def infer(self, name: str, x: np.ndarray) -> np.ndarray:
+        meta = self.models[name]
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        batch = x.shape[0]
+        ob = [b for b in meta.bindings if not b["is_input"]][0]
+        out = np.empty((batch,) + ob["shape"], dtype=np.float32)
+        check(self._lib.trt_manager_infer(self.handle, name.encode(), batch, x.ctypes.data, x.nbytes,
+                                          out.ctypes.data, out.nbytes, None))
+        return out
+
+    def prefill_inputs(self, name: str, ring: np.ndarray):
+        ring = np.ascontiguousarray(ring, dtype=np.float32)
+        check(self._lib.trt_manager_prefill_inputs(self.handle, name.encode(), ring.ctypes.data, ring.shape[0]))
+
+    def bench(self, name: str, batch: int, seconds: float = 5.0, max_batches: int = 0, want_latencies: bool = True):
+        res = (C.c_double * 16)()
+        cap = max(max_batches, 1 << 20) if want_latencies else 0
+        lat = (C.c_double * cap)() if cap else None
+        n = _SZ(0)
+        check(self._lib.trt_manager_bench(self.handle, name.encode(), batch, seconds, max_batches, res, lat, cap, C.byref(n)))
+        out = {k: res[i] for i, k in enumerate(BENCH_KEYS)}
+        lats = np.frombuffer(lat, dtype=np.float64, count=n.value).copy() if cap else np.zeros(0)
+        return out, lats
+
+    def close(self):
+        if self.handle and self.handle.value:
+            self._lib.trt_manager_destroy(self.handle)
+            self.handle = _VP()
+        for e in self.models.values():
+            e.destroy()
+        self.models = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def timed_pipeline(blob: bytes, iters: int = 20):
+    a, b, c = C.c_float(), C.c_float(), C.c_float()
+    check(load().trt_timed_pipeline(blob, len(blob), iters, C.byref(a), C.byref(b), C.byref(c)))
+    return dict(h2d_ms=a.value, compute_ms=b.value, d2h_ms=c.value)
+
+
+def device_throughput(blob: bytes, contexts: int, batch: int, steps: int, warmup: int, ring: np.ndarray):
+    """-> (elapsed_ms, kernel launches per step).  ``ring``: [R, batch, C, H, W] fp32 host array."""
+    ring = np.ascontiguousarray(ring, dtype=np.float32)
+    ms = _D()
+    nl = _I()
+    check(load().trt_device_throughput(blob, len(blob), contexts, batch, steps, warmup, ring.ctypes.data,
+                                       ring.shape[0], C.byref(ms), C.byref(nl)))
+    return ms.value, nl.value

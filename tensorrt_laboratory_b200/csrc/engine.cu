@@ -714,7 +714,7 @@ void b2_context_destroy(b2_context* c) {
 
 int b2_context_set_device_memory(b2_context* c, void* scratch) {
     if (!c || !scratch) return fail(B2_EINVAL, "null context or scratch");
-    if (reinterpret_cast<uintptr_t>(scratch) % 1024 != 0) return fail(B2_EINVAL, "scratch must be 1024-byte aligned");
+    if (reinterpret_cast<uintptr_t>(scratch) % 256 != 0) return fail(B2_EINVAL, "scratch must be 256-byte aligned (cudaMalloc alignment)");
     if (c->scratch != scratch) drop_cached(c);
     c->scratch = static_cast<uint8_t*>(scratch);
     return B2_OK;

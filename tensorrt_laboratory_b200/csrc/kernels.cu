@@ -656,8 +656,71 @@ __global__ void fc_kernel(const T* __restrict__ in, const T* __restrict__ w, con
     }
 }
 
+// fp16 fast path: up to 8 batch rows staged in shared memory, one warp per output neuron, 128-bit loads.
+// Requires K % 256 == 0 (each lane owns 8 consecutive K elements per 256-element slab).
+template <int ROWS>
+__global__ void __launch_bounds__(256)
+fc_h8_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const float* __restrict__ bias,
+             float* __restrict__ out, int N, int K, int Cout) {
+    extern __shared__ uint4 s_in[];  // [ROWS][K/8]
+    const int kv = K / 8;
+    for (int nb = 0; nb < N; nb += ROWS) {
+        const int rows = min(ROWS, N - nb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * kv; i += blockDim.x)
+            s_in[i] = __ldg(reinterpret_cast<const uint4*>(in + static_cast<size_t>(nb) * K) + i);
+        __syncthreads();
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int j = blockIdx.x * (blockDim.x >> 5) + warp;
+        if (j < Cout) {
+            float acc[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+            const uint4* wr = reinterpret_cast<const uint4*>(w + static_cast<size_t>(j) * K);
+            for (int v = lane; v < kv; v += 32) {
+                const uint4 wv = __ldg(wr + v);
+                const __half2* w2 = reinterpret_cast<const __half2*>(&wv);
+                float2 wf[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) wf[q] = __half22float2(w2[q]);
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    if (r < rows) {
+                        const uint4 xv = s_in[r * kv + v];
+                        const __half2* x2 = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 xf = __half22float2(x2[q]);
+                            acc[r] = fmaf(wf[q].x, xf.x, acc[r]);
+                            acc[r] = fmaf(wf[q].y, xf.y, acc[r]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                float v = acc[r];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && r < rows) out[static_cast<size_t>(nb + r) * Cout + j] = v + bias[j];
+            }
+        }
+    }
+}
+
 int launch_fc(const void* in, const void* w, const float* bias, float* out, int N, int K, int Cout, bool half_storage,
               cudaStream_t stream) {
+    if (half_storage && K % 8 == 0 && static_cast<size_t>(K) * 2 * 8 <= 96 * 1024) {
+        const int threads = 256;  // 8 warps -> 8 neurons per block
+        const unsigned blocks = static_cast<unsigned>((Cout + 7) / 8);
+        const size_t smem = static_cast<size_t>(K) * 2 * 8;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(fc_h8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            attr_set = true;
+        }
+        fc_h8_kernel<8><<<blocks, threads, smem, stream>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<const __half*>(w), bias, out, N, K, Cout);
+        return static_cast<int>(cudaGetLastError());
+    }
     const int threads = 128;  // 4 warps
     const unsigned blocks = static_cast<unsigned>((Cout + 3) / 4);
     if (half_storage)

@@ -1,0 +1,274 @@
+// extern "C" access to the C++ host layer (InferenceManager / InferRunner / InferBench / workspaces) for
+// the Python tests and bench.py.  Exceptions become B2_E* codes + b2_last_error().
+#define B2_WITH_CUDA_RUNTIME 1
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <algorithm>
+#include <exception>
+
+#include "../b2_internal.h"
+#include "trtlab/tensorrt/tensorrt.h"
+#include "trtlab_host.h"
+
+using namespace trtlab;
+using namespace trtlab::TensorRT;
+using b2i::fail;
+
+struct trt_manager {
+    std::shared_ptr<InferenceManager> mgr;
+    std::shared_ptr<Runtime> runtime;
+};
+
+#define TRT_TRY try {
+#define TRT_CATCH                                                                  \
+    }                                                                              \
+    catch (const std::bad_alloc&) { return fail(B2_ENOMEM, "out of memory"); }     \
+    catch (const std::exception& ex) { return fail(B2_EINVAL, "%s", ex.what()); }
+
+extern "C" {
+
+int trt_manager_create(int max_exec, int max_buffers, int pre_threads, int cuda_threads, int post_threads,
+                       trt_manager** out) {
+    if (!out || max_exec < 1) return fail(B2_EINVAL, "bad arguments");
+    TRT_TRY
+    auto* m = new trt_manager();
+    m->mgr = std::make_shared<InferenceManager>(max_exec, max_buffers);
+    m->runtime = std::make_shared<StandardRuntime>();
+    // same pool names/sizes the reference's infer.x registers (examples/00_TensorRT/infer.cc:91-93)
+    m->mgr->RegisterThreadPool("pre", std::make_unique<ThreadPool>(size_t(std::max(pre_threads, 1))));
+    m->mgr->RegisterThreadPool("cuda", std::make_unique<ThreadPool>(size_t(std::max(cuda_threads, 1))));
+    m->mgr->RegisterThreadPool("post", std::make_unique<ThreadPool>(size_t(std::max(post_threads, 1))));
+    m->mgr->RegisterRuntime("default", m->runtime);
+    m->mgr->SetActiveRuntime("default");
+    *out = m;
+    return B2_OK;
+    TRT_CATCH
+}
+
+void trt_manager_destroy(trt_manager* m) {
+    if (!m) return;
+    m->mgr->JoinAllThreads();
+    delete m;
+}
+
+int trt_manager_register_model(trt_manager* m, const char* name, const void* blob, size_t nbytes, int max_concurrency) {
+    if (!m || !name || !blob) return fail(B2_EINVAL, "bad arguments");
+    TRT_TRY
+    auto model = m->mgr->ActiveRuntime().DeserializeEngine(blob, nbytes);
+    if (max_concurrency > 0)
+        m->mgr->RegisterModel(name, model, uint32_t(max_concurrency));
+    else
+        m->mgr->RegisterModel(name, model);
+    return B2_OK;
+    TRT_CATCH
+}
+
+int trt_manager_allocate(trt_manager* m) {
+    if (!m) return fail(B2_EINVAL, "null manager");
+    TRT_TRY
+    m->mgr->AllocateResources();
+    return B2_OK;
+    TRT_CATCH
+}
+
+int trt_manager_infer(trt_manager* m, const char* model_name, int batch, const float* input, size_t input_bytes,
+                      float* output, size_t output_bytes, double* compute_seconds) {
+    if (!m || !model_name || !input || !output) return fail(B2_EINVAL, "bad arguments");
+    TRT_TRY
+    auto model = m->mgr->GetModel(model_name);
+    if (model->GetInputBindingIds().size() != 1 || model->GetOutputBindingIds().size() != 1)
+        return fail(B2_EINVAL, "trt_manager_infer handles single-input single-output models");
+    const uint32_t in_id = model->GetInputBindingIds()[0], out_id = model->GetOutputBindingIds()[0];
+    if (batch < 1 || batch > model->GetMaxBatchSize()) return fail(B2_EINVAL, "batch %d out of range", batch);
+    if (input_bytes != model->GetBinding(in_id).bytesPerBatchItem * size_t(batch) ||
+        output_bytes != model->GetBinding(out_id).bytesPerBatchItem * size_t(batch))
+        return fail(B2_EINVAL, "binding size mismatch");
+    InferRunner runner(model, m->mgr);
+    auto fut = runner.Infer(
+        [&](Bindings& b) {  // "pre" stage: fill the pinned input binding
+            b.SetBatchSize(uint32_t(batch));
+            memcpy(b.HostAddress(in_id), input, input_bytes);
+        },
+        [&](std::shared_ptr<Bindings>& b) {  // "post" stage: read the pinned output binding
+            memcpy(output, b->HostAddress(out_id), output_bytes);
+            return 0;
+        });
+    fut.get();
+    if (compute_seconds) *compute_seconds = 0.0;
+    return B2_OK;
+    TRT_CATCH
+}
+
+// Give every pooled Buffers a distinct input batch in its pinned host stack.  Bindings are bump-allocated
+// from a stack that is Reset() on return, so the addresses (and contents) persist across requests.
+int trt_manager_prefill_inputs(trt_manager* m, const char* model_name, const float* ring, size_t ring_batches) {
+    if (!m || !model_name || !ring || ring_batches == 0) return fail(B2_EINVAL, "bad arguments");
+    TRT_TRY
+    auto model = m->mgr->GetModel(model_name);
+    const uint32_t in_id = model->GetInputBindingIds()[0];
+    const size_t bytes = model->GetBinding(in_id).bytesPerBatchItem * size_t(model->GetMaxBatchSize());
+    std::vector<std::shared_ptr<Buffers>> held;
+    for (int i = 0; i < m->mgr->MaxCopyConcurrency(); ++i) {
+        auto buffers = m->mgr->GetBuffers();
+        auto bindings = buffers->CreateBindings(model);
+        memcpy(bindings->HostAddress(in_id), reinterpret_cast<const char*>(ring) + (size_t(i) % ring_batches) * bytes, bytes);
+        held.push_back(buffers);  // hold all of them so each pop yields a different Buffers
+    }
+    return B2_OK;
+    TRT_CATCH
+}
+
+int trt_manager_bench(trt_manager* m, const char* model_name, int batch, double seconds, size_t max_batches,
+                      double* results16, double* latencies, size_t lat_cap, size_t* lat_count) {
+    if (!m || !model_name || !results16) return fail(B2_EINVAL, "bad arguments");
+    TRT_TRY
+    auto model = m->mgr->GetModel(model_name);
+    InferBench bench(m->mgr);
+    std::vector<double> lat;
+    InferBench::ModelsList models = {model};
+    auto res = bench.Run(models, uint32_t(batch), seconds, max_batches, latencies ? &lat : nullptr);
+    for (int i = 0; i < 16; ++i) results16[i] = 0.0;
+    for (const auto& kv : *res)
+        if (int(kv.first) < 16) results16[int(kv.first)] = kv.second;
+    if (latencies && lat_count) {
+        *lat_count = std::min(lat.size(), lat_cap);
+        memcpy(latencies, lat.data(), *lat_count * sizeof(double));
+    }
+    return B2_OK;
+    TRT_CATCH
+}
+
+// H2D / compute / D2H breakdown of the v2 single-stream pipeline (TimedBenchmarkWorkspace)
+int trt_timed_pipeline(const void* blob, size_t nbytes, int iters, float* h2d_ms, float* compute_ms, float* d2h_ms) {
+    if (!blob || iters < 1) return fail(B2_EINVAL, "bad arguments");
+    TRT_TRY
+    auto runtime = std::make_shared<StandardRuntime>();
+    auto model = runtime->deserialize_engine(blob, nbytes);
+    TimedBenchmarkWorkspace ws(model);
+    double a = 0, b = 0, c = 0;
+    for (int i = 0; i < iters + 2; ++i) {
+        ws.enqueue_pipeline();
+        if (cudaStreamSynchronize(ws.stream()) != cudaSuccess) return fail(B2_ECUDA, "pipeline failed");
+        if (i >= 2) {
+            a += ws.get_h2d_time_ms();
+            b += ws.get_compute_time_ms();
+            c += ws.get_d2h_time_ms();
+        }
+    }
+    if (h2d_ms) *h2d_ms = float(a / iters);
+    if (compute_ms) *compute_ms = float(b / iters);
+    if (d2h_ms) *d2h_ms = float(c / iters);
+    return B2_OK;
+    TRT_CATCH
+}
+
+// Device-resident throughput: `contexts` execution contexts on independent streams, inputs cycled through
+// a device ring (sized by the caller to exceed L2), `steps` forward passes issued round-robin, timed with
+// CUDA events from the first launch to the completion of the last stream.
+int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int batch, int steps, int warmup,
+                          const float* host_ring, int ring_batches, double* elapsed_ms, int* launches_per_step) {
+    if (!blob || contexts < 1 || steps < 1 || !host_ring || ring_batches < 1 || !elapsed_ms) return fail(B2_EINVAL, "bad arguments");
+    b2_runtime* rt = nullptr;
+    b2_engine* eng = nullptr;
+    int rc = b2_runtime_create(&rt);
+    if (rc) return rc;
+    rc = b2_engine_deserialize(rt, blob, nbytes, &eng);
+    if (rc) {
+        b2_runtime_destroy(rt);
+        return rc;
+    }
+    const int nb = b2_engine_nb_bindings(eng);
+    int in_id = -1;
+    std::vector<size_t> bytes(nb);
+    for (int i = 0; i < nb; ++i) {
+        int32_t dims[8];
+        int nd = 0;
+        b2_engine_binding_dims(eng, i, dims, &nd);
+        size_t n = 4;
+        for (int d = 0; d < nd; ++d) n *= size_t(dims[d]);
+        bytes[i] = n * size_t(b2_engine_max_batch(eng));
+        if (b2_engine_binding_is_input(eng, i)) in_id = i;
+    }
+    struct Ctx {
+        b2_context* c = nullptr;
+        void* scratch = nullptr;
+        std::vector<void*> bind;
+        cudaStream_t s = nullptr;
+        cudaEvent_t done = nullptr;
+    };
+    std::vector<Ctx> ctx(contexts);
+    std::vector<void*> ring(ring_batches, nullptr);
+    cudaStream_t ctrl = nullptr;
+    cudaEvent_t start = nullptr, stop = nullptr;
+    int status = B2_OK;
+    auto cuda_ok = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && status == B2_OK) status = fail(B2_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    const size_t in_bytes = bytes[in_id] / size_t(b2_engine_max_batch(eng)) * size_t(batch);
+    for (int r = 0; r < ring_batches && status == B2_OK; ++r) {
+        if (cuda_ok(cudaMalloc(&ring[r], bytes[in_id]), "cudaMalloc ring"))
+            cuda_ok(cudaMemcpy(ring[r], reinterpret_cast<const char*>(host_ring) + size_t(r) * in_bytes, in_bytes, cudaMemcpyHostToDevice), "ring upload");
+    }
+    for (auto& x : ctx) {
+        if (status != B2_OK) break;
+        if ((status = b2_context_create(eng, &x.c))) break;
+        if (!cuda_ok(cudaMalloc(&x.scratch, std::max<size_t>(b2_engine_device_memory_size(eng), 1024)), "cudaMalloc scratch")) break;
+        if ((status = b2_context_set_device_memory(x.c, x.scratch))) break;
+        x.bind.assign(nb, nullptr);
+        for (int i = 0; i < nb; ++i)
+            if (i != in_id && !cuda_ok(cudaMalloc(&x.bind[i], bytes[i]), "cudaMalloc binding")) break;
+        cuda_ok(cudaStreamCreate(&x.s), "cudaStreamCreate");
+        cuda_ok(cudaEventCreateWithFlags(&x.done, cudaEventDisableTiming), "cudaEventCreate");
+    }
+    if (status == B2_OK) {
+        cuda_ok(cudaStreamCreate(&ctrl), "cudaStreamCreate");
+        cuda_ok(cudaEventCreate(&start), "cudaEventCreate");
+        cuda_ok(cudaEventCreate(&stop), "cudaEventCreate");
+    }
+    auto issue = [&](int n_steps, int offset) {
+        for (int i = 0; i < n_steps && status == B2_OK; ++i) {
+            Ctx& x = ctx[size_t(i % contexts)];
+            x.bind[in_id] = ring[size_t((i + offset) % ring_batches)];
+            status = b2_context_enqueue(x.c, batch, x.bind.data(), x.s, nullptr);
+        }
+    };
+    if (status == B2_OK) {
+        issue(std::max(warmup, contexts * ring_batches <= 256 ? contexts * ring_batches : warmup), 0);  // also builds every cached graph
+        cuda_ok(cudaDeviceSynchronize(), "warmup sync");
+    }
+    if (status == B2_OK) {
+        cuda_ok(cudaEventRecord(start, ctrl), "record start");
+        for (auto& x : ctx) cuda_ok(cudaStreamWaitEvent(x.s, start, 0), "wait start");
+        issue(steps, 0);
+        for (auto& x : ctx) {
+            cuda_ok(cudaEventRecord(x.done, x.s), "record done");
+            cuda_ok(cudaStreamWaitEvent(ctrl, x.done, 0), "wait done");
+        }
+        cuda_ok(cudaEventRecord(stop, ctrl), "record stop");
+        cuda_ok(cudaStreamSynchronize(ctrl), "sync");
+        float ms = 0.f;
+        if (status == B2_OK && cuda_ok(cudaEventElapsedTime(&ms, start, stop), "elapsed")) *elapsed_ms = ms;
+        if (launches_per_step) *launches_per_step = b2_context_nb_launches(ctx[0].c, batch);
+    }
+    cudaDeviceSynchronize();
+    for (auto& x : ctx) {
+        if (x.c) b2_context_destroy(x.c);
+        if (x.scratch) cudaFree(x.scratch);
+        for (int i = 0; i < nb && i < int(x.bind.size()); ++i)
+            if (i != in_id && x.bind[i]) cudaFree(x.bind[i]);
+        if (x.s) cudaStreamDestroy(x.s);
+        if (x.done) cudaEventDestroy(x.done);
+    }
+    for (void* p : ring)
+        if (p) cudaFree(p);
+    if (ctrl) cudaStreamDestroy(ctrl);
+    if (start) cudaEventDestroy(start);
+    if (stop) cudaEventDestroy(stop);
+    b2_engine_destroy(eng);
+    b2_runtime_destroy(rt);
+    return status;
+}
+
+}  // extern "C"

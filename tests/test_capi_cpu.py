@@ -1,0 +1,121 @@
+"""CPU: the C-ABI library loads, exports every symbol the headers declare, and validates plans.
+No compute entry point is exercised here (there is no CPU fallback to exercise)."""
+import ctypes as C
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from tensorrt_laboratory_b200 import builder, capi, graph, weights
+from tests import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    for hdr in ("b200infer.h", "b200cuda.h", "trtlab_host.h"):
+        with open(os.path.join(ROOT, "include", hdr)) as f:
+            text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+        names |= set(re.findall(r"\b((?:b2|trt)_[a-z0-9_]+)\s*\(", text))
+    return names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = _declared_symbols()
+    assert len(declared) > 55
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    bound = {n for n, _, _ in capi.SYMBOLS}
+    assert declared == bound, (declared - bound, bound - declared)
+    assert lib.b2_abi_version() == 1
+
+
+def _small_plan(precision):
+    _, _, low = helpers.conv_case(3, 16, 16, 64, 3, 1, 1)
+    return builder.build_plan(low, precision, max_batch=4)
+
+
+def test_plan_roundtrip_metadata(lib):
+    blob = builder.build_resnet_plan(50, builder.PREC_FP16, 8)
+    eng = capi.Engine(blob, inspect_only=True)
+    assert eng.name == "ResNet-50" and eng.max_batch == 8 and eng.precision == builder.PREC_FP16
+    assert [(b["name"], b["is_input"], b["shape"]) for b in eng.bindings] == [("data", True, (3, 224, 224)), ("prob", False, (1000,))]
+    assert eng.bindings[0]["item_bytes"] * 8 == 4816896 and eng.bindings[1]["item_bytes"] * 8 == 32000
+    assert abs(eng.flops(8) - 61.73e9) < 1e7
+    assert 50e6 < eng.weights_size < 52e6  # ~51.0 MB of fp16 weights
+    assert 20e6 < eng.device_memory_size < 60e6
+    assert lib.b2_engine_nb_layers(eng.handle) == 58  # input cast + 57 fused ops
+    assert lib.b2_engine_binding_index(eng.handle, b"prob") == 1 and lib.b2_engine_binding_index(eng.handle, b"nope") == -1
+    eng.destroy()
+
+
+def test_fp32_plan_is_twice_the_size(lib):
+    a = capi.Engine(_small_plan(builder.PREC_FP16), inspect_only=True)
+    b = capi.Engine(_small_plan(builder.PREC_FP32), inspect_only=True)
+    assert a.bindings == b.bindings
+    assert b.precision == builder.PREC_FP32
+    a.destroy(), b.destroy()
+
+
+def test_malformed_plans_are_rejected(lib):
+    blob = bytearray(_small_plan(builder.PREC_FP16))
+    for mutate in (lambda b: b.__setitem__(slice(0, 8), b"NOTAPLAN"),
+                   lambda b: b.__setitem__(slice(8, 12), struct.pack("<I", 99)),
+                   lambda b: b.__delitem__(slice(len(b) - 100, len(b))),
+                   lambda b: b.__setitem__(slice(16, 20), struct.pack("<I", 0))):
+        bad = bytearray(blob)
+        mutate(bad)
+        with pytest.raises(capi.B2Error) as ei:
+            capi.Engine(bytes(bad), inspect_only=True)
+        assert ei.value.code == 1
+    with pytest.raises(capi.B2Error):
+        capi.Engine(b"short", inspect_only=True)
+
+
+def test_inspect_only_engine_cannot_execute(lib):
+    eng = capi.Engine(_small_plan(builder.PREC_FP16), inspect_only=True)
+    ctx = C.c_void_p()
+    assert lib.b2_context_create(eng.handle, C.byref(ctx)) == 5  # B2_ESTATE
+    eng.destroy()
+
+
+def test_no_device_means_loud_failure_not_fallback(lib):
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is visible here")
+    with pytest.raises(capi.B2Error) as ei:
+        capi.Engine(_small_plan(builder.PREC_FP16))
+    assert ei.value.code == 2 and "no CPU fallback" in str(ei.value)
+
+
+def test_builder_layouts():
+    net, wts, low = helpers.conv_case(3, 8, 8, 64, 7, 2, 3)
+    blob = builder.build_plan(low, builder.PREC_FP16, 2)
+    hdr = struct.unpack_from("<8sIIIIIIQQ", blob, 0)
+    assert hdr[0] == b"B2ENGINE" and hdr[2] == builder.PREC_FP16 and hdr[3] == 2
+    n_t, n_o, n_b = hdr[4], hdr[5], hdr[6]
+    assert (n_t, n_o, n_b) == (2, 3, 2)  # data, conv | cast, conv, cast | data, conv
+    op_off = 128 + n_t * 96 + 176  # second op record = the conv
+    rec = struct.unpack_from("<64sIiiiiIIIIIIIIIIIQQQQ", blob, op_off)
+    assert rec[1] == builder.OP_CONV
+    k, cin, cout, cin_p, cout_p, taps, taps_p = rec[6], rec[11], rec[12], rec[13], rec[14], rec[15], rec[16]
+    assert (k, cin, cout, cin_p, cout_p, taps, taps_p) == (7, 3, 64, 8, 64, 49, 50)  # C padded to 8, taps to even
+    w_off, w_bytes = rec[17], rec[18]
+    assert w_bytes == 64 * 50 * 8 * 2
+    payload = hdr[7]
+    W = np.frombuffer(blob, np.float16, 64 * 50 * 8, payload + w_off).reshape(64, 50, 8)
+    assert np.all(W[:, 49, :] == 0) and np.all(W[:, :, 3:] == 0)
+    np.testing.assert_array_equal(W[:, :49, :3], low["ops"][0]["W"].reshape(64, 49, 3).astype(np.float16))
+    assert builder.phys_channels(3, builder.PREC_FP16) == 8 and builder.phys_channels(1000, builder.PREC_FP16) == 1024
+    assert builder.phys_channels(3, builder.PREC_FP32) == 3
+
+
+def test_cpp_core_unit_tests(tmp_path):
+    exe = tmp_path / "test_core"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "test_core.cc"), "-o", str(exe), "-lpthread"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "ALL OK" in out.stdout, out.stderr

@@ -1,0 +1,85 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution, one layer at a time, THROUGH THE C ABI
+(single-conv plans: b2_engine_deserialize -> b2_context_enqueue), against the CPU oracle that emulates
+the engine's fp16 rounding points.  Bit-level agreement is not expected (fp32 accumulation order differs
+between the tensor core and the oracle); the bar is 2 fp16 ulp of the tensor's max magnitude."""
+import numpy as np
+import pytest
+
+from oracle.caffe_forward import lowered_forward_f16emu
+from tensorrt_laboratory_b200 import builder
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2.0 ** -9  # 2 ulp of fp16 at the top binade, relative to max|ref|
+
+# the 20 unique ResNet-50 convolution shapes (Cin, H_in, Cout, k, stride) -- SURVEY.md 8(d)
+RN50_CONVS = [
+    (3, 224, 64, 7, 2), (64, 56, 64, 1, 1), (64, 56, 64, 3, 1), (64, 56, 256, 1, 1), (256, 56, 64, 1, 1),
+    (256, 56, 128, 1, 2), (256, 56, 512, 1, 2), (128, 28, 128, 3, 1), (128, 28, 512, 1, 1), (512, 28, 128, 1, 1),
+    (512, 28, 256, 1, 2), (512, 28, 1024, 1, 2), (256, 14, 256, 3, 1), (256, 14, 1024, 1, 1), (1024, 14, 256, 1, 1),
+    (1024, 14, 512, 1, 2), (1024, 14, 2048, 1, 2), (512, 7, 512, 3, 1), (512, 7, 2048, 1, 1), (2048, 7, 512, 1, 1),
+]
+
+
+def _check(cin, h, cout, k, stride, batch, relu=True, residual=False, options=None, seed=0):
+    pad = {1: 0, 3: 1, 7: 3}[k]
+    net, wts, low = helpers.conv_case(cin, h, h, cout, k, stride, pad, relu=relu, residual=residual, seed=seed)
+    x = np.random.default_rng(seed + 1).standard_normal((batch, cin, h, h), dtype=np.float32)
+    ref = lowered_forward_f16emu(low, x)
+    out = helpers.run_engine(low, x, builder.PREC_FP16, options)
+    got = list(out.values())[0].reshape(batch, -1)
+    assert got.shape == ref.shape
+    assert np.isfinite(got).all()
+    err = helpers.rel_err(got, ref)
+    assert err <= TOL, f"rel err {err:.3e} > {TOL:.3e}"
+    return got
+
+
+@pytest.mark.parametrize("cin,h,cout,k,stride", RN50_CONVS)
+def test_resnet50_conv_shapes(gpu, cin, h, cout, k, stride):
+    _check(cin, h, cout, k, stride, batch=2)
+
+
+@pytest.mark.parametrize("cin,h,cout,k,stride", [(64, 56, 256, 1, 1), (128, 28, 512, 1, 1), (512, 7, 2048, 1, 1), (64, 56, 64, 3, 1)])
+def test_fused_residual_and_relu(gpu, cin, h, cout, k, stride):
+    _check(cin, h, cout, k, stride, batch=2, relu=True, residual=True)
+
+
+def test_no_relu_keeps_negative_values(gpu):
+    got = _check(64, 28, 64, 1, 1, batch=1, relu=False)
+    assert (got < 0).any()
+
+
+@pytest.mark.parametrize("bn", [32, 64, 128, 256])
+def test_every_n_tile(gpu, bn):
+    _check(64, 28, 256, 1, 1, batch=2, options={"bn": bn})
+    _check(3, 64, 256, 7, 2, batch=1, options={"bn": bn})  # un-swizzled 8-channel K path
+
+
+def test_im2col_tma_equals_tiled_tma_on_pointwise(gpu):
+    a = _check(256, 28, 128, 1, 1, batch=2, options={"im2col": 0})
+    b = _check(256, 28, 128, 1, 1, batch=2, options={"im2col": 1})
+    np.testing.assert_array_equal(a, b)  # same MMA order -> bit identical
+
+
+@pytest.mark.parametrize("batch,h", [(1, 7), (3, 7), (1, 14), (5, 28), (8, 7)])
+def test_ragged_m_tails(gpu, batch, h):
+    # M = batch*h*h is not a multiple of the 128-row tile: TMA zero-fills, the epilogue predicates stores
+    _check(512 if h == 7 else 128, h, 512 if h == 7 else 128, 3, 1, batch=batch)
+
+
+def test_tcgen05_agrees_with_simt_kernel(gpu):
+    a = _check(128, 28, 128, 3, 1, batch=2, options={"simt": 0})
+    b = _check(128, 28, 128, 3, 1, batch=2, options={"simt": 1})
+    assert helpers.rel_err(a, b) <= TOL
+
+
+def test_fp32_engine_conv_matches_fp32_oracle(gpu):
+    import torch
+    from oracle.caffe_forward import caffe_forward
+    net, wts, low = helpers.conv_case(16, 20, 20, 24, 3, 2, 1, relu=True, residual=False)
+    x = np.random.default_rng(3).standard_normal((3, 16, 20, 20), dtype=np.float32)
+    ref = caffe_forward(net, wts, x, dtype=torch.float64)
+    got = list(helpers.run_engine(low, x, builder.PREC_FP32).values())[0].reshape(3, -1)
+    assert helpers.rel_err(got, ref) < 1e-6

@@ -22,6 +22,7 @@ CASES = {
     "c3x3_tail": (512, 7, 7, 512, 3, 1, 1, True, False, 1, {}),
     "c7x7_stem": (3, 224, 224, 64, 7, 2, 3, True, False, 2, {}),
     "c1x1_bn32": (64, 56, 56, 64, 1, 1, 0, True, False, 2, {"bn": 32}),
+    "c1x1_bn64": (64, 56, 56, 64, 1, 1, 0, True, False, 2, {"bn": 64}),
     "c1x1_bn128": (64, 56, 56, 256, 1, 1, 0, False, False, 2, {"bn": 128}),
     "c1x1_bn256": (64, 56, 56, 256, 1, 1, 0, False, False, 2, {"bn": 256}),
     "c1x1_simt": (64, 56, 56, 64, 1, 1, 0, True, False, 2, {"simt": 1}),
