@@ -214,6 +214,11 @@ class Buffers : public std::enable_shared_from_this<Buffers> {
 
   private:
     cudaStream_t m_Stream;
+    // The pool hands this object out through a SECOND shared_ptr (own control block, return-to-pool
+    // deleter; core/pool.h:193-203), so shared_from_this() would not keep the lease alive.  GetBuffers()
+    // records the lease here and CreateBindings() gives it to the Bindings, which is what makes
+    // "a Bindings keeps its Buffers checked out" (bindings.h:107-108) actually hold.
+    std::weak_ptr<Buffers> m_Lease;
     friend class InferenceManager;
 };
 

@@ -201,7 +201,9 @@ Buffers::~Buffers() {  // buffers.cc:48-53
 }
 
 auto Buffers::CreateBindings(const std::shared_ptr<Model>& model) -> std::shared_ptr<Bindings> {  // buffers.cc:55-60
-    auto bindings = std::shared_ptr<Bindings>(new Bindings(model, shared_from_this()));
+    auto self = m_Lease.lock();  // the pooled lease when we came from InferenceManager::GetBuffers()
+    if (!self) self = shared_from_this();
+    auto bindings = std::shared_ptr<Bindings>(new Bindings(model, self));
     ConfigureBindings(model, bindings);
     return bindings;
 }
@@ -397,7 +399,12 @@ auto InferenceManager::GetModel(std::string model_name) -> std::shared_ptr<Model
 
 auto InferenceManager::GetBuffers() -> std::shared_ptr<Buffers> {  // inference_manager.cc:232-239
     TRTLAB_CHECK(m_Buffers) << "Call AllocateResources() before trying to acquire a Buffers object.";
-    return m_Buffers->Pop([](Buffers* ptr) { ptr->Reset(); });
+    auto lease = m_Buffers->Pop([](Buffers* ptr) {
+        ptr->m_Lease.reset();
+        ptr->Reset();
+    });
+    lease->m_Lease = lease;
+    return lease;
 }
 
 auto InferenceManager::GetExecutionContext(const Model* model) -> std::shared_ptr<ExecutionContext> {
