@@ -105,7 +105,9 @@ int b2_context_enqueue(b2_context* c, int batch, void* const* bindings, b2_strea
 /* number of kernels one enqueue at `batch` launches (for reporting) */
 int b2_context_nb_launches(b2_context* c, int batch);
 /* knobs: "graph"=0/1 replay the forward as a cached CUDA graph (default 1); "simt"=0/1 force the
- * SIMT reference kernels instead of the tcgen05 path (debug); returns B2_EINVAL for unknown keys */
+ * SIMT reference kernels instead of the tcgen05 path (debug); "bn"/"stages"/"splits" force the conv tile,
+ * pipeline depth and split-K factor (0 = cost model); "pdl"=0/1 programmatic dependent launch (process-wide);
+ * "pdl_trigger"=0/1 release point of the dependent kernel; returns B2_EINVAL for unknown keys */
 int b2_context_set_option(b2_context* c, const char* key, int value);
 
 /* per-layer device timing of one forward (serialised launches, CUDA events): fills up to `cap`

@@ -83,6 +83,8 @@ int load_driver_entry_points() {
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr size_t kSplitWorkspaceBytes = 12u << 20;  // bounds tiles*splits*128*BN*4 (see pick_conv_config)
+constexpr int kMaxSplitTiles = 4096;                 // tile counters per context
 
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -155,6 +157,7 @@ struct b2_engine {
     uint8_t* d_payload = nullptr;
     size_t payload_bytes = 0;
     size_t arena_bytes = 0;
+    size_t act_bytes = 0;
     int device = -1;
     bool inspect_only = false;
     double flops_per_item = 0;
@@ -164,17 +167,28 @@ struct b2_engine {
 struct b2_context {
     b2_engine* e = nullptr;
     uint8_t* scratch = nullptr;
-    std::map<int, std::unique_ptr<Plan>> plans;
     struct GraphKey {
         int batch;
         std::vector<void*> ptrs;
         bool operator<(const GraphKey& o) const { return batch != o.batch ? batch < o.batch : ptrs < o.ptrs; }
     };
-    std::map<GraphKey, cudaGraphExec_t> graphs;
+    // Launch plans (TMA maps embed arena addresses) and captured graphs are cached PER SCRATCH pointer: the
+    // reference pairs a pooled IExecutionContext with whichever pooled activation block the request drew
+    // (inference_manager.cc:254-273), so the same context sees several scratch pointers over its life.
+    struct ScratchState {
+        std::map<int, std::unique_ptr<Plan>> plans;
+        std::map<GraphKey, cudaGraphExec_t> graphs;
+    };
+    std::map<uint8_t*, ScratchState> states;
+    ScratchState* cur = nullptr;
+    int* d_counters = nullptr;  // split-K tile arrival counters (always zero between launches)
     int use_graph = 1;
     int force_simt = 0;
     int force_im2col = 0;
     int force_bn = 0;
+    int force_stages = 0;
+    int force_splits = 0;
+    int pdl_trigger = 1;
 };
 
 namespace {
@@ -318,7 +332,9 @@ void plan_arena(b2_engine* e) {
         live.push_back({off, size, t.last_use});
         top = std::max(top, off + size);
     }
-    e->arena_bytes = align_up(std::max<size_t>(top, 1024), 1024);
+    e->act_bytes = align_up(std::max<size_t>(top, 1024), 1024);
+    // fp16 engines reserve a fixed split-K workspace behind the activations (partial fp32 tiles)
+    e->arena_bytes = e->act_bytes + (e->half() ? kSplitWorkspaceBytes : 0);
 }
 
 // ---- tensor maps ------------------------------------------------------------------------------
@@ -358,25 +374,65 @@ int make_map_im2col(CUtensorMap* map, const void* base, int C, int W, int H, int
     return B2_OK;
 }
 
-int pick_bn(int m_tiles, int cout_phys, int forced) {
-    const int cands[4] = {256, 128, 64, 32};
-    if (forced && cout_phys % forced == 0) return forced;
-    for (int bn : cands)
-        if (cout_phys % bn == 0 && m_tiles * (cout_phys / bn) >= 148) return bn;
-    for (int i = 3; i >= 0; --i)
-        if (cout_phys % cands[i] == 0) return cands[i];
-    return 0;
+struct ConvConfig {
+    int bn, stages, splits;
+    double est_us;
+};
+
+// Analytic cost model (microseconds) over the instantiated (N tile, pipeline depth, split-K) space.  The
+// constants are rough B200 figures: ~70 KB/us of L2->SM bandwidth per SM, ~1 us TMA round trip, ~5 TB/s of
+// aggregate L2 bandwidth, ~2 us of fixed per-CTA cost.  It only has to rank configurations sensibly.
+ConvConfig pick_conv_config(int M, int cout_phys, int kblocks, int kb, bool residual, const b2_context* c) {
+    const int m_tiles = (M + 127) / 128;
+    ConvConfig best{0, 0, 1, 1e30};
+    const int bns[3] = {128, 64, 32};
+    const int stgs[4] = {1, 2, 4, 8};
+    for (int bn : bns) {
+        if (cout_phys % bn) continue;
+        if (c->force_bn && bn != c->force_bn) continue;
+        const int tiles = m_tiles * (cout_phys / bn);
+        for (int splits = 1; splits <= 8; ++splits) {
+            if (c->force_splits && splits != c->force_splits) continue;
+            if (splits > 1 && (kb != 64 || kblocks / splits < 4 || tiles * splits > 160 || tiles > kMaxSplitTiles ||
+                               size_t(tiles) * splits * 128 * bn * 4 > kSplitWorkspaceBytes))
+                continue;
+            const int kpc = (kblocks + splits - 1) / splits;
+            if (splits > 1 && (splits - 1) * kpc >= kblocks) continue;  // an empty split
+            for (int st : stgs) {
+                if (!b2k::conv_config_exists(bn, kb, st)) continue;
+                if (c->force_stages && st != c->force_stages) continue;
+                if (!c->force_stages && st > 1 && st / 2 >= kpc) continue;  // deeper than the loop is long
+                const double smem = b2k::conv_smem_bytes(bn, st);
+                int per_sm = int(227.0 * 1024 / smem);
+                per_sm = std::min(per_sm, 512 / std::max(32, bn));
+                per_sm = std::max(1, std::min(per_sm, 8));
+                const int ctas = tiles * splits;
+                const int waves = (ctas + 148 * per_sm - 1) / (148 * per_sm);
+                const int sharing = std::max(1, std::min(per_sm, (ctas + 147) / 148));
+                const double stage_bytes = 16384.0 + bn * 128.0;
+                const double t_kb = std::max(stage_bytes / (70000.0 / sharing), 1.0 / st);
+                double t_epi = 0.6 + bn / 64.0 * 0.4 + (residual ? 0.4 : 0.0);
+                if (splits > 1) t_epi += 1.0 + 0.3 * splits;
+                const double t_cta = 2.0 + kpc * t_kb + t_epi;
+                double total = waves * t_cta;
+                const double traffic = double(ctas) * kpc * stage_bytes;
+                total = std::max(total, traffic / 5.0e6 + 2.0);
+                if (total < best.est_us) best = ConvConfig{bn, st, splits, total};
+            }
+        }
+    }
+    return best;
 }
 
 // ---- per-batch launch plan ---------------------------------------------------------------------
 int build_plan(b2_context* c, int batch, Plan** out) {
     b2_engine* e = c->e;
-    auto it = c->plans.find(batch);
-    if (it != c->plans.end()) {
+    if (!c->scratch || !c->cur) return fail(B2_ESTATE, "b2_context_set_device_memory has not been called");
+    auto it = c->cur->plans.find(batch);
+    if (it != c->cur->plans.end()) {
         *out = it->second.get();
         return B2_OK;
     }
-    if (!c->scratch) return fail(B2_ESTATE, "b2_context_set_device_memory has not been called");
     if (load_driver_entry_points() != 0) return fail(B2_ECUDA, "cuTensorMapEncode* driver entry points unavailable");
     auto plan = std::make_unique<Plan>();
     plan->batch = batch;
@@ -428,9 +484,20 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                     memset(&cl, 0, sizeof cl);
                     cl.kb = kb64 ? 64 : 8;
                     cl.grid_m = (M + 127) / 128;
-                    cl.bn = pick_bn(cl.grid_m, int(r.cout_phys), c->force_bn);
+                    const int nkb = kb64 ? int(r.taps) * (int(r.cin_phys) / 64) : (int(r.taps_phys) + 7) / 8;
+                    const ConvConfig cfg = pick_conv_config(M, int(r.cout_phys), nkb, cl.kb, r.res >= 0, c);
+                    if (cfg.bn == 0)
+                        return fail(B2_EINVAL, "conv %s: no kernel configuration (bn=%d stages=%d splits=%d forced)",
+                                    op.name.c_str(), c->force_bn, c->force_stages, c->force_splits);
+                    cl.bn = cfg.bn;
+                    cl.stages = cfg.stages;
                     cl.grid_n = int(r.cout_phys) / cl.bn;
                     b2k::ConvArgs& a = cl.args;
+                    a.splits = cfg.splits;
+                    a.kb_per_split = (nkb + cfg.splits - 1) / cfg.splits;
+                    a.workspace = reinterpret_cast<float*>(c->scratch + e->act_bytes);
+                    a.tile_counters = c->d_counters;
+                    a.pdl_trigger = c->pdl_trigger;
                     a.bias = bias;
                     a.residual = r.res >= 0 ? reinterpret_cast<const __half*>(tptr(r.res)) : nullptr;
                     a.out = reinterpret_cast<__half*>(tptr(r.out));
@@ -446,7 +513,6 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                     a.stride = int(r.stride);
                     a.pad = int(r.pad_);
                     a.relu = int(r.relu);
-                    a.split_k = 1;
                     const bool tiled = r.k == 1 && r.stride == 1 && r.pad_ == 0 && kb64 && !c->force_im2col;
                     a.a_mode = tiled ? b2k::A_TILED : b2k::A_IM2COL;
                     const CUtensorMapSwizzle swz = kb64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
@@ -525,7 +591,7 @@ int build_plan(b2_context* c, int batch, Plan** out) {
         plan->launches.push_back(std::move(L));
     }
     *out = plan.get();
-    c->plans[batch] = std::move(plan);
+    c->cur->plans[batch] = std::move(plan);
     return B2_OK;
 }
 
@@ -696,27 +762,41 @@ int b2_context_create(b2_engine* e, b2_context** out) {
     c->force_simt = env_int("B2_FORCE_SIMT", 0);
     c->force_im2col = env_int("B2_FORCE_IM2COL", 0);
     c->force_bn = env_int("B2_FORCE_BN", 0);
+    c->force_stages = env_int("B2_FORCE_STAGES", 0);
+    c->force_splits = env_int("B2_FORCE_SPLITS", 0);
+    c->pdl_trigger = env_int("B2_PDL_TRIGGER", 1);
+    if (getenv("B2_PDL")) b2k::set_pdl(env_int("B2_PDL", 1) != 0);
+    void* p = nullptr;
+    if (cudaMalloc(&p, kMaxSplitTiles * sizeof(int)) != cudaSuccess || cudaMemset(p, 0, kMaxSplitTiles * sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        return fail(B2_ENOMEM, "cudaMalloc for split-K counters failed");
+    }
+    c->d_counters = static_cast<int*>(p);
     *out = c;
     return B2_OK;
 }
 
 static void drop_cached(b2_context* c) {
-    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
-    c->graphs.clear();
-    c->plans.clear();
+    for (auto& st : c->states)
+        for (auto& kv : st.second.graphs) cudaGraphExecDestroy(kv.second);
+    c->states.clear();
+    c->cur = c->scratch ? &c->states[c->scratch] : nullptr;
 }
 
 void b2_context_destroy(b2_context* c) {
     if (!c) return;
     drop_cached(c);
+    if (c->d_counters) cudaFree(c->d_counters);
     delete c;
 }
 
 int b2_context_set_device_memory(b2_context* c, void* scratch) {
     if (!c || !scratch) return fail(B2_EINVAL, "null context or scratch");
     if (reinterpret_cast<uintptr_t>(scratch) % 256 != 0) return fail(B2_EINVAL, "scratch must be 256-byte aligned (cudaMalloc alignment)");
-    if (c->scratch != scratch) drop_cached(c);
+    if (c->states.size() >= 32 && c->states.find(static_cast<uint8_t*>(scratch)) == c->states.end()) drop_cached(c);
     c->scratch = static_cast<uint8_t*>(scratch);
+    c->cur = &c->states[c->scratch];
     return B2_OK;
 }
 
@@ -727,9 +807,15 @@ int b2_context_set_option(b2_context* c, const char* key, int value) {
         c->use_graph = value;
         return B2_OK;
     }
-    if (k == "simt") c->force_simt = value;
+    if (k == "pdl") {
+        b2k::set_pdl(value != 0);  // process-wide
+        value = 0;
+    } else if (k == "simt") c->force_simt = value;
     else if (k == "im2col") c->force_im2col = value;
     else if (k == "bn") c->force_bn = value;
+    else if (k == "stages") c->force_stages = value;
+    else if (k == "splits") c->force_splits = value;
+    else if (k == "pdl_trigger") c->pdl_trigger = value;
     else return fail(B2_EINVAL, "unknown option '%s'", key);
     drop_cached(c);
     return B2_OK;
@@ -756,11 +842,12 @@ int b2_context_enqueue(b2_context* c, int batch, void* const* bindings, b2_strea
         b2_context::GraphKey key;
         key.batch = batch;
         key.ptrs.assign(bindings, bindings + c->e->bindings.size());
-        auto it = c->graphs.find(key);
-        if (it == c->graphs.end()) {
-            if (c->graphs.size() >= 256) {  // bound the cache; callers normally cycle through a small Buffers pool
-                for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
-                c->graphs.clear();
+        auto& graphs = c->cur->graphs;
+        auto it = graphs.find(key);
+        if (it == graphs.end()) {
+            if (graphs.size() >= 256) {  // bound the cache; callers normally cycle through a small Buffers pool
+                for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+                graphs.clear();
             }
             cudaGraph_t graph = nullptr;
             B2_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
@@ -775,7 +862,7 @@ int b2_context_enqueue(b2_context* c, int batch, void* const* bindings, b2_strea
             ce = cudaGraphInstantiate(&exec, graph, 0);
             cudaGraphDestroy(graph);
             if (ce != cudaSuccess) return fail(B2_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
-            it = c->graphs.emplace(std::move(key), exec).first;
+            it = graphs.emplace(std::move(key), exec).first;
         }
         B2_CUDA(cudaGraphLaunch(it->second, stream));
     }
@@ -823,8 +910,9 @@ const char* b2_context_launch_name(b2_context* c, int batch, int i) {
     s = std::string(kinds[L->kind]) + ":" + L->name;
     if (L->kind == L_CONV_TC)
         s += " bn=" + std::to_string(L->conv.bn) + " kb=" + std::to_string(L->conv.kb) +
-             (L->conv.args.a_mode == b2k::A_TILED ? " tiled" : " im2col") + " grid=" + std::to_string(L->conv.grid_n) +
-             "x" + std::to_string(L->conv.grid_m) + " kblk=" + std::to_string(L->conv.args.num_kblocks);
+             " st=" + std::to_string(L->conv.stages) + (L->conv.args.a_mode == b2k::A_TILED ? " tiled" : " im2col") +
+             " grid=" + std::to_string(L->conv.grid_n) + "x" + std::to_string(L->conv.grid_m) + "x" +
+             std::to_string(L->conv.args.splits) + " kblk=" + std::to_string(L->conv.args.num_kblocks);
     return s.c_str();
 }
 double b2_context_launch_flops(b2_context* c, int batch, int i) {

@@ -12,6 +12,7 @@
 #include "kernels.h"
 
 #include <stdio.h>
+#include <string.h>
 
 namespace b2k {
 
@@ -150,42 +151,68 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
 }
 
 // =================================================================================================
-// conv_f16_tcgen05
+// conv_f16_tcgen05  (v2: per-layer pipeline depth, split-K, weight prefetch ahead of the PDL wait,
+//                    bias in smem, residual prefetched into registers, 32/64-column TMEM loads)
 // =================================================================================================
-template <int BN>
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// Programmatic dependent launch: the next kernel in the stream may begin its prologue while this one
+// drains; it must not touch data written by its predecessor before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <int BN, int STAGES>
 struct ConvCfg {
-    static constexpr int STAGES = (BN == 128) ? 3 : 4;
     static constexpr int A_STAGE = 128 * 64 * 2;  // 16 KiB: 128 rows x 64 K-elements
     static constexpr int B_STAGE = BN * 64 * 2;
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-    static constexpr int SMEM = STAGES * (A_STAGE + B_STAGE) + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int BAR_OFF = STAGES * (A_STAGE + B_STAGE);
+    static constexpr int BIAS_OFF = BAR_OFF + 256;
+    static constexpr int SMEM = BIAS_OFF + BN * 4 + 1024 /*alignment slack*/;
 };
 
-template <int BN, int KB>
+template <int BN, int KB, int STAGES>
 __global__ void __launch_bounds__(128)
 conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const ConvArgs p) {
-    using Cfg = ConvCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
+    using Cfg = ConvCfg<BN, STAGES>;
     constexpr int TPS = 64 / KB;            // TMA sub-tiles (filter taps) per stage; 1 when KB == 64
     constexpr int A_SUB = 128 * KB * 2;     // bytes of one A sub-tile
     constexpr int B_SUB = BN * KB * 2;
+    constexpr int NG = BN / 32;             // 32-column groups of the accumulator
     constexpr uint32_t IDESC = make_idesc_f16(128, BN);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * Cfg::A_STAGE;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_STAGE + Cfg::B_STAGE));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* accum_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint32_t* last_flag = tmem_slot + 1;
+    float* s_bias = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN;
     const int m0 = blockIdx.y * 128;
+    const int kb_begin = blockIdx.z * p.kb_per_split;
+    const int kb_end = min(p.num_kblocks, kb_begin + p.kb_per_split);
+    const int nk = kb_end - kb_begin;
 
+    // ---------------- prologue: nothing here depends on the previous kernel's output ----------------
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
@@ -198,10 +225,30 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         fence_proxy_async();
     }
     if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == 3)
+        for (int i = lane; i < BN; i += 32) s_bias[i] = __ldg(p.bias + n0 + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (p.pdl_trigger == 0) pdl_launch_dependents();
+
+    auto stage_bytes = [&](int kb) -> uint32_t {
+        if (KB == 64) return Cfg::A_STAGE + Cfg::B_STAGE;
+        int ntaps = p.taps_phys - kb * TPS;
+        ntaps = ntaps > TPS ? TPS : ntaps;
+        return static_cast<uint32_t>(ntaps * (A_SUB + B_SUB));
+    };
+    auto load_b = [&](int kb, int s) {  // weights: constant data, legal before pdl_wait()
+        uint8_t* b_dst = sB + s * Cfg::B_STAGE;
+        if (KB == 64) {
+            tma_load_2d(&mapB, &full_bar[s], b_dst, kb * 64, n0);
+        } else {
+            int ntaps = p.taps_phys - kb * TPS;
+            ntaps = ntaps > TPS ? TPS : ntaps;
+            for (int t = 0; t < ntaps; ++t) tma_load_2d(&mapB, &full_bar[s], b_dst + t * B_SUB, (kb * TPS + t) * KB, n0);
+        }
+    };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -215,14 +262,9 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
             const int base_w = q0 * p.stride - p.pad;
             const int base_h = p0 * p.stride - p.pad;
-            for (int kb = 0; kb < p.num_kblocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
+            auto load_a = [&](int kb, int s) {
                 uint8_t* a_dst = sA + s * Cfg::A_STAGE;
-                uint8_t* b_dst = sB + s * Cfg::B_STAGE;
                 if (KB == 64) {
-                    mbar_expect_tx(&full_bar[s], Cfg::A_STAGE + Cfg::B_STAGE);
                     const int tap = kb / p.cblocks;
                     const int cb = kb - tap * p.cblocks;
                     if (p.a_mode == A_TILED) {
@@ -233,11 +275,9 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         tma_load_im2col_4d(&mapA, &full_bar[s], a_dst, cb * 64, base_w, base_h, img0,
                                            static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
                     }
-                    tma_load_2d(&mapB, &full_bar[s], b_dst, kb * 64, n0);
                 } else {
                     int ntaps = p.taps_phys - kb * TPS;
                     ntaps = ntaps > TPS ? TPS : ntaps;
-                    mbar_expect_tx(&full_bar[s], ntaps * (A_SUB + B_SUB));
                     for (int t = 0; t < ntaps; ++t) {
                         const int tap = kb * TPS + t;
                         const int tap_a = tap < p.taps ? tap : p.taps - 1;  // padded tap: weights are zero
@@ -245,18 +285,32 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         const int sx = tap_a - r * p.kw;
                         tma_load_im2col_4d(&mapA, &full_bar[s], a_dst + t * A_SUB, 0, base_w, base_h, img0,
                                            static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
-                        tma_load_2d(&mapB, &full_bar[s], b_dst + t * B_SUB, tap * KB, n0);
                     }
                 }
+            };
+            const int npre = nk < STAGES ? nk : STAGES;
+            for (int i = 0; i < npre; ++i) {  // first ring pass: weights fly while the previous kernel drains
+                mbar_expect_tx(&full_bar[i], stage_bytes(kb_begin + i));
+                load_b(kb_begin + i, i);
+            }
+            pdl_wait();
+            for (int i = 0; i < npre; ++i) load_a(kb_begin + i, i);
+            for (int i = npre; i < nk; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], stage_bytes(kb_begin + i));
+                load_a(kb_begin + i, s);
+                load_b(kb_begin + i, s);
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
             // ================= MMA issuer =================
-            for (int kb = 0; kb < p.num_kblocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + s * Cfg::A_STAGE);
@@ -266,15 +320,15 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     for (int j = 0; j < 4; ++j) {  // 4 x (K = 16) inside one 128-byte swizzle row
                         const uint64_t ad = make_smem_desc(a_addr + j * 32, 16, 1024, 2);
                         const uint64_t bd = make_smem_desc(b_addr + j * 32, 16, 1024, 2);
-                        umma_f16(tmem_base, ad, bd, IDESC, (kb > 0 || j > 0) ? 1u : 0u);
+                        umma_f16(tmem_base, ad, bd, IDESC, (i > 0 || j > 0) ? 1u : 0u);
                     }
                 } else {
-                    int ntaps = p.taps_phys - kb * TPS;
+                    int ntaps = p.taps_phys - (kb_begin + i) * TPS;
                     ntaps = ntaps > TPS ? TPS : ntaps;
                     for (int j = 0; j < ntaps / 2; ++j) {  // one K=16 step = two 8-channel taps
                         const uint64_t ad = make_smem_desc(a_addr + 2 * j * A_SUB, A_SUB, 128, 0);
                         const uint64_t bd = make_smem_desc(b_addr + 2 * j * B_SUB, B_SUB, 128, 0);
-                        umma_f16(tmem_base, ad, bd, IDESC, (kb > 0 || j > 0) ? 1u : 0u);
+                        umma_f16(tmem_base, ad, bd, IDESC, (i > 0 || j > 0) ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
@@ -285,55 +339,122 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
 
     // ================= epilogue: TMEM -> registers -> bias/residual/ReLU -> fp16 NHWC =================
+    pdl_wait();  // residual reads and every global write below depend on the previous kernel
+    const int row = warp * 32 + lane;
+    const int m = m0 + row;
+    const bool valid = m < p.M;
+    const size_t off = static_cast<size_t>(m) * p.Cout + n0;
+    const bool split = p.splits > 1;
+
+    // residual prefetch: the loads overlap the tail of the MMA pipeline
+    uint4 res[NG * 4];
+    const bool has_res = p.residual != nullptr;
+    if (has_res && valid && !split) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+        for (int i = 0; i < NG * 4; ++i) res[i] = __ldg(rp + i);
+    }
+
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    {
-        const int row = warp * 32 + lane;
-        const int m = m0 + row;
-        const bool valid = m < p.M;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-        const size_t off = static_cast<size_t>(m) * p.Cout + n0;
-        const float* bias = p.bias + n0;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + c, v);
-            tmem_wait_ld();
-            if (valid) {
-                float f[16];
+    if (p.pdl_trigger == 1) pdl_launch_dependents();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+
+    auto finish_group = [&](int g, float (&f)[32]) {  // bias + residual + relu + store for 32 columns
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = f[q * 8 + i] + s_bias[g * 32 + q * 8 + i];
+            if (has_res) {
+                const __half2* r2 = reinterpret_cast<const __half2*>(&res[g * 4 + q]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c) + i);
-                    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
-                    f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
-                    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
-                    f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+                    const float2 rf = __half22float2(r2[i]);
+                    v[2 * i] += rf.x;
+                    v[2 * i + 1] += rf.y;
                 }
-                if (p.residual != nullptr) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c);
+            }
+            if (p.relu) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint4 rv = __ldg(rp + h);
-                        const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+            }
+            uint4 o;
+            __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 rf = __half22float2(r2[i]);
-                            f[8 * h + 2 * i + 0] += rf.x;
-                            f[8 * h + 2 * i + 1] += rf.y;
+            for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            *reinterpret_cast<uint4*>(p.out + off + g * 32 + q * 8) = o;
+        }
+    };
+
+    if (!split) {
+        constexpr int GP = NG >= 2 ? 2 : 1;  // groups per TMEM round trip
+#pragma unroll
+        for (int g0 = 0; g0 < NG; g0 += GP) {
+            uint32_t acc[GP][32];
+#pragma unroll
+            for (int j = 0; j < GP; ++j) tmem_ld32(taddr + (g0 + j) * 32, acc[j]);
+            tmem_wait_ld();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < GP; ++j) {
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(acc[j][i]);
+                    finish_group(g0 + j, f);
+                }
+            }
+        }
+    } else {
+        // ---- split-K: publish the fp32 partial tile, the last CTA of the tile reduces IN FIXED ORDER ----
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+        float* ws_tile = p.workspace + static_cast<size_t>(tile) * p.splits * (128 * BN);
+        float* mine = ws_tile + static_cast<size_t>(blockIdx.z) * (128 * BN) + static_cast<size_t>(row) * BN;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            uint32_t acc[32];
+            tmem_ld32(taddr + g * 32, acc);
+            tmem_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                __stcg(reinterpret_cast<uint4*>(mine + g * 32) + q, make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int prev = atomicAdd(p.tile_counters + tile, 1);
+            const uint32_t last = (prev == p.splits - 1) ? 1u : 0u;
+            if (last) p.tile_counters[tile] = 0;  // re-arm for the next launch
+            *last_flag = last;
+        }
+        __syncthreads();
+        if (*last_flag) {
+            __threadfence();
+            if (has_res && valid) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+                for (int i = 0; i < NG * 4; ++i) res[i] = __ldg(rp + i);
+            }
+            if (valid) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = 0.f;
+                    for (int sp = 0; sp < p.splits; ++sp) {
+                        const float4* src = reinterpret_cast<const float4*>(ws_tile + static_cast<size_t>(sp) * (128 * BN) +
+                                                                            static_cast<size_t>(row) * BN + g * 32);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 t = __ldcg(src + q);
+                            f[4 * q] += t.x;
+                            f[4 * q + 1] += t.y;
+                            f[4 * q + 2] += t.z;
+                            f[4 * q + 3] += t.w;
                         }
                     }
+                    finish_group(g, f);
                 }
-                if (p.relu) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
-                }
-                uint4 o[2];
-                __half2* o2 = reinterpret_cast<__half2*>(o);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-                uint4* op = reinterpret_cast<uint4*>(p.out + off + c);
-                op[0] = o[0];
-                op[1] = o[1];
             }
         }
     }
@@ -342,55 +463,83 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, int KB>
+static bool g_use_pdl = true;
+void set_pdl(bool on) { g_use_pdl = on; }
+bool get_pdl() { return g_use_pdl; }
+
+template <typename Kern, typename... Args>
+static int launch_kernel(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && g_use_pdl) ? 1 : 0;
+    return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, args...));
+}
+
+template <int BN, int KB, int STAGES>
 static int launch_one(const ConvLaunch& L, cudaStream_t stream) {
-    dim3 grid(L.grid_n, L.grid_m, 1);
-    conv_f16_tcgen05<BN, KB><<<grid, 128, ConvCfg<BN>::SMEM, stream>>>(L.mapA, L.mapB, L.args);
-    return static_cast<int>(cudaGetLastError());
+    dim3 grid(L.grid_n, L.grid_m, L.args.splits);
+    return launch_kernel(conv_f16_tcgen05<BN, KB, STAGES>, grid, dim3(128), ConvCfg<BN, STAGES>::SMEM, stream, true, L.mapA,
+                         L.mapB, L.args);
 }
 
-template <int BN, int KB>
+template <int BN, int KB, int STAGES>
 static int init_one() {
-    return static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM));
+    return static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 ConvCfg<BN, STAGES>::SMEM));
 }
 
-bool conv_tile_supported(int bn, int kb) {
+int conv_smem_bytes(int bn, int stages) { return stages * (128 * 64 * 2 + bn * 64 * 2) + 256 + bn * 4 + 1024; }
+
+bool conv_tile_supported(int bn, int kb, int stages) {
     if (kb != 64 && kb != 8) return false;
-    return bn == 32 || bn == 64 || bn == 128 || bn == 256;
+    if (bn != 32 && bn != 64 && bn != 128) return false;
+    if (stages != 1 && stages != 2 && stages != 4 && stages != 8) return false;
+    return conv_smem_bytes(bn, stages) <= 227 * 1024 && !(bn == 128 && stages == 8);
 }
+
+#define B2_FOR_EACH_CONV(X) \
+    X(32, 64, 1) X(32, 64, 2) X(32, 64, 4) X(32, 64, 8) \
+    X(64, 64, 1) X(64, 64, 2) X(64, 64, 4) X(64, 64, 8) \
+    X(128, 64, 1) X(128, 64, 2) X(128, 64, 4) \
+    X(32, 8, 2) X(32, 8, 4) X(64, 8, 2) X(64, 8, 4) X(64, 8, 8) X(128, 8, 4)
 
 int init_conv_kernels() {
     int e = 0;
-    if ((e = init_one<32, 64>())) return e;
-    if ((e = init_one<64, 64>())) return e;
-    if ((e = init_one<128, 64>())) return e;
-    if ((e = init_one<256, 64>())) return e;
-    if ((e = init_one<32, 8>())) return e;
-    if ((e = init_one<64, 8>())) return e;
-    if ((e = init_one<128, 8>())) return e;
-    if ((e = init_one<256, 8>())) return e;
+#define B2_INIT(BN_, KB_, ST_) \
+    if ((e = init_one<BN_, KB_, ST_>())) return e;
+    B2_FOR_EACH_CONV(B2_INIT)
+#undef B2_INIT
     return 0;
 }
 
 int launch_conv_f16_tcgen05(const ConvLaunch& L, cudaStream_t stream) {
-#define B2_CASE(BN_, KB_) \
-    if (L.bn == BN_ && L.kb == KB_) return launch_one<BN_, KB_>(L, stream);
-    B2_CASE(32, 64)
-    B2_CASE(64, 64)
-    B2_CASE(128, 64)
-    B2_CASE(256, 64)
-    B2_CASE(32, 8)
-    B2_CASE(64, 8)
-    B2_CASE(128, 8)
-    B2_CASE(256, 8)
+#define B2_CASE(BN_, KB_, ST_) \
+    if (L.bn == BN_ && L.kb == KB_ && L.stages == ST_) return launch_one<BN_, KB_, ST_>(L, stream);
+    B2_FOR_EACH_CONV(B2_CASE)
 #undef B2_CASE
     return static_cast<int>(cudaErrorInvalidValue);
+}
+
+bool conv_config_exists(int bn, int kb, int stages) {
+#define B2_HAS(BN_, KB_, ST_) \
+    if (bn == BN_ && kb == KB_ && stages == ST_) return true;
+    B2_FOR_EACH_CONV(B2_HAS)
+#undef B2_HAS
+    return false;
 }
 
 // =================================================================================================
 // SIMT kernels
 // =================================================================================================
+static thread_local int B2_LAUNCH_RC = 0;
+
 template <typename T>
 struct Acc;
 template <>
@@ -413,6 +562,8 @@ __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_
 // direct convolution, one thread per output element (co fastest)
 template <typename T>
 __global__ void conv_simt_kernel(SimtConvArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     using acc_t = typename Acc<T>::type;
     const long long total = static_cast<long long>(a.N) * a.Ho * a.Wo * a.Cout_phys;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -455,10 +606,10 @@ int launch_conv_simt(const SimtConvArgs& a, bool half_storage, cudaStream_t stre
     const long long blocks = (total + threads - 1) / threads;
     if (blocks <= 0) return 0;
     if (half_storage)
-        conv_simt_kernel<__half><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(a);
+        B2_LAUNCH_RC = launch_kernel(conv_simt_kernel<__half>, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, stream, true, a);
     else
-        conv_simt_kernel<float><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(a);
-    return static_cast<int>(cudaGetLastError());
+        B2_LAUNCH_RC = launch_kernel(conv_simt_kernel<float>, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, stream, true, a);
+    return B2_LAUNCH_RC;
 }
 
 // fp32 NCHW -> NHWC (channel-padded).  One thread per pixel: reads are coalesced per channel plane,
@@ -466,6 +617,8 @@ int launch_conv_simt(const SimtConvArgs& a, bool half_storage, cudaStream_t stre
 template <typename T>
 __global__ void input_cast_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int HW,
                                   int C_phys) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * HW) return;
     const int n = static_cast<int>(idx / HW);
@@ -477,6 +630,8 @@ __global__ void input_cast_kernel(const float* __restrict__ src, T* __restrict__
 
 // specialisation used by the fp16 path when C_phys == 8: one 16-byte store per pixel
 __global__ void input_cast_c8_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int N, int C, int HW) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * HW) return;
     const int n = static_cast<int>(idx / HW);
@@ -498,17 +653,19 @@ int launch_input_cast(const float* src, void* dst, int N, int C, int H, int W, i
     const int threads = 256;
     const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
     if (half_storage && C_phys == 8 && C <= 8)
-        input_cast_c8_kernel<<<blocks, threads, 0, stream>>>(src, reinterpret_cast<uint4*>(dst), N, C, H * W);
+        B2_LAUNCH_RC = launch_kernel(input_cast_c8_kernel, dim3(blocks), dim3(threads), 0, stream, false, src, reinterpret_cast<uint4*>(dst), N, C, H * W);
     else if (half_storage)
-        input_cast_kernel<__half><<<blocks, threads, 0, stream>>>(src, reinterpret_cast<__half*>(dst), N, C, H * W, C_phys);
+        B2_LAUNCH_RC = launch_kernel(input_cast_kernel<__half>, dim3(blocks), dim3(threads), 0, stream, false, src, reinterpret_cast<__half*>(dst), N, C, H * W, C_phys);
     else
-        input_cast_kernel<float><<<blocks, threads, 0, stream>>>(src, reinterpret_cast<float*>(dst), N, C, H * W, C_phys);
-    return static_cast<int>(cudaGetLastError());
+        B2_LAUNCH_RC = launch_kernel(input_cast_kernel<float>, dim3(blocks), dim3(threads), 0, stream, false, src, reinterpret_cast<float*>(dst), N, C, H * W, C_phys);
+    return B2_LAUNCH_RC;
 }
 
 template <typename T>
 __global__ void output_cast_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int HW,
                                    int C_phys) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * C * HW) return;
     const int px = static_cast<int>(idx % HW);
@@ -524,16 +681,18 @@ int launch_output_cast(const void* src, float* dst, int N, int C, int H, int W, 
     const int threads = 256;
     const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
     if (half_storage)
-        output_cast_kernel<__half><<<blocks, threads, 0, stream>>>(reinterpret_cast<const __half*>(src), dst, N, C, H * W, C_phys);
+        B2_LAUNCH_RC = launch_kernel(output_cast_kernel<__half>, dim3(blocks), dim3(threads), 0, stream, true, reinterpret_cast<const __half*>(src), dst, N, C, H * W, C_phys);
     else
-        output_cast_kernel<float><<<blocks, threads, 0, stream>>>(reinterpret_cast<const float*>(src), dst, N, C, H * W, C_phys);
-    return static_cast<int>(cudaGetLastError());
+        B2_LAUNCH_RC = launch_kernel(output_cast_kernel<float>, dim3(blocks), dim3(threads), 0, stream, true, reinterpret_cast<const float*>(src), dst, N, C, H * W, C_phys);
+    return B2_LAUNCH_RC;
 }
 
 // max pool, NHWC, windows clipped to the image (Caffe ceil mode produces partial windows)
 template <typename T>
 __global__ void maxpool_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int H, int W, int C, int Ho,
                                int Wo, int k, int stride, int pad) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo * C) return;
     const int c = static_cast<int>(idx % C);
@@ -558,6 +717,8 @@ __global__ void maxpool_kernel(const T* __restrict__ src, T* __restrict__ dst, i
 // fp16 NHWC, 8 channels (16 bytes) per thread
 __global__ void maxpool_h8_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int H, int W,
                                   int C8, int Ho, int Wo, int k, int stride, int pad) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * Ho * Wo * C8) return;
     const int c = static_cast<int>(idx % C8);
@@ -592,21 +753,23 @@ int launch_maxpool(const void* src, void* dst, int N, int H, int W, int C_phys, 
     const int threads = 256;
     if (half_storage && C_phys % 8 == 0) {
         const long long total = static_cast<long long>(N) * Ho * Wo * (C_phys / 8);
-        maxpool_h8_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
+        B2_LAUNCH_RC = launch_kernel(maxpool_h8_kernel, dim3(static_cast<unsigned>((total + threads - 1) / threads)), dim3(threads), 0, stream, true, 
             reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), N, H, W, C_phys / 8, Ho, Wo, k, stride, pad);
     } else {
         const long long total = static_cast<long long>(N) * Ho * Wo * C_phys;
         const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
         if (half_storage)
-            maxpool_kernel<__half><<<blocks, threads, 0, stream>>>(reinterpret_cast<const __half*>(src), reinterpret_cast<__half*>(dst), N, H, W, C_phys, Ho, Wo, k, stride, pad);
+            B2_LAUNCH_RC = launch_kernel(maxpool_kernel<__half>, dim3(blocks), dim3(threads), 0, stream, true, reinterpret_cast<const __half*>(src), reinterpret_cast<__half*>(dst), N, H, W, C_phys, Ho, Wo, k, stride, pad);
         else
-            maxpool_kernel<float><<<blocks, threads, 0, stream>>>(reinterpret_cast<const float*>(src), reinterpret_cast<float*>(dst), N, H, W, C_phys, Ho, Wo, k, stride, pad);
+            B2_LAUNCH_RC = launch_kernel(maxpool_kernel<float>, dim3(blocks), dim3(threads), 0, stream, true, reinterpret_cast<const float*>(src), reinterpret_cast<float*>(dst), N, H, W, C_phys, Ho, Wo, k, stride, pad);
     }
-    return static_cast<int>(cudaGetLastError());
+    return B2_LAUNCH_RC;
 }
 
 template <typename T>
 __global__ void avgpool_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int HW, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     using acc_t = typename Acc<T>::type;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * C) return;
@@ -621,16 +784,18 @@ int launch_avgpool(const void* src, void* dst, int N, int HW, int C_phys, bool h
     const int threads = 128;
     const unsigned blocks = static_cast<unsigned>((N * C_phys + threads - 1) / threads);
     if (half_storage)
-        avgpool_kernel<__half><<<blocks, threads, 0, stream>>>(reinterpret_cast<const __half*>(src), reinterpret_cast<__half*>(dst), N, HW, C_phys);
+        B2_LAUNCH_RC = launch_kernel(avgpool_kernel<__half>, dim3(blocks), dim3(threads), 0, stream, true, reinterpret_cast<const __half*>(src), reinterpret_cast<__half*>(dst), N, HW, C_phys);
     else
-        avgpool_kernel<float><<<blocks, threads, 0, stream>>>(reinterpret_cast<const float*>(src), reinterpret_cast<float*>(dst), N, HW, C_phys);
-    return static_cast<int>(cudaGetLastError());
+        B2_LAUNCH_RC = launch_kernel(avgpool_kernel<float>, dim3(blocks), dim3(threads), 0, stream, true, reinterpret_cast<const float*>(src), reinterpret_cast<float*>(dst), N, HW, C_phys);
+    return B2_LAUNCH_RC;
 }
 
 // fully connected: one warp per output neuron, all batch rows (<= 8 per pass) share each weight read
 template <typename T>
 __global__ void fc_kernel(const T* __restrict__ in, const T* __restrict__ w, const float* __restrict__ bias,
                           float* __restrict__ out, int N, int K, int Cout) {
+    pdl_launch_dependents();
+    pdl_wait();
     using acc_t = typename Acc<T>::type;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -656,43 +821,55 @@ __global__ void fc_kernel(const T* __restrict__ in, const T* __restrict__ w, con
     }
 }
 
-// fp16 fast path: up to 8 batch rows staged in shared memory, one warp per output neuron, 128-bit loads.
-// Requires K % 256 == 0 (each lane owns 8 consecutive K elements per 256-element slab).
+// fp16 fast path (K == 256 * KV, KV <= 8): one warp per output neuron; each lane first pulls its slice of the
+// weight row into registers -- weights are constants, so this happens BEFORE the PDL wait and overlaps the
+// previous kernel -- then up to 8 batch rows are staged in shared memory and reduced with warp shuffles.
 template <int ROWS>
 __global__ void __launch_bounds__(256)
 fc_h8_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const float* __restrict__ bias,
              float* __restrict__ out, int N, int K, int Cout) {
     extern __shared__ uint4 s_in[];  // [ROWS][K/8]
-    const int kv = K / 8;
+    const int kv = K / 8;            // uint4 per row
+    const int per_lane = kv / 32;    // <= 8
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + warp;
+    uint4 wreg[8];
+    if (j < Cout) {
+        const uint4* wr = reinterpret_cast<const uint4*>(w + static_cast<size_t>(j) * K);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < per_lane) wreg[i] = __ldg(wr + lane + 32 * i);
+    }
+    pdl_launch_dependents();
+    pdl_wait();
     for (int nb = 0; nb < N; nb += ROWS) {
         const int rows = min(ROWS, N - nb);
         __syncthreads();
         for (int i = threadIdx.x; i < rows * kv; i += blockDim.x)
             s_in[i] = __ldg(reinterpret_cast<const uint4*>(in + static_cast<size_t>(nb) * K) + i);
         __syncthreads();
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int j = blockIdx.x * (blockDim.x >> 5) + warp;
         if (j < Cout) {
             float acc[ROWS];
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
-            const uint4* wr = reinterpret_cast<const uint4*>(w + static_cast<size_t>(j) * K);
-            for (int v = lane; v < kv; v += 32) {
-                const uint4 wv = __ldg(wr + v);
-                const __half2* w2 = reinterpret_cast<const __half2*>(&wv);
-                float2 wf[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) wf[q] = __half22float2(w2[q]);
+            for (int i = 0; i < 8; ++i) {
+                if (i < per_lane) {
+                    const __half2* w2 = reinterpret_cast<const __half2*>(&wreg[i]);
+                    float2 wf[4];
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                    if (r < rows) {
-                        const uint4 xv = s_in[r * kv + v];
-                        const __half2* x2 = reinterpret_cast<const __half2*>(&xv);
+                    for (int q = 0; q < 4; ++q) wf[q] = __half22float2(w2[q]);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float2 xf = __half22float2(x2[q]);
-                            acc[r] = fmaf(wf[q].x, xf.x, acc[r]);
-                            acc[r] = fmaf(wf[q].y, xf.y, acc[r]);
+                    for (int r = 0; r < ROWS; ++r) {
+                        if (r < rows) {
+                            const uint4 xv = s_in[r * kv + lane + 32 * i];
+                            const __half2* x2 = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 xf = __half22float2(x2[q]);
+                                acc[r] = fmaf(wf[q].x, xf.x, acc[r]);
+                                acc[r] = fmaf(wf[q].y, xf.y, acc[r]);
+                            }
                         }
                     }
                 }
@@ -709,29 +886,31 @@ fc_h8_kernel(const __half* __restrict__ in, const __half* __restrict__ w, const 
 
 int launch_fc(const void* in, const void* w, const float* bias, float* out, int N, int K, int Cout, bool half_storage,
               cudaStream_t stream) {
-    if (half_storage && K % 8 == 0 && static_cast<size_t>(K) * 2 * 8 <= 96 * 1024) {
-        const int threads = 256;  // 8 warps -> 8 neurons per block
-        const unsigned blocks = static_cast<unsigned>((Cout + 7) / 8);
+    if (half_storage && K % 256 == 0 && K <= 2048) {
+        const int threads = 128;  // 4 warps -> 4 neurons per block (250 blocks for the 1000-way classifier)
+        const unsigned blocks = static_cast<unsigned>((Cout + 3) / 4);
         const size_t smem = static_cast<size_t>(K) * 2 * 8;
         static bool attr_set = false;
         if (!attr_set) {
             cudaFuncSetAttribute(fc_h8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             attr_set = true;
         }
-        fc_h8_kernel<8><<<blocks, threads, smem, stream>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<const __half*>(w), bias, out, N, K, Cout);
-        return static_cast<int>(cudaGetLastError());
+        B2_LAUNCH_RC = launch_kernel(fc_h8_kernel<8>, dim3(blocks), dim3(threads), smem, stream, true, reinterpret_cast<const __half*>(in), reinterpret_cast<const __half*>(w), bias, out, N, K, Cout);
+        return B2_LAUNCH_RC;
     }
     const int threads = 128;  // 4 warps
     const unsigned blocks = static_cast<unsigned>((Cout + 3) / 4);
     if (half_storage)
-        fc_kernel<__half><<<blocks, threads, 0, stream>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<const __half*>(w), bias, out, N, K, Cout);
+        B2_LAUNCH_RC = launch_kernel(fc_kernel<__half>, dim3(blocks), dim3(threads), 0, stream, true, reinterpret_cast<const __half*>(in), reinterpret_cast<const __half*>(w), bias, out, N, K, Cout);
     else
-        fc_kernel<float><<<blocks, threads, 0, stream>>>(reinterpret_cast<const float*>(in), reinterpret_cast<const float*>(w), bias, out, N, K, Cout);
-    return static_cast<int>(cudaGetLastError());
+        B2_LAUNCH_RC = launch_kernel(fc_kernel<float>, dim3(blocks), dim3(threads), 0, stream, true, reinterpret_cast<const float*>(in), reinterpret_cast<const float*>(w), bias, out, N, K, Cout);
+    return B2_LAUNCH_RC;
 }
 
 // row softmax, one 256-thread block per row
 __global__ void softmax_kernel(const float* __restrict__ in, float* __restrict__ out, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[32];
     const float* x = in + static_cast<size_t>(blockIdx.x) * C;
     float* y = out + static_cast<size_t>(blockIdx.x) * C;
@@ -757,8 +936,8 @@ __global__ void softmax_kernel(const float* __restrict__ in, float* __restrict__
 
 int launch_softmax(const float* in, float* out, int N, int C, cudaStream_t stream) {
     if (N <= 0) return 0;
-    softmax_kernel<<<N, 256, 0, stream>>>(in, out, C);
-    return static_cast<int>(cudaGetLastError());
+    B2_LAUNCH_RC = launch_kernel(softmax_kernel, dim3(N), dim3(256), 0, stream, true, in, out, C);
+    return B2_LAUNCH_RC;
 }
 
 }  // namespace b2k

@@ -30,15 +30,20 @@ struct ConvArgs {
     int stride, pad;
     int relu;
     int a_mode;              // A_TILED (1x1 stride-1: plain 2-D TMA) or A_IM2COL (TMA im2col mode)
-    int split_k;             // reserved (1)
+    int splits;              // split-K factor (gridDim.z); 1 = none
+    int kb_per_split;        // k-blocks per split
+    float* workspace;        // splits > 1: [tile][split][128][BN] fp32 partial tiles
+    int* tile_counters;      // splits > 1: one arrival counter per output tile (zero between launches)
+    int pdl_trigger;         // 0: release the dependent kernel right after the prologue, 1: after the main loop
 };
 
 struct ConvLaunch {
     CUtensorMap mapA;  // activations: 2-D tiled [M, Cin] or 4-D im2col (C, W, H, N)
     CUtensorMap mapB;  // weights: 2-D tiled [Cout_phys, Ktot]
     ConvArgs args;
-    int bn;            // N tile: 16..256
+    int bn;            // N tile: 32 / 64 / 128
     int kb;            // K elements per TMA sub-tile: 64 (SWIZZLE_128B) or 8 (no swizzle, Cin_phys == 8)
+    int stages;        // smem pipeline depth: 1 / 2 / 4 / 8
     int grid_m, grid_n;
 };
 
@@ -46,8 +51,11 @@ struct ConvLaunch {
 int launch_conv_f16_tcgen05(const ConvLaunch& L, cudaStream_t stream);
 // one-time: opt in to large dynamic shared memory for every instantiation
 int init_conv_kernels();
-// smallest supported N tile that divides cout_phys given a preferred tile
-bool conv_tile_supported(int bn, int kb);
+bool conv_config_exists(int bn, int kb, int stages);  // is this (tile, K-chunk, depth) instantiated?
+int conv_smem_bytes(int bn, int stages);
+// programmatic dependent launch on/off for every kernel of this library (default on)
+void set_pdl(bool on);
+bool get_pdl();
 
 // ---------------------------------------------------------------------------------------------
 // SIMT kernels (reference/fp32 engine path, and the non-GEMM operators of the fp16 path)

@@ -75,12 +75,12 @@ def exp_rn50_fp16_nograph():
     return dict(exp="rn50_fp16_tcgen05_nograph", **_resnet(1, 2, {"graph": 0}, emu=True))
 
 
-def exp_profile():
+def exp_profile(options=None, tag="profile_b8"):
     import numpy as np
     from tensorrt_laboratory_b200 import builder, capi, weights
     blob = builder.build_resnet_plan(50, builder.PREC_FP16, 8)
     eng = capi.Engine(blob)
-    sess = capi.Session(eng)
+    sess = capi.Session(eng, options)
     x = weights.synthetic_input(8)
     sess.infer(x)
     sess.infer(x)
@@ -101,11 +101,29 @@ def exp_profile():
     total = sum(p["ms"] for p in prof)
     conv = sum(p["ms"] for p in prof if p["name"].startswith("conv"))
     sess.close()
-    return dict(exp="profile_b8", graph_ms_per_batch=ms, img_per_s=8 / ms * 1e3, serial_sum_ms=total, conv_ms=conv,
+    return dict(exp=tag, options=options, graph_ms_per_batch=ms, img_per_s=8 / ms * 1e3, serial_sum_ms=total, conv_ms=conv,
                 tflops_graph=eng.flops(8) / ms / 1e9, layers=prof)
 
 
+def _variant(name, opts):
+    def f():
+        return exp_profile(opts, name)
+    f.__name__ = "exp_" + name
+    return f
+
+
+VARIANTS = {
+    "p_nopdl": {"pdl": 0},
+    "p_trig0": {"pdl": 1, "pdl_trigger": 0},
+    "p_nosplit": {"splits": 1},
+    "p_bn64": {"bn": 64},
+    "p_bn64_nosplit": {"bn": 64, "splits": 1},
+    "p_bn128": {"bn": 128},
+    "p_st4": {"stages": 4},
+    "p_st4_nosplit": {"stages": 4, "splits": 1},
+}
 EXPS = {f.__name__[4:]: f for f in (exp_mnist, exp_rn50_fp32, exp_rn50_fp16_simt, exp_rn50_fp16, exp_rn50_fp16_nograph, exp_profile)}
+EXPS.update({k: _variant(k, v) for k, v in VARIANTS.items()})
 
 
 def main():
