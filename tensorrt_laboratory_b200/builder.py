@@ -22,7 +22,7 @@ VERSION = 1
 
 _HEADER = struct.Struct("<8sIIIIIIQQ64s16x")
 _TENSOR = struct.Struct("<64sIIIIIi8x")
-_OP = struct.Struct("<64sIiiiiIIIIIIIIIIIQQQQ16x")
+_OP = struct.Struct("<64sIiiiiIIIIIIIIIIIQQQQIIII")
 _BINDING = struct.Struct("<64sIIiI8i16x")
 assert _HEADER.size == 128 and _TENSOR.size == 96 and _OP.size == 176 and _BINDING.size == 128
 
@@ -39,6 +39,31 @@ def phys_channels(c: int, precision: int) -> int:
     return 8 if c <= 8 else _roundup(c, 64)
 
 
+def stem_s2d_transform(W: np.ndarray, k: int, pad: int, w_in: int):
+    """Re-express a stride-2, thin-input (Cin <= 4) convolution on a horizontally space-to-depth packed input.
+
+    The packed tensor holds pixel pairs: X2[n, h, w2, dw*4 + c] = X[n, c, h, 2*w2 + dw].  Column 2q - pad + s of
+    the original becomes packed column q + a with a = floor((s - pad)/2), dw = (s - pad) mod 2, so the
+    kxk / stride-2 conv turns into a k x kw2 conv with stride (2, 1) over 8 channels -- 4/7 of the im2col TMA
+    loads and of the zero-padded K for the 7x7 stem.  Returns (W2 [cout, k, kw2, 8], kw2, pad_lo, pad_hi).
+    """
+    cout, kh, kw, cin = W.shape
+    assert kh == kw == k and cin <= 4 and w_in % 2 == 0
+    a_min = (0 - pad) // 2
+    a_max = (k - 1 - pad) // 2
+    kw2 = a_max - a_min + 1
+    W2 = np.zeros((cout, kh, kw2, 8), dtype=W.dtype)
+    for s_ in range(k):
+        a = (s_ - pad) // 2
+        dw = (s_ - pad) - 2 * a
+        W2[:, :, a - a_min, dw * 4:dw * 4 + cin] = W[:, :, s_, :]
+    q = (w_in + 2 * pad - k) // 2 + 1
+    pad_lo = -a_min
+    pad_hi = q - 1 + kw2 - w_in // 2 - pad_lo
+    assert pad_hi >= 0
+    return W2, kw2, pad_lo, pad_hi
+
+
 def _name(s: str) -> bytes:
     b = s.encode()
     if len(b) > 63:
@@ -47,7 +72,7 @@ def _name(s: str) -> bytes:
 
 
 def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
-               outputs: Optional[Sequence[str]] = None, name: Optional[str] = None) -> bytes:
+               outputs: Optional[Sequence[str]] = None, name: Optional[str] = None, stem_s2d: bool = True) -> bytes:
     """Serialize ``lowered`` (from :func:`graph.lower` with weights) into a plan blob.
 
     ``outputs``: tensor names to expose as output bindings (default: the graph output).  4-D activation
@@ -92,6 +117,16 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
     t_in = add_tensor(lowered["input"])
     bindings.append(dict(name=lowered["input"], is_input=1, dtype=0, tensor=t_in, dims=[cin, hin, win]))
     ops.append(dict(name="cast:" + lowered["input"], type=OP_INPUT_CAST, inp=-1, res=-1, out=t_in, binding=0))
+    # fp16 stem: a stride-2 conv that is the only reader of a thin (<= 4 channel) even-width input runs on a
+    # horizontally space-to-depth packed copy of the input (see stem_s2d_transform)
+    readers = [o for o in lowered["ops"] if o["input"] == lowered["input"] or o.get("residual") == lowered["input"]]
+    s2d_op = None
+    if (precision == PREC_FP16 and stem_s2d and len(readers) == 1 and readers[0]["type"] == G.OP_CONV
+            and readers[0]["stride"] == 2 and cin <= 4 and win % 2 == 0 and lowered["input"] not in outputs
+            and readers[0]["k"] >= 3):
+        s2d_op = readers[0]
+        tensors[t_in].update(w=win // 2, c=8, c_phys=8)
+        ops[0]["k"] = 2
 
     for op in lowered["ops"]:
         t = op["type"]
@@ -104,17 +139,23 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
             cin_phys = tensors[ti]["c_phys"]
             cout_phys = tensors[to]["c_phys"]
             k = op["k"]
+            Wsrc, cin_eff, extra = op["W"], op["cin"], {}
             taps = k * k
+            if op is s2d_op:
+                Wsrc, kw2, pad_lo, pad_hi = stem_s2d_transform(op["W"], k, op["pad"], win)
+                cin_eff, taps = 8, k * kw2
+                extra = dict(kw=kw2, stride_w=1, pad_w_lo=pad_lo, pad_w_hi=pad_hi, ceil_mode=op["cin"] * k * k)
             taps_phys = _roundup(taps, 2) if (precision == PREC_FP16 and cin_phys == 8) else taps
             W = np.zeros((cout_phys, taps_phys, cin_phys), dtype=np.float32)
-            W[:op["cout"], :taps, :op["cin"]] = op["W"].reshape(op["cout"], taps, op["cin"])
+            W[:op["cout"], :taps, :cin_eff] = Wsrc.reshape(op["cout"], taps, cin_eff)
             bias = np.zeros(cout_phys, dtype=np.float32)
             bias[:op["cout"]] = op["bias"]
             w_off, w_bytes = add_payload(W.astype(wdtype))
             b_off, b_bytes = add_payload(bias)
             rec.update(type=OP_CONV, k=k, stride=op["stride"], pad=op["pad"], relu=int(op["relu"]),
-                       cin=op["cin"], cout=op["cout"], cin_phys=cin_phys, cout_phys=cout_phys,
+                       cin=cin_eff, cout=op["cout"], cin_phys=cin_phys, cout_phys=cout_phys,
                        taps=taps, taps_phys=taps_phys, w_off=w_off, w_bytes=w_bytes, b_off=b_off, b_bytes=b_bytes)
+            rec.update(extra)
             if op["residual"] is not None:
                 rec["res"] = add_tensor(op["residual"])
         elif t == G.OP_MAXPOOL:
@@ -163,7 +204,8 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
                          o.get("k", 0), o.get("stride", 0), o.get("pad", 0), o.get("relu", 0), o.get("ceil_mode", 0),
                          o.get("cin", 0), o.get("cout", 0), o.get("cin_phys", 0), o.get("cout_phys", 0),
                          o.get("taps", 0), o.get("taps_phys", 0),
-                         o.get("w_off", 0), o.get("w_bytes", 0), o.get("b_off", 0), o.get("b_bytes", 0))
+                         o.get("w_off", 0), o.get("w_bytes", 0), o.get("b_off", 0), o.get("b_bytes", 0),
+                         o.get("kw", 0), o.get("stride_w", 0), o.get("pad_w_lo", 0), o.get("pad_w_hi", 0))
     for b in bindings:
         dims = list(b["dims"]) + [0] * (8 - len(b["dims"]))
         blob += _BINDING.pack(_name(b["name"]), b["is_input"], b["dtype"], b["tensor"], len(b["dims"]), *dims)

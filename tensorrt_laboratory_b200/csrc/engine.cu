@@ -103,6 +103,15 @@ struct Tensor {
 struct Op {
     b2plan::OpRec r;
     std::string name;
+    // conv geometry with the "0 = square" defaults resolved
+    int kh() const { return int(r.k); }
+    int kw() const { return int(r.kw ? r.kw : r.k); }
+    int sh() const { return int(r.stride); }
+    int sw() const { return int(r.kw ? r.stride_w : r.stride); }
+    int ph() const { return int(r.pad_); }
+    int pw_lo() const { return int(r.kw ? r.pad_w_lo : r.pad_); }
+    int pw_hi() const { return int(r.kw ? r.pad_w_hi : r.pad_); }
+    double algo_k() const { return r.ceil_mode ? double(r.ceil_mode) : double(r.cin) * r.taps; }
 };
 
 struct Binding {
@@ -138,6 +147,11 @@ struct Plan {
 
 }  // namespace
 
+struct ConvConfig {
+    int bn, stages, splits;
+    double est_us;
+};
+
 struct b2_runtime {
     b2_alloc_fn alloc = nullptr;
     b2_free_fn free_ = nullptr;
@@ -161,6 +175,8 @@ struct b2_engine {
     int device = -1;
     bool inspect_only = false;
     double flops_per_item = 0;
+    std::mutex tune_mutex;
+    std::map<std::pair<int, int>, ConvConfig> tuned;  // (op index, batch) -> measured-best configuration
     bool half() const { return precision == B2_PREC_FP16; }
 };
 
@@ -189,6 +205,7 @@ struct b2_context {
     int force_stages = 0;
     int force_splits = 0;
     int pdl_trigger = 1;
+    int autotune = 4;  // 0 off (cost model), 1 latency mode, N>=2 throughput mode over N streams
 };
 
 namespace {
@@ -255,7 +272,7 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
         if (r.w_off + r.w_bytes > h.payload_bytes || r.b_off + r.b_bytes > h.payload_bytes)
             return fail(B2_EINVAL, "plan: op %s weights outside payload", op.name.c_str());
         if (r.type == OP_CONV) {
-            if (r.k == 0 || r.stride == 0 || r.taps != r.k * r.k || r.taps_phys < r.taps)
+            if (r.k == 0 || r.stride == 0 || int(r.taps) != op.kh() * op.kw() || r.taps_phys < r.taps || op.sw() == 0)
                 return fail(B2_EINVAL, "plan: conv %s has bad geometry", op.name.c_str());
             if (r.w_bytes != size_t(r.cout_phys) * r.taps_phys * r.cin_phys * elt || r.b_bytes != size_t(r.cout_phys) * 4)
                 return fail(B2_EINVAL, "plan: conv %s weight size mismatch", op.name.c_str());
@@ -263,9 +280,10 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
             const Tensor& to = e->tensors[r.out];
             if (ti.c_phys != r.cin_phys || to.c_phys != r.cout_phys || ti.c != r.cin || to.c != r.cout)
                 return fail(B2_EINVAL, "plan: conv %s channel mismatch with its tensors", op.name.c_str());
-            const uint32_t ho = (ti.h + 2 * r.pad_ - r.k) / r.stride + 1, wo = (ti.w + 2 * r.pad_ - r.k) / r.stride + 1;
+            const uint32_t ho = (ti.h + 2 * r.pad_ - r.k) / r.stride + 1;
+            const uint32_t wo = uint32_t((int(ti.w) + op.pw_lo() + op.pw_hi() - op.kw()) / op.sw() + 1);
             if (to.h != ho || to.w != wo) return fail(B2_EINVAL, "plan: conv %s output dims mismatch", op.name.c_str());
-            e->flops_per_item += 2.0 * ho * wo * r.cout * r.cin * r.taps;
+            e->flops_per_item += 2.0 * ho * wo * r.cout * op.algo_k();
         } else if (r.type == OP_FC) {
             const Tensor& ti = e->tensors[r.in];
             const size_t K = size_t(ti.h) * ti.w * ti.c_phys;
@@ -353,20 +371,21 @@ int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t out
     return B2_OK;
 }
 
-int make_map_im2col(CUtensorMap* map, const void* base, int C, int W, int H, int N, int k, int stride, int pad,
-                    uint32_t channels_per_pixel, uint32_t pixels_per_column, CUtensorMapSwizzle swz) {
+int make_map_im2col(CUtensorMap* map, const void* base, int C, int W, int H, int N, int kh, int kw, int stride_h,
+                    int stride_w, int pad_h, int pad_w_lo, int pad_w_hi, uint32_t channels_per_pixel,
+                    uint32_t pixels_per_column, CUtensorMapSwizzle swz) {
     cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
     cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
     // fprop bounding box: base pixel positions run over [-pad, dim - 1 + pad - (k-1)] (dilation 1)
-    int lower[2] = {-pad, -pad};
-    int upper[2] = {pad - (k - 1), pad - (k - 1)};
-    cuuint32_t estr[4] = {1, cuuint32_t(stride), cuuint32_t(stride), 1};
+    int lower[2] = {-pad_w_lo, -pad_h};                            // (W, H) order
+    int upper[2] = {pad_w_hi - (kw - 1), pad_h - (kh - 1)};
+    cuuint32_t estr[4] = {1, cuuint32_t(stride_w), cuuint32_t(stride_h), 1};
     CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
                                  upper, channels_per_pixel, pixels_per_column, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
-        return fail(B2_ECUDA, "cuTensorMapEncodeIm2col failed (%d) C=%d W=%d H=%d N=%d k=%d s=%d p=%d", int(r), C, W, H,
-                    N, k, stride, pad);
+        return fail(B2_ECUDA, "cuTensorMapEncodeIm2col failed (%d) C=%d W=%d H=%d N=%d k=%dx%d s=%dx%d p=%d,%d/%d", int(r), C,
+                    W, H, N, kh, kw, stride_h, stride_w, pad_h, pad_w_lo, pad_w_hi);
     // Driver workaround mirrored from CUTLASS (cute/atom/copy_traits_sm90_im2col.hpp): drivers <= 13.1 set a
     // descriptor bit that misbehaves for tensors smaller than 128 KiB.
     if (g_driver_version <= 13010 && size_t(C) * W * H * N * 2 < 131072)
@@ -374,25 +393,20 @@ int make_map_im2col(CUtensorMap* map, const void* base, int C, int W, int H, int
     return B2_OK;
 }
 
-struct ConvConfig {
-    int bn, stages, splits;
-    double est_us;
-};
-
 // Analytic cost model (microseconds) over the instantiated (N tile, pipeline depth, split-K) space.  The
 // constants are rough B200 figures: ~70 KB/us of L2->SM bandwidth per SM, ~1 us TMA round trip, ~5 TB/s of
 // aggregate L2 bandwidth, ~2 us of fixed per-CTA cost.  It only has to rank configurations sensibly.
-ConvConfig pick_conv_config(int M, int cout_phys, int kblocks, int kb, bool residual, const b2_context* c) {
+ConvConfig pick_conv_config(int M, int cout_phys, int kblocks, int kb, bool residual, const b2_context* c, bool honor_forced) {
     const int m_tiles = (M + 127) / 128;
     ConvConfig best{0, 0, 1, 1e30};
     const int bns[3] = {128, 64, 32};
     const int stgs[4] = {1, 2, 4, 8};
     for (int bn : bns) {
         if (cout_phys % bn) continue;
-        if (c->force_bn && bn != c->force_bn) continue;
+        if (honor_forced && c->force_bn && bn != c->force_bn) continue;
         const int tiles = m_tiles * (cout_phys / bn);
         for (int splits = 1; splits <= 8; ++splits) {
-            if (c->force_splits && splits != c->force_splits) continue;
+            if (c->force_splits ? splits != c->force_splits : splits != 1) continue;  // split-K is opt-in (measured slower)
             if (splits > 1 && (kb != 64 || kblocks / splits < 4 || tiles * splits > 160 || tiles > kMaxSplitTiles ||
                                size_t(tiles) * splits * 128 * bn * 4 > kSplitWorkspaceBytes))
                 continue;
@@ -400,8 +414,8 @@ ConvConfig pick_conv_config(int M, int cout_phys, int kblocks, int kb, bool resi
             if (splits > 1 && (splits - 1) * kpc >= kblocks) continue;  // an empty split
             for (int st : stgs) {
                 if (!b2k::conv_config_exists(bn, kb, st)) continue;
-                if (c->force_stages && st != c->force_stages) continue;
-                if (!c->force_stages && st > 1 && st / 2 >= kpc) continue;  // deeper than the loop is long
+                if (honor_forced && c->force_stages && st != c->force_stages) continue;
+                if (!(honor_forced && c->force_stages) && st > 1 && st / 2 >= kpc) continue;  // deeper than the loop is long
                 const double smem = b2k::conv_smem_bytes(bn, st);
                 int per_sm = int(227.0 * 1024 / smem);
                 per_sm = std::min(per_sm, 512 / std::max(32, bn));
@@ -422,6 +436,151 @@ ConvConfig pick_conv_config(int M, int cout_phys, int kblocks, int kb, bool resi
         }
     }
     return best;
+}
+
+// Fill a ConvLaunch (kernel arguments + TMA tensor maps) for one conv op under a given configuration.
+int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& cfg, b2k::ConvLaunch* out) {
+    b2_engine* e = c->e;
+    const b2plan::OpRec& r = op.r;
+    const Tensor& ti = e->tensors[r.in];
+    const Tensor& to = e->tensors[r.out];
+    auto tptr = [&](int idx) -> uint8_t* { return c->scratch + e->tensors[idx].offset; };
+    const uint8_t* w = e->d_payload + r.w_off;
+    const int M = batch * int(to.h) * int(to.w);
+    const bool kb64 = r.cin_phys % 64 == 0;
+    b2k::ConvLaunch& cl = *out;
+    memset(&cl, 0, sizeof cl);
+    cl.kb = kb64 ? 64 : 8;
+    cl.grid_m = (M + 127) / 128;
+    const int nkb = kb64 ? int(r.taps) * (int(r.cin_phys) / 64) : (int(r.taps_phys) + 7) / 8;
+    cl.bn = cfg.bn;
+    cl.stages = cfg.stages;
+    cl.grid_n = int(r.cout_phys) / cl.bn;
+    b2k::ConvArgs& a = cl.args;
+    a.splits = cfg.splits;
+    a.kb_per_split = (nkb + cfg.splits - 1) / cfg.splits;
+    a.workspace = reinterpret_cast<float*>(c->scratch + e->act_bytes);
+    a.tile_counters = c->d_counters;
+    a.pdl_trigger = c->pdl_trigger;
+    a.bias = reinterpret_cast<const float*>(e->d_payload + r.b_off);
+    a.residual = r.res >= 0 ? reinterpret_cast<const __half*>(tptr(r.res)) : nullptr;
+    a.out = reinterpret_cast<__half*>(tptr(r.out));
+    a.M = M;
+    a.Cout = int(r.cout_phys);
+    a.taps = int(r.taps);
+    a.taps_phys = int(r.taps_phys);
+    a.kw = op.kw();
+    a.cblocks = kb64 ? int(r.cin_phys) / 64 : 1;
+    a.num_kblocks = nkb;
+    a.HoWo = int(to.h * to.w);
+    a.Wo = int(to.w);
+    a.stride_h = op.sh();
+    a.stride_w = op.sw();
+    a.pad_h = op.ph();
+    a.pad_w = op.pw_lo();
+    a.relu = int(r.relu);
+    const bool tiled = r.k == 1 && op.kw() == 1 && r.stride == 1 && op.sw() == 1 && r.pad_ == 0 && op.pw_lo() == 0 &&
+                       op.pw_hi() == 0 && kb64 && !c->force_im2col;
+    a.a_mode = tiled ? b2k::A_TILED : b2k::A_IM2COL;
+    const CUtensorMapSwizzle swz = kb64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    int rc;
+    if (tiled)
+        rc = make_map_2d(&cl.mapA, tptr(r.in), r.cin_phys, uint64_t(M), 64, 128, swz);
+    else
+        rc = make_map_im2col(&cl.mapA, tptr(r.in), int(r.cin_phys), int(ti.w), int(ti.h), batch, op.kh(), op.kw(), op.sh(),
+                             op.sw(), op.ph(), op.pw_lo(), op.pw_hi(), uint32_t(cl.kb), 128, swz);
+    if (rc) return rc;
+    return make_map_2d(&cl.mapB, w, uint64_t(r.taps_phys) * r.cin_phys, r.cout_phys, uint32_t(cl.kb), uint32_t(cl.bn), swz);
+}
+
+// Tactic selection, the role TensorRT's builder plays for the reference's engines: time every instantiated
+// (N tile, pipeline depth) on THIS device with the layer's real shapes and keep the fastest.  Runs once per
+// (engine, layer, batch); results are shared by all contexts of the engine.
+int autotune_conv(b2_context* c, const Op& op, int batch, ConvConfig* best_out) {
+    b2_engine* e = c->e;
+    const b2plan::OpRec& r = op.r;
+    const Tensor& to = e->tensors[r.out];
+    const int M = batch * int(to.h) * int(to.w);
+    const bool kb64 = r.cin_phys % 64 == 0;
+    const int kbsz = kb64 ? 64 : 8;
+    const int nkb = kb64 ? int(r.taps) * (int(r.cin_phys) / 64) : (int(r.taps_phys) + 7) / 8;
+    // c->autotune == 1: latency mode (one stream).  >= 2: throughput mode -- the candidate is launched on that
+    // many streams at once, which is how the kernels meet each other when several ExecutionContexts overlap
+    // (BASELINE config: 4 contexts); deep pipelines that win alone can lose here because they hog shared memory.
+    const int ns = std::max(1, std::min(c->autotune, 8));
+    std::vector<cudaStream_t> ss(ns, nullptr);
+    std::vector<cudaEvent_t> done(ns, nullptr);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool ok = cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
+    for (int i = 0; i < ns && ok; ++i)
+        ok = cudaStreamCreateWithFlags(&ss[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) == cudaSuccess;
+    auto cleanup = [&] {
+        for (auto s_ : ss)
+            if (s_) cudaStreamDestroy(s_);
+        for (auto d : done)
+            if (d) cudaEventDestroy(d);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+    if (!ok) {
+        cudaGetLastError();
+        cleanup();
+        return fail(B2_ECUDA, "autotune: cannot create streams/events");
+    }
+    ConvConfig best = *best_out;
+    double best_ms = 1e30;
+    const int bns[3] = {128, 64, 32};
+    const int stgs[4] = {1, 2, 4, 8};
+    int status = B2_OK;
+    const int iters = 12;
+    const int m_tiles = (M + 127) / 128;
+    const int split_cands[4] = {1, 2, 4, 8};
+    for (int bn : bns) {
+        if (int(r.cout_phys) % bn) continue;
+        const int tiles = m_tiles * (int(r.cout_phys) / bn);
+        for (int sp : split_cands)
+        for (int st : stgs) {
+            if (!b2k::conv_config_exists(bn, kbsz, st)) continue;
+            const int kpc = (nkb + sp - 1) / sp;
+            if (st > 1 && st / 2 >= kpc) continue;
+            if (sp > 1 && (kbsz != 64 || tiles >= 100 || kpc < 4 || tiles * sp > 160 || (sp - 1) * kpc >= nkb ||
+                           size_t(tiles) * sp * 128 * bn * 4 > kSplitWorkspaceBytes))
+                continue;  // split-K only where the plain grid leaves SMs idle
+            ConvConfig cand{bn, st, sp, 0.0};
+            b2k::ConvLaunch cl;
+            if ((status = make_conv_launch(c, op, batch, cand, &cl))) break;
+            int rc = 0;
+            for (int i = 0; i < 2 && !rc; ++i)
+                for (int k = 0; k < ns && !rc; ++k) rc = b2k::launch_conv_f16_tcgen05(cl, ss[k]);
+            for (int k = 0; k < ns; ++k) cudaStreamSynchronize(ss[k]);
+            cudaEventRecord(e0, ss[0]);
+            for (int k = 1; k < ns; ++k) cudaStreamWaitEvent(ss[k], e0, 0);
+            for (int i = 0; i < iters && !rc; ++i)
+                for (int k = 0; k < ns && !rc; ++k) rc = b2k::launch_conv_f16_tcgen05(cl, ss[k]);
+            for (int k = 1; k < ns; ++k) {
+                cudaEventRecord(done[k], ss[k]);
+                cudaStreamWaitEvent(ss[0], done[k], 0);
+            }
+            cudaEventRecord(e1, ss[0]);
+            cudaError_t se = cudaStreamSynchronize(ss[0]);
+            if (rc || se != cudaSuccess) {
+                status = fail(B2_ECUDA, "autotune of %s (bn=%d st=%d) failed: %s", op.name.c_str(), bn, st,
+                              cudaGetErrorString(rc ? cudaError_t(rc) : se));
+                break;
+            }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (ms < best_ms) best_ms = ms, best = cand;
+        }
+        if (status) break;
+    }
+    cleanup();
+    if (status) return status;
+    best.est_us = best_ms * 1e3 / (iters * ns);
+    *best_out = best;
+    (void)M;
+    return B2_OK;
 }
 
 // ---- per-batch launch plan ---------------------------------------------------------------------
@@ -454,6 +613,13 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                 L.in_binding = r.binding;
                 L.out = tptr(r.out);
                 L.C = t.c, L.H = t.h, L.W = t.w, L.C_phys = t.c_phys;
+                L.k = int(r.k);  // 2: horizontal space-to-depth (tensor is [H, W/2, 8]; binding is [C, H, W])
+                if (r.k == 2) {
+                    const Binding& b = e->bindings[r.binding];
+                    if (!half || b.nd != 3 || b.dims[0] > 4 || t.c_phys != 8 || int(t.w) * 2 != b.dims[2] || int(t.h) != b.dims[1])
+                        return fail(B2_EINVAL, "input cast %s: inconsistent space-to-depth geometry", op.name.c_str());
+                    L.C = b.dims[0], L.W = b.dims[2];
+                }
                 L.bytes = double(batch) * t.h * t.w * (t.c * 4.0 + t.c_phys * elt);
                 break;
             }
@@ -472,7 +638,7 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                 const uint8_t* w = e->d_payload + r.w_off;
                 const float* bias = reinterpret_cast<const float*>(e->d_payload + r.b_off);
                 const int M = batch * int(to.h) * int(to.w);
-                L.flops = 2.0 * M * r.cout * r.cin * r.taps;
+                L.flops = 2.0 * M * r.cout * op.algo_k();
                 L.bytes = double(batch) * (ti.item_bytes + to.item_bytes * (r.res >= 0 ? 2 : 1)) + double(r.w_bytes);
                 const bool kb64 = r.cin_phys % 64 == 0;
                 const bool kb8 = r.cin_phys == 8;
@@ -480,51 +646,29 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                                    (kb64 || r.taps_phys % 2 == 0);
                 if (tc_ok) {
                     L.kind = L_CONV_TC;
-                    b2k::ConvLaunch& cl = L.conv;
-                    memset(&cl, 0, sizeof cl);
-                    cl.kb = kb64 ? 64 : 8;
-                    cl.grid_m = (M + 127) / 128;
+                    const int kbsz = kb64 ? 64 : 8;
                     const int nkb = kb64 ? int(r.taps) * (int(r.cin_phys) / 64) : (int(r.taps_phys) + 7) / 8;
-                    const ConvConfig cfg = pick_conv_config(M, int(r.cout_phys), nkb, cl.kb, r.res >= 0, c);
-                    if (cfg.bn == 0)
-                        return fail(B2_EINVAL, "conv %s: no kernel configuration (bn=%d stages=%d splits=%d forced)",
-                                    op.name.c_str(), c->force_bn, c->force_stages, c->force_splits);
-                    cl.bn = cfg.bn;
-                    cl.stages = cfg.stages;
-                    cl.grid_n = int(r.cout_phys) / cl.bn;
-                    b2k::ConvArgs& a = cl.args;
-                    a.splits = cfg.splits;
-                    a.kb_per_split = (nkb + cfg.splits - 1) / cfg.splits;
-                    a.workspace = reinterpret_cast<float*>(c->scratch + e->act_bytes);
-                    a.tile_counters = c->d_counters;
-                    a.pdl_trigger = c->pdl_trigger;
-                    a.bias = bias;
-                    a.residual = r.res >= 0 ? reinterpret_cast<const __half*>(tptr(r.res)) : nullptr;
-                    a.out = reinterpret_cast<__half*>(tptr(r.out));
-                    a.M = M;
-                    a.Cout = int(r.cout_phys);
-                    a.taps = int(r.taps);
-                    a.taps_phys = int(r.taps_phys);
-                    a.kw = int(r.k);
-                    a.cblocks = kb64 ? int(r.cin_phys) / 64 : 1;
-                    a.num_kblocks = kb64 ? int(r.taps) * a.cblocks : (int(r.taps_phys) + 7) / 8;
-                    a.HoWo = int(to.h * to.w);
-                    a.Wo = int(to.w);
-                    a.stride = int(r.stride);
-                    a.pad = int(r.pad_);
-                    a.relu = int(r.relu);
-                    const bool tiled = r.k == 1 && r.stride == 1 && r.pad_ == 0 && kb64 && !c->force_im2col;
-                    a.a_mode = tiled ? b2k::A_TILED : b2k::A_IM2COL;
-                    const CUtensorMapSwizzle swz = kb64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
-                    int rc;
-                    if (tiled)
-                        rc = make_map_2d(&cl.mapA, tptr(r.in), r.cin_phys, uint64_t(M), 64, 128, swz);
-                    else
-                        rc = make_map_im2col(&cl.mapA, tptr(r.in), int(r.cin_phys), int(ti.w), int(ti.h), batch, int(r.k),
-                                             int(r.stride), int(r.pad_), uint32_t(cl.kb), 128, swz);
-                    if (rc) return rc;
-                    rc = make_map_2d(&cl.mapB, w, uint64_t(r.taps_phys) * r.cin_phys, r.cout_phys, uint32_t(cl.kb),
-                                     uint32_t(cl.bn), swz);
+                    ConvConfig cfg = pick_conv_config(M, int(r.cout_phys), nkb, kbsz, r.res >= 0, c, true);
+                    if (cfg.bn == 0)  // a forced tile that does not divide this layer: fall back to the model
+                        cfg = pick_conv_config(M, int(r.cout_phys), nkb, kbsz, r.res >= 0, c, false);
+                    if (cfg.bn == 0) return fail(B2_EINVAL, "conv %s: no kernel configuration", op.name.c_str());
+                    const bool forced = c->force_bn || c->force_stages || c->force_splits;
+                    const int op_index = int(&op - &e->ops[0]);
+                    if (!forced && c->autotune) {
+                        bool have = false;
+                        {
+                            std::lock_guard<std::mutex> lock(e->tune_mutex);
+                            auto it = e->tuned.find({op_index, batch});
+                            if (it != e->tuned.end()) cfg = it->second, have = true;
+                        }
+                        if (!have) {
+                            int rc = autotune_conv(c, op, batch, &cfg);
+                            if (rc) return rc;
+                            std::lock_guard<std::mutex> lock(e->tune_mutex);
+                            e->tuned[{op_index, batch}] = cfg;
+                        }
+                    }
+                    int rc = make_conv_launch(c, op, batch, cfg, &L.conv);
                     if (rc) return rc;
                 } else {
                     L.kind = L_CONV_SIMT;
@@ -535,7 +679,8 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                     a.out = tptr(r.out);
                     a.N = batch, a.H = int(ti.h), a.W = int(ti.w), a.Cin = int(r.cin), a.Cin_phys = int(r.cin_phys);
                     a.Ho = int(to.h), a.Wo = int(to.w), a.Cout = int(r.cout), a.Cout_phys = int(r.cout_phys);
-                    a.k = int(r.k), a.taps_phys = int(r.taps_phys), a.stride = int(r.stride), a.pad = int(r.pad_);
+                    a.kh = op.kh(), a.kw = op.kw(), a.taps_phys = int(r.taps_phys);
+                    a.stride_h = op.sh(), a.stride_w = op.sw(), a.pad_h = op.ph(), a.pad_w = op.pw_lo();
                     a.relu = int(r.relu);
                 }
                 break;
@@ -601,6 +746,7 @@ int run_launch(const b2_engine* e, const Launch& L, void* const* bindings, cudaS
     void* out = L.out_binding >= 0 ? bindings[L.out_binding] : L.out;
     switch (L.kind) {
         case L_INPUT_CAST:
+            if (L.k == 2) return b2k::launch_input_cast_s2d(static_cast<const float*>(in), out, L.N, L.C, L.H, L.W, s);
             return b2k::launch_input_cast(static_cast<const float*>(in), out, L.N, L.C, L.H, L.W, L.C_phys, half, s);
         case L_OUTPUT_CAST:
             return b2k::launch_output_cast(in, static_cast<float*>(out), L.N, L.C, L.H, L.W, L.C_phys, half, s);
@@ -765,6 +911,7 @@ int b2_context_create(b2_engine* e, b2_context** out) {
     c->force_stages = env_int("B2_FORCE_STAGES", 0);
     c->force_splits = env_int("B2_FORCE_SPLITS", 0);
     c->pdl_trigger = env_int("B2_PDL_TRIGGER", 1);
+    c->autotune = env_int("B2_AUTOTUNE", 4);
     if (getenv("B2_PDL")) b2k::set_pdl(env_int("B2_PDL", 1) != 0);
     void* p = nullptr;
     if (cudaMalloc(&p, kMaxSplitTiles * sizeof(int)) != cudaSuccess || cudaMemset(p, 0, kMaxSplitTiles * sizeof(int)) != cudaSuccess) {
@@ -816,6 +963,7 @@ int b2_context_set_option(b2_context* c, const char* key, int value) {
     else if (k == "stages") c->force_stages = value;
     else if (k == "splits") c->force_splits = value;
     else if (k == "pdl_trigger") c->pdl_trigger = value;
+    else if (k == "autotune") c->autotune = value;
     else return fail(B2_EINVAL, "unknown option '%s'", key);
     drop_cached(c);
     return B2_OK;
@@ -902,6 +1050,31 @@ static const Launch* get_launch(b2_context* c, int batch, int i) {
     if (i < 0 || i >= int(plan->launches.size())) return nullptr;
     return &plan->launches[i];
 }
+// Debug aid (not part of the drop-in surface): run launch `i` of the plan `reps` times back to back on `stream`
+// with per-CTA phase timestamps enabled; `stamps` receives 16 int64 per CTA of the LAST repetition.
+int b2_context_debug_conv_timing(b2_context* c, int batch, int i, int reps, b2_stream_t stream_, long long* stamps,
+                                 int cap_ctas, int* n_ctas) {
+    Plan* plan = nullptr;
+    if (!c || build_plan(c, batch, &plan)) return fail(B2_EINVAL, "no plan");
+    if (i < 0 || i >= int(plan->launches.size()) || plan->launches[i].kind != L_CONV_TC) return fail(B2_EINVAL, "not a tcgen05 conv launch");
+    b2k::ConvLaunch cl = plan->launches[i].conv;
+    const int ctas = cl.grid_m * cl.grid_n * cl.args.splits;
+    if (n_ctas) *n_ctas = ctas;
+    if (ctas > cap_ctas) return fail(B2_EINVAL, "stamp buffer too small (%d CTAs)", ctas);
+    long long* d = nullptr;
+    B2_CUDA(cudaMalloc(&d, size_t(ctas) * 16 * sizeof(long long)));
+    cudaMemset(d, 0, size_t(ctas) * 16 * sizeof(long long));
+    cl.args.dbg = d;
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    int rc = 0;
+    for (int r = 0; r < reps && !rc; ++r) rc = b2k::launch_conv_f16_tcgen05(cl, s);
+    cudaError_t se = cudaStreamSynchronize(s);
+    if (!rc && se == cudaSuccess) cudaMemcpy(stamps, d, size_t(ctas) * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (rc || se != cudaSuccess) return fail(B2_ECUDA, "debug launch failed: %s", cudaGetErrorString(rc ? cudaError_t(rc) : se));
+    return B2_OK;
+}
+
 const char* b2_context_launch_name(b2_context* c, int batch, int i) {
     static thread_local std::string s;
     const Launch* L = get_launch(c, batch, i);

@@ -208,6 +208,16 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN;
     const int m0 = blockIdx.y * 128;
+    long long* dbg = p.dbg ? p.dbg + 16ll * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+    if (dbg && threadIdx.x == 0) {
+        dbg[0] = clock64();
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        dbg[8] = static_cast<long long>(gt);
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        dbg[10] = smid;
+    }
     const int kb_begin = blockIdx.z * p.kb_per_split;
     const int kb_end = min(p.num_kblocks, kb_begin + p.kb_per_split);
     const int nk = kb_end - kb_begin;
@@ -225,13 +235,16 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         fence_proxy_async();
     }
     if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    if (warp == 3)
-        for (int i = lane; i < BN; i += 32) s_bias[i] = __ldg(p.bias + n0 + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 3) {  // bias -> smem while the pipeline spins up; published by the pre-epilogue barrier
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) s_bias[lane + 32 * i] = __ldg(p.bias + n0 + lane + 32 * i);
+    }
     if (p.pdl_trigger == 0) pdl_launch_dependents();
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
     auto stage_bytes = [&](int kb) -> uint32_t {
         if (KB == 64) return Cfg::A_STAGE + Cfg::B_STAGE;
@@ -260,8 +273,8 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 p0 = rem / p.Wo;
                 q0 = rem - p0 * p.Wo;
             }
-            const int base_w = q0 * p.stride - p.pad;
-            const int base_h = p0 * p.stride - p.pad;
+            const int base_w = q0 * p.stride_w - p.pad_w;
+            const int base_h = p0 * p.stride_h - p.pad_h;
             auto load_a = [&](int kb, int s) {
                 uint8_t* a_dst = sA + s * Cfg::A_STAGE;
                 if (KB == 64) {
@@ -294,6 +307,7 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 load_b(kb_begin + i, i);
             }
             pdl_wait();
+            if (dbg) dbg[2] = clock64();
             for (int i = 0; i < npre; ++i) load_a(kb_begin + i, i);
             for (int i = npre; i < nk; ++i) {
                 const int s = i % STAGES;
@@ -313,6 +327,7 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const uint32_t ph = (i / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
+                if (dbg && i == 0) dbg[3] = clock64();
                 const uint32_t a_addr = smem_u32(sA + s * Cfg::A_STAGE);
                 const uint32_t b_addr = smem_u32(sB + s * Cfg::B_STAGE);
                 if (KB == 64) {
@@ -334,6 +349,7 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
             }
             umma_commit(accum_bar);  // accumulator complete
+            if (dbg) dbg[4] = clock64();
         }
         __syncwarp();
     }
@@ -357,6 +373,8 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    __syncthreads();  // s_bias visible; every role has left its loop
+    if (dbg && threadIdx.x == 64) dbg[5] = clock64();
     if (p.pdl_trigger == 1) pdl_launch_dependents();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
 
@@ -419,9 +437,9 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             for (int q = 0; q < 8; ++q)
                 __stcg(reinterpret_cast<uint4*>(mine + g * 32) + q, make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
         }
-        __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence();  // cumulative: orders the whole CTA's partial-tile stores before the arrival
             const int prev = atomicAdd(p.tile_counters + tile, 1);
             const uint32_t last = (prev == p.splits - 1) ? 1u : 0u;
             if (last) p.tile_counters[tile] = 0;  // re-arm for the next launch
@@ -458,9 +476,16 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
         }
     }
+    if (dbg && threadIdx.x == 64) dbg[6] = clock64();
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (dbg && threadIdx.x == 64) {
+        dbg[7] = clock64();
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        dbg[9] = static_cast<long long>(gt);
+    }
 }
 
 static bool g_use_pdl = true;
@@ -582,14 +607,14 @@ __global__ void conv_simt_kernel(SimtConvArgs a) {
     const T* in = reinterpret_cast<const T*>(a.in);
     const T* w = reinterpret_cast<const T*>(a.w) + static_cast<size_t>(co) * a.taps_phys * a.Cin_phys;
     acc_t acc = 0;
-    for (int r = 0; r < a.k; ++r) {
-        const int hi = ho * a.stride - a.pad + r;
+    for (int r = 0; r < a.kh; ++r) {
+        const int hi = ho * a.stride_h - a.pad_h + r;
         if (hi < 0 || hi >= a.H) continue;
-        for (int s = 0; s < a.k; ++s) {
-            const int wi = wo * a.stride - a.pad + s;
+        for (int s = 0; s < a.kw; ++s) {
+            const int wi = wo * a.stride_w - a.pad_w + s;
             if (wi < 0 || wi >= a.W) continue;
             const T* ip = in + ((static_cast<size_t>(n) * a.H + hi) * a.W + wi) * a.Cin_phys;
-            const T* wp = w + static_cast<size_t>(r * a.k + s) * a.Cin_phys;
+            const T* wp = w + static_cast<size_t>(r * a.kw + s) * a.Cin_phys;
             for (int c = 0; c < a.Cin; ++c)
                 acc += static_cast<acc_t>(to_f(ip[c])) * static_cast<acc_t>(to_f(wp[c]));
         }
@@ -658,6 +683,42 @@ int launch_input_cast(const float* src, void* dst, int N, int C, int H, int W, i
         B2_LAUNCH_RC = launch_kernel(input_cast_kernel<__half>, dim3(blocks), dim3(threads), 0, stream, false, src, reinterpret_cast<__half*>(dst), N, C, H * W, C_phys);
     else
         B2_LAUNCH_RC = launch_kernel(input_cast_kernel<float>, dim3(blocks), dim3(threads), 0, stream, false, src, reinterpret_cast<float*>(dst), N, C, H * W, C_phys);
+    return B2_LAUNCH_RC;
+}
+
+// fp32 NCHW -> fp16 [N, H, W/2, 8], channel = dw*4 + c: one 16-byte store per PAIR of input pixels
+__global__ void input_cast_s2d_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int N, int C, int H, int W) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int W2 = W >> 1;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= static_cast<long long>(N) * H * W2) return;
+    const int w2 = static_cast<int>(idx % W2);
+    const long long t = idx / W2;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    const float* s = src + (static_cast<size_t>(n) * C * H + h) * W + 2 * w2;
+    float f[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float2 v = make_float2(0.f, 0.f);
+        if (c < C) v = __ldg(reinterpret_cast<const float2*>(s + static_cast<size_t>(c) * H * W));
+        f[c] = v.x;
+        f[4 + c] = v.y;
+    }
+    uint4 o;
+    __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    dst[idx] = o;
+}
+
+int launch_input_cast_s2d(const float* src, void* dst, int N, int C, int H, int W, cudaStream_t stream) {
+    const long long total = static_cast<long long>(N) * H * (W / 2);
+    const int threads = 256;
+    const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+    B2_LAUNCH_RC = launch_kernel(input_cast_s2d_kernel, dim3(blocks), dim3(threads), 0, stream, false, src,
+                                 reinterpret_cast<uint4*>(dst), N, C, H, W);
     return B2_LAUNCH_RC;
 }
 

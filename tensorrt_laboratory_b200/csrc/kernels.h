@@ -27,7 +27,8 @@ struct ConvArgs {
     int taps_phys;           // taps incl. zero-weight padding (even for KB==8)
     int kw;                  // filter width (tap -> (r, s))
     int HoWo, Wo;            // output plane, output width (m -> (img, p, q))
-    int stride, pad;
+    int stride_h, stride_w;  // conv strides
+    int pad_h, pad_w;        // top / left padding
     int relu;
     int a_mode;              // A_TILED (1x1 stride-1: plain 2-D TMA) or A_IM2COL (TMA im2col mode)
     int splits;              // split-K factor (gridDim.z); 1 = none
@@ -35,6 +36,7 @@ struct ConvArgs {
     float* workspace;        // splits > 1: [tile][split][128][BN] fp32 partial tiles
     int* tile_counters;      // splits > 1: one arrival counter per output tile (zero between launches)
     int pdl_trigger;         // 0: release the dependent kernel right after the prologue, 1: after the main loop
+    long long* dbg;          // optional per-CTA phase timestamps (16 x int64 per CTA), nullptr in production
 };
 
 struct ConvLaunch {
@@ -67,13 +69,15 @@ struct SimtConvArgs {
     const void* residual;  // NHWC out-shaped or nullptr
     void* out;             // NHWC [N,Ho,Wo,Cout_phys]
     int N, H, W, Cin, Cin_phys, Ho, Wo, Cout, Cout_phys;
-    int k, taps_phys, stride, pad, relu;
+    int kh, kw, taps_phys, stride_h, stride_w, pad_h, pad_w, relu;
 };
 int launch_conv_simt(const SimtConvArgs& a, bool half_storage, cudaStream_t stream);
 
 // fp32 NCHW binding -> NHWC activations (zero-filled channel padding)
 int launch_input_cast(const float* src, void* dst, int N, int C, int H, int W, int C_phys,
                       bool half_storage, cudaStream_t stream);
+// fp32 NCHW binding -> fp16 [N, H, W/2, 8] with channel = dw*4 + c (horizontal space-to-depth, C <= 4)
+int launch_input_cast_s2d(const float* src, void* dst, int N, int C, int H, int W, cudaStream_t stream);
 // NHWC activations -> fp32 NCHW binding
 int launch_output_cast(const void* src, float* dst, int N, int C, int H, int W, int C_phys,
                        bool half_storage, cudaStream_t stream);

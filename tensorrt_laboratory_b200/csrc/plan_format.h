@@ -48,10 +48,15 @@ struct OpRec {  // 176 bytes
     uint32_t type;
     int32_t in, res, out;  // tensor indices (-1 = none)
     int32_t binding;       // cast ops: binding index
-    uint32_t k, stride, pad_, relu, ceil_mode;
+    uint32_t k, stride, pad_, relu;
+    uint32_t ceil_mode;    // pools: Caffe ceil mode.  convs: algorithmic K (Cin*kh*kw of the ORIGINAL conv) when the
+                           // builder re-expressed the layer (0 = cin*taps)
     uint32_t cin, cout, cin_phys, cout_phys, taps, taps_phys;
     uint64_t w_off, w_bytes, b_off, b_bytes;  // payload-relative
-    uint8_t pad[16];
+    // rectangular / anisotropic convs (0 = square: kw=k, stride_w=stride, pad_w_*=pad_).  `k`, `stride`, `pad_`
+    // then describe the H direction.  INPUT_CAST: k = horizontal space-to-depth factor (0/1 = none, 2 = pack pixel
+    // pairs into channels [dw*4 + c]).
+    uint32_t kw, stride_w, pad_w_lo, pad_w_hi;
 };
 struct BindingRec {  // 128 bytes
     char name[64];

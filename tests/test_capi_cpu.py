@@ -93,24 +93,55 @@ def test_no_device_means_loud_failure_not_fallback(lib):
 
 def test_builder_layouts():
     net, wts, low = helpers.conv_case(3, 8, 8, 64, 7, 2, 3)
-    blob = builder.build_plan(low, builder.PREC_FP16, 2)
+    # plain layout (stem re-expression off): channels padded to 8, taps padded to an even count
+    blob = builder.build_plan(low, builder.PREC_FP16, 2, stem_s2d=False)
     hdr = struct.unpack_from("<8sIIIIIIQQ", blob, 0)
     assert hdr[0] == b"B2ENGINE" and hdr[2] == builder.PREC_FP16 and hdr[3] == 2
     n_t, n_o, n_b = hdr[4], hdr[5], hdr[6]
     assert (n_t, n_o, n_b) == (2, 3, 2)  # data, conv | cast, conv, cast | data, conv
     op_off = 128 + n_t * 96 + 176  # second op record = the conv
-    rec = struct.unpack_from("<64sIiiiiIIIIIIIIIIIQQQQ", blob, op_off)
+    fmt = "<64sIiiiiIIIIIIIIIIIQQQQIIII"
+    rec = struct.unpack_from(fmt, blob, op_off)
     assert rec[1] == builder.OP_CONV
     k, cin, cout, cin_p, cout_p, taps, taps_p = rec[6], rec[11], rec[12], rec[13], rec[14], rec[15], rec[16]
-    assert (k, cin, cout, cin_p, cout_p, taps, taps_p) == (7, 3, 64, 8, 64, 49, 50)  # C padded to 8, taps to even
+    assert (k, cin, cout, cin_p, cout_p, taps, taps_p) == (7, 3, 64, 8, 64, 49, 50)
     w_off, w_bytes = rec[17], rec[18]
-    assert w_bytes == 64 * 50 * 8 * 2
+    assert w_bytes == 64 * 50 * 8 * 2 and rec[21:25] == (0, 0, 0, 0)
     payload = hdr[7]
     W = np.frombuffer(blob, np.float16, 64 * 50 * 8, payload + w_off).reshape(64, 50, 8)
     assert np.all(W[:, 49, :] == 0) and np.all(W[:, :, 3:] == 0)
     np.testing.assert_array_equal(W[:, :49, :3], low["ops"][0]["W"].reshape(64, 49, 3).astype(np.float16))
+    # default fp16 layout: the stride-2 stem runs on a horizontally space-to-depth packed input (7x4 taps x 8 ch)
+    blob = builder.build_plan(low, builder.PREC_FP16, 2)
+    cast = struct.unpack_from(fmt, blob, 128 + n_t * 96)
+    rec = struct.unpack_from(fmt, blob, op_off)
+    assert cast[1] == builder.OP_INPUT_CAST and cast[6] == 2
+    assert (rec[6], rec[7], rec[8], rec[11], rec[13], rec[15], rec[16]) == (7, 2, 3, 8, 8, 28, 28)
+    assert rec[10] == 3 * 49  # algorithmic K of the original conv, for FLOP accounting
+    assert rec[21:25] == (4, 1, 2, 1)  # kw, stride_w, pad_w_lo, pad_w_hi
+    t0 = struct.unpack_from("<64sIIIIIi", blob, 128)
+    assert t0[2:6] == (8, 4, 8, 8)  # tensor `data`: h=8, w=8/2, c=8, c_phys=8
     assert builder.phys_channels(3, builder.PREC_FP16) == 8 and builder.phys_channels(1000, builder.PREC_FP16) == 1024
     assert builder.phys_channels(3, builder.PREC_FP32) == 3
+
+
+def test_stem_space_to_depth_is_exact():
+    """7x7/s2 conv on (N,3,H,W)  ==  7x4/s(2,1) conv on the pixel-pair packed input (N,8,H,W/2)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(0)
+    for k, pad, w_in in ((7, 3, 16), (3, 1, 12), (5, 2, 10)):
+        W = rng.standard_normal((5, k, k, 3)).astype(np.float32)
+        x = rng.standard_normal((2, 3, 14, w_in)).astype(np.float32)
+        ref = F.conv2d(torch.from_numpy(x), torch.from_numpy(W).permute(0, 3, 1, 2).contiguous(), stride=2, padding=pad).numpy()
+        W2, kw2, plo, phi = builder.stem_s2d_transform(W, k, pad, w_in)
+        X2 = np.zeros((2, 8, 14, w_in // 2), np.float32)
+        for dw in range(2):
+            X2[:, dw * 4:dw * 4 + 3] = x[:, :, :, dw::2]
+        xp = F.pad(torch.from_numpy(X2), (plo, phi, pad, pad))
+        got = F.conv2d(xp, torch.from_numpy(W2).permute(0, 3, 1, 2).contiguous(), stride=(2, 1)).numpy()
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, atol=1e-5)
 
 
 def test_cpp_core_unit_tests(tmp_path):

@@ -63,14 +63,15 @@ def test_every_pipeline_depth(gpu, stages):
     _check(128, 28, 128, 3, 1, batch=2, options={"bn": 64, "stages": stages})
 
 
-@pytest.mark.parametrize("splits", [2, 3, 4, 8])
+@pytest.mark.parametrize("splits", [2, 3, 4, 8])  # 8: bn 64 keeps tiles*splits within the workspace bound
 def test_split_k_matches_oracle_and_is_deterministic(gpu, splits):
     # res5-like: M = 2*7*7 = 98 (one ragged tile), K = 4608 -> 72 k-blocks
     opts = {"bn": 64, "stages": 4, "splits": splits}
     a = _check(512, 7, 512, 3, 1, batch=2, options=opts)
     b = _check(512, 7, 512, 3, 1, batch=2, options=opts)
     np.testing.assert_array_equal(a, b)  # fixed-order reduction: bitwise repeatable
-    _check(1024, 14, 256, 1, 1, batch=3, residual=False, options={"bn": 32, "stages": 2, "splits": splits})
+    if splits <= 4:  # 5 m-tiles x 8 n-tiles x splits must stay within the 160-CTA split budget
+        _check(1024, 14, 256, 1, 1, batch=3, residual=False, options={"bn": 32, "stages": 2, "splits": splits})
 
 
 def test_split_k_with_fused_residual(gpu):
