@@ -496,7 +496,7 @@ int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& c
 // Tactic selection, the role TensorRT's builder plays for the reference's engines: time every instantiated
 // (N tile, pipeline depth) on THIS device with the layer's real shapes and keep the fastest.  Runs once per
 // (engine, layer, batch); results are shared by all contexts of the engine.
-int autotune_conv(b2_context* c, const Op& op, int batch, ConvConfig* best_out) {
+int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, ConvConfig* best_out) {
     b2_engine* e = c->e;
     const b2plan::OpRec& r = op.r;
     const Tensor& to = e->tensors[r.out];
@@ -541,29 +541,46 @@ int autotune_conv(b2_context* c, const Op& op, int batch, ConvConfig* best_out) 
         const int tiles = m_tiles * (int(r.cout_phys) / bn);
         for (int sp : split_cands)
         for (int st : stgs) {
+            if (fixed_splits > 0 && sp != fixed_splits) continue;
             if (!b2k::conv_config_exists(bn, kbsz, st)) continue;
             const int kpc = (nkb + sp - 1) / sp;
             if (st > 1 && st / 2 >= kpc) continue;
-            if (sp > 1 && (kbsz != 64 || tiles >= 100 || kpc < 4 || tiles * sp > 160 || (sp - 1) * kpc >= nkb ||
+            if (sp > 1 && (kbsz != 64 || tiles >= 100 || tiles > kMaxSplitTiles / 8 || kpc < 4 || tiles * sp > 160 ||
+                           (sp - 1) * kpc >= nkb ||
                            size_t(tiles) * sp * 128 * bn * 4 > kSplitWorkspaceBytes))
                 continue;  // split-K only where the plain grid leaves SMs idle
             ConvConfig cand{bn, st, sp, 0.0};
-            b2k::ConvLaunch cl;
-            if ((status = make_conv_launch(c, op, batch, cand, &cl))) break;
+            b2k::ConvLaunch cl0;
+            if ((status = make_conv_launch(c, op, batch, cand, &cl0))) break;
+            // concurrent split-K launches must not share arrival counters or partial-tile storage
+            std::vector<b2k::ConvLaunch> cls(ns, cl0);
+            void* tmp_ws = nullptr;
+            if (sp > 1) {
+                const size_t ws_bytes = size_t(tiles) * sp * 128 * bn * 4;
+                if (cudaMalloc(&tmp_ws, ws_bytes * ns) != cudaSuccess) {
+                    cudaGetLastError();
+                    continue;
+                }
+                for (int k = 0; k < ns; ++k) {
+                    cls[k].args.workspace = reinterpret_cast<float*>(static_cast<uint8_t*>(tmp_ws) + ws_bytes * k);
+                    cls[k].args.tile_counters = c->d_counters + k * (kMaxSplitTiles / 8);
+                }
+            }
             int rc = 0;
             for (int i = 0; i < 2 && !rc; ++i)
-                for (int k = 0; k < ns && !rc; ++k) rc = b2k::launch_conv_f16_tcgen05(cl, ss[k]);
+                for (int k = 0; k < ns && !rc; ++k) rc = b2k::launch_conv_f16_tcgen05(cls[k], ss[k]);
             for (int k = 0; k < ns; ++k) cudaStreamSynchronize(ss[k]);
             cudaEventRecord(e0, ss[0]);
             for (int k = 1; k < ns; ++k) cudaStreamWaitEvent(ss[k], e0, 0);
             for (int i = 0; i < iters && !rc; ++i)
-                for (int k = 0; k < ns && !rc; ++k) rc = b2k::launch_conv_f16_tcgen05(cl, ss[k]);
+                for (int k = 0; k < ns && !rc; ++k) rc = b2k::launch_conv_f16_tcgen05(cls[k], ss[k]);
             for (int k = 1; k < ns; ++k) {
                 cudaEventRecord(done[k], ss[k]);
                 cudaStreamWaitEvent(ss[0], done[k], 0);
             }
             cudaEventRecord(e1, ss[0]);
             cudaError_t se = cudaStreamSynchronize(ss[0]);
+            if (tmp_ws) cudaFree(tmp_ws);
             if (rc || se != cudaSuccess) {
                 status = fail(B2_ECUDA, "autotune of %s (bn=%d st=%d) failed: %s", op.name.c_str(), bn, st,
                               cudaGetErrorString(rc ? cudaError_t(rc) : se));
@@ -662,7 +679,26 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                             if (it != e->tuned.end()) cfg = it->second, have = true;
                         }
                         if (!have) {
-                            int rc = autotune_conv(c, op, batch, &cfg);
+                            // The split-K factor fixes the fp32 summation order, so it is chosen ONCE, at max batch,
+                            // and reused for every batch size: an image's result does not depend on its batch.
+                            int splits = 0;
+                            if (batch != e->max_batch) {
+                                ConvConfig top = cfg;
+                                bool have_top = false;
+                                {
+                                    std::lock_guard<std::mutex> lock(e->tune_mutex);
+                                    auto it = e->tuned.find({op_index, e->max_batch});
+                                    if (it != e->tuned.end()) top = it->second, have_top = true;
+                                }
+                                if (!have_top) {
+                                    int rc = autotune_conv(c, op, e->max_batch, 0, &top);
+                                    if (rc) return rc;
+                                    std::lock_guard<std::mutex> lock(e->tune_mutex);
+                                    e->tuned[{op_index, e->max_batch}] = top;
+                                }
+                                splits = top.splits;
+                            }
+                            int rc = autotune_conv(c, op, batch, splits, &cfg);
                             if (rc) return rc;
                             std::lock_guard<std::mutex> lock(e->tune_mutex);
                             e->tuned[{op_index, batch}] = cfg;
