@@ -342,7 +342,13 @@ class InferenceManager : public ::trtlab::Resources {
     int MaxExecConcurrency() const;
     int MaxCopyConcurrency() const;
 
+    // CUDA's current device is per thread and defaults to 0: pipeline stages running on pool threads adopt the
+    // device the manager was created on (one manager per GPU is the multi-GPU topology)
+    int Device() const { return m_Device; }
+    void ActivateDevice() const;
+
   private:
+    int m_Device;
     int m_MaxExecutions;
     int m_MaxBuffers;
     size_t m_HostStackSize;
@@ -394,6 +400,7 @@ struct InferRunner : public AsyncComputeWrapper<void(std::shared_ptr<Bindings>&)
         auto model = m_Model;
         auto resources = m_Resources;
         Workers("pre").enqueue([model, resources, Pre, Post]() mutable {
+            resources->ActivateDevice();
             auto buffers = resources->GetBuffers();
             auto bindings = buffers->CreateBindings(model);
             Pre(*bindings);
@@ -411,11 +418,13 @@ struct InferRunner : public AsyncComputeWrapper<void(std::shared_ptr<Bindings>&)
     static void EnqueueStatic(std::shared_ptr<InferenceManager> resources, std::shared_ptr<Bindings> bindings,
                               std::shared_ptr<AsyncCompute<T>> Post) {
         resources->AcquireThreadPool("cuda").enqueue([resources, bindings, Post]() mutable {
+            resources->ActivateDevice();
             bindings->CopyToDevice(bindings->InputBindings());                     // H2D
             auto trt_ctx = resources->GetExecutionContext(bindings->GetModel());   // may block on 2 pools
             trt_ctx->Infer(bindings);                                              // forward, async
             bindings->CopyFromDevice(bindings->OutputBindings());                  // D2H
-            resources->AcquireThreadPool("post").enqueue([bindings, trt_ctx, Post]() mutable {
+            resources->AcquireThreadPool("post").enqueue([resources, bindings, trt_ctx, Post]() mutable {
+                resources->ActivateDevice();
                 trt_ctx->Synchronize();
                 trt_ctx.reset();  // returns both pool tokens
                 bindings->Synchronize();

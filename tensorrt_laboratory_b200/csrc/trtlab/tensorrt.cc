@@ -307,14 +307,20 @@ void ExecutionContext::Reset() { m_Context.reset(); }  // inference_manager.cc:2
 
 // ---- InferenceManager ----------------------------------------------------------------------------------
 InferenceManager::InferenceManager(int max_executions, int max_buffers)  // inference_manager.cc:59-69
-    : m_MaxExecutions(max_executions), m_MaxBuffers(max_buffers ? max_buffers : max_executions * 2), m_HostStackSize(0),
+    : m_Device(0), m_MaxExecutions(max_executions), m_MaxBuffers(max_buffers ? max_buffers : max_executions * 2), m_HostStackSize(0),
       m_DeviceStackSize(0), m_ActivationsSize(0), m_Buffers{nullptr}, m_ExecutionContexts{nullptr}, m_ActiveRuntime{nullptr} {
+    if (cudaGetDevice(&m_Device) != cudaSuccess) {
+        cudaGetLastError();
+        m_Device = 0;
+    }
     TRTLAB_LOG_INFO << "-- Initialzing TensorRT Resource Manager --";
     TRTLAB_LOG_INFO << "Maximum Execution Concurrency: " << m_MaxExecutions;
     TRTLAB_LOG_INFO << "Maximum Copy Concurrency: " << m_MaxBuffers;
 }
 
 InferenceManager::~InferenceManager() { JoinAllThreads(); }
+
+void InferenceManager::ActivateDevice() const { TRT_CHECK_CUDA(cudaSetDevice(m_Device)); }
 
 int InferenceManager::MaxExecConcurrency() const { return m_MaxExecutions; }
 int InferenceManager::MaxCopyConcurrency() const { return m_MaxBuffers; }
