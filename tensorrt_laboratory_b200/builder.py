@@ -125,8 +125,11 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
             and readers[0]["stride"] == 2 and cin <= 4 and win % 2 == 0 and lowered["input"] not in outputs
             and readers[0]["k"] >= 3):
         s2d_op = readers[0]
-        tensors[t_in].update(w=win // 2, c=8, c_phys=8)
-        ops[0]["k"] = 2
+        _, _, s2d_lo, s2d_hi = stem_s2d_transform(s2d_op["W"], s2d_op["k"], s2d_op["pad"], win)
+        # the horizontal padding is made PHYSICAL (zero pixels written by the cast), so the conv has pad_w = 0 and its
+        # kw taps are contiguous in memory: the engine reads a whole filter row as one 64-byte TMA "pixel"
+        tensors[t_in].update(w=win // 2 + s2d_lo + s2d_hi, c=8, c_phys=8)
+        ops[0].update(k=2, pad=s2d_lo, stride=s2d_hi)
 
     for op in lowered["ops"]:
         t = op["type"]
@@ -144,7 +147,7 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
             if op is s2d_op:
                 Wsrc, kw2, pad_lo, pad_hi = stem_s2d_transform(op["W"], k, op["pad"], win)
                 cin_eff, taps = 8, k * kw2
-                extra = dict(kw=kw2, stride_w=1, pad_w_lo=pad_lo, pad_w_hi=pad_hi, ceil_mode=op["cin"] * k * k)
+                extra = dict(kw=kw2, stride_w=1, pad_w_lo=0, pad_w_hi=0, ceil_mode=op["cin"] * k * k)
             taps_phys = _roundup(taps, 2) if (precision == PREC_FP16 and cin_phys == 8) else taps
             W = np.zeros((cout_phys, taps_phys, cin_phys), dtype=np.float32)
             W[:op["cout"], :taps, :cin_eff] = Wsrc.reshape(op["cout"], taps, cin_eff)

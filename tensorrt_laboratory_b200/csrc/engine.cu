@@ -205,6 +205,7 @@ struct b2_context {
     int force_stages = 0;
     int force_splits = 0;
     int pdl_trigger = 1;
+    int no_fold = 0;    // 1: run the stem through the generic 8-channel tap path instead of the row-folded one
     int autotune = 4;  // 0 off (cost model), 1 latency mode, N>=2 throughput mode over N streams
 };
 
@@ -371,11 +372,14 @@ int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t out
     return B2_OK;
 }
 
-int make_map_im2col(CUtensorMap* map, const void* base, int C, int W, int H, int N, int kh, int kw, int stride_h,
-                    int stride_w, int pad_h, int pad_w_lo, int pad_w_hi, uint32_t channels_per_pixel,
-                    uint32_t pixels_per_column, CUtensorMapSwizzle swz) {
+// `pix_bytes` / `row_bytes` / `img_bytes`: global strides of the W, H, N modes.  The row-folded stem passes a pixel
+// stride SMALLER than the C extent (overlapping windows): each "pixel" of the map is then kw real pixels.
+int make_map_im2col(CUtensorMap* map, const void* base, int C, int W, int H, int N, uint64_t pix_bytes,
+                    uint64_t row_bytes, uint64_t img_bytes, int kh, int kw, int stride_h, int stride_w, int pad_h,
+                    int pad_w_lo, int pad_w_hi, uint32_t channels_per_pixel, uint32_t pixels_per_column,
+                    CUtensorMapSwizzle swz) {
     cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
-    cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
+    cuuint64_t strides[3] = {pix_bytes, row_bytes, img_bytes};
     // fprop bounding box: base pixel positions run over [-pad, dim - 1 + pad - (k-1)] (dilation 1)
     int lower[2] = {-pad_w_lo, -pad_h};                            // (W, H) order
     int upper[2] = {pad_w_hi - (kw - 1), pad_h - (kh - 1)};
@@ -388,7 +392,7 @@ int make_map_im2col(CUtensorMap* map, const void* base, int C, int W, int H, int
                     W, H, N, kh, kw, stride_h, stride_w, pad_h, pad_w_lo, pad_w_hi);
     // Driver workaround mirrored from CUTLASS (cute/atom/copy_traits_sm90_im2col.hpp): drivers <= 13.1 set a
     // descriptor bit that misbehaves for tensors smaller than 128 KiB.
-    if (g_driver_version <= 13010 && size_t(C) * W * H * N * 2 < 131072)
+    if (g_driver_version <= 13010 && img_bytes * uint64_t(N) < 131072)
         reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
     return B2_OK;
 }
@@ -438,6 +442,23 @@ ConvConfig pick_conv_config(int M, int cout_phys, int kblocks, int kb, bool resi
     return best;
 }
 
+// Row-folded stem: an 8-channel input whose kw taps are contiguous in memory (stride_w 1, no W padding left to
+// resolve) is read as ONE 64-byte "pixel" per filter row through an overlapping pixel stride.
+bool conv_is_row_folded(const b2_context* c, const Op& op) {
+    const b2plan::OpRec& r = op.r;
+    return !c->no_fold && r.cin_phys == 8 && op.kw() * 8 * 2 == 64 && op.sw() == 1 && op.pw_lo() == 0 && op.pw_hi() == 0;
+}
+int conv_kb(const b2_context* c, const Op& op) {
+    if (op.r.cin_phys % 64 == 0) return 64;
+    return conv_is_row_folded(c, op) ? 32 : 8;
+}
+int conv_num_kblocks(const b2_context* c, const Op& op) {
+    const b2plan::OpRec& r = op.r;
+    if (r.cin_phys % 64 == 0) return int(r.taps) * (int(r.cin_phys) / 64);
+    if (conv_is_row_folded(c, op)) return (op.kh() + 1) / 2;  // two filter rows (2 x 32 K) per 64-wide k-block
+    return (int(r.taps_phys) + 7) / 8;
+}
+
 // Fill a ConvLaunch (kernel arguments + TMA tensor maps) for one conv op under a given configuration.
 int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& cfg, b2k::ConvLaunch* out) {
     b2_engine* e = c->e;
@@ -448,11 +469,12 @@ int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& c
     const uint8_t* w = e->d_payload + r.w_off;
     const int M = batch * int(to.h) * int(to.w);
     const bool kb64 = r.cin_phys % 64 == 0;
+    const bool fold = conv_is_row_folded(c, op);
     b2k::ConvLaunch& cl = *out;
     memset(&cl, 0, sizeof cl);
-    cl.kb = kb64 ? 64 : 8;
+    cl.kb = conv_kb(c, op);
     cl.grid_m = (M + 127) / 128;
-    const int nkb = kb64 ? int(r.taps) * (int(r.cin_phys) / 64) : (int(r.taps_phys) + 7) / 8;
+    const int nkb = conv_num_kblocks(c, op);
     cl.bn = cfg.bn;
     cl.stages = cfg.stages;
     cl.grid_n = int(r.cout_phys) / cl.bn;
@@ -467,9 +489,9 @@ int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& c
     a.out = reinterpret_cast<__half*>(tptr(r.out));
     a.M = M;
     a.Cout = int(r.cout_phys);
-    a.taps = int(r.taps);
-    a.taps_phys = int(r.taps_phys);
-    a.kw = op.kw();
+    a.taps = fold ? op.kh() : int(r.taps);            // folded: one "tap" = one filter row of kw*8 K-elements
+    a.taps_phys = fold ? op.kh() : int(r.taps_phys);
+    a.kw = fold ? 1 : op.kw();
     a.cblocks = kb64 ? int(r.cin_phys) / 64 : 1;
     a.num_kblocks = nkb;
     a.HoWo = int(to.h * to.w);
@@ -482,15 +504,28 @@ int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& c
     const bool tiled = r.k == 1 && op.kw() == 1 && r.stride == 1 && op.sw() == 1 && r.pad_ == 0 && op.pw_lo() == 0 &&
                        op.pw_hi() == 0 && kb64 && !c->force_im2col;
     a.a_mode = tiled ? b2k::A_TILED : b2k::A_IM2COL;
-    const CUtensorMapSwizzle swz = kb64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    const CUtensorMapSwizzle swz = kb64 ? CU_TENSOR_MAP_SWIZZLE_128B : (fold ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+    const uint64_t pix = uint64_t(r.cin_phys) * 2, rowb = uint64_t(ti.w) * pix, imgb = uint64_t(ti.h) * rowb;
     int rc;
     if (tiled)
         rc = make_map_2d(&cl.mapA, tptr(r.in), r.cin_phys, uint64_t(M), 64, 128, swz);
+    else if (fold)  // kw pixels x 8 channels = 32 contiguous K-elements per window; windows advance by ONE pixel
+        rc = make_map_im2col(&cl.mapA, tptr(r.in), int(r.cin_phys) * op.kw(), int(ti.w) - op.kw() + 1, int(ti.h), batch, pix,
+                             rowb, imgb, op.kh(), 1, op.sh(), 1, op.ph(), 0, 0, 32, 128, swz);
     else
-        rc = make_map_im2col(&cl.mapA, tptr(r.in), int(r.cin_phys), int(ti.w), int(ti.h), batch, op.kh(), op.kw(), op.sh(),
-                             op.sw(), op.ph(), op.pw_lo(), op.pw_hi(), uint32_t(cl.kb), 128, swz);
+        rc = make_map_im2col(&cl.mapA, tptr(r.in), int(r.cin_phys), int(ti.w), int(ti.h), batch, pix, rowb, imgb, op.kh(),
+                             op.kw(), op.sh(), op.sw(), op.ph(), op.pw_lo(), op.pw_hi(), uint32_t(cl.kb), 128, swz);
     if (rc) return rc;
-    return make_map_2d(&cl.mapB, w, uint64_t(r.taps_phys) * r.cin_phys, r.cout_phys, uint32_t(cl.kb), uint32_t(cl.bn), swz);
+    rc = make_map_2d(&cl.mapB, w, uint64_t(r.taps_phys) * r.cin_phys, r.cout_phys, uint32_t(cl.kb), uint32_t(cl.bn), swz);
+    if (rc) return rc;
+    // epilogue maps: 128-row x min(64, BN)-column boxes, 128B (or 64B for BN=32) swizzle = conflict-free staging
+    const uint32_t ow = cl.bn >= 64 ? 64 : 32;
+    const CUtensorMapSwizzle oswz = cl.bn >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    rc = make_map_2d(&cl.mapOut, tptr(r.out), r.cout_phys, uint64_t(M), ow, 128, oswz);
+    if (rc) return rc;
+    if (r.res >= 0) rc = make_map_2d(&cl.mapRes, tptr(r.res), r.cout_phys, uint64_t(M), ow, 128, oswz);
+    else cl.mapRes = cl.mapOut;
+    return rc;
 }
 
 // Tactic selection, the role TensorRT's builder plays for the reference's engines: time every instantiated
@@ -501,9 +536,8 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, Conv
     const b2plan::OpRec& r = op.r;
     const Tensor& to = e->tensors[r.out];
     const int M = batch * int(to.h) * int(to.w);
-    const bool kb64 = r.cin_phys % 64 == 0;
-    const int kbsz = kb64 ? 64 : 8;
-    const int nkb = kb64 ? int(r.taps) * (int(r.cin_phys) / 64) : (int(r.taps_phys) + 7) / 8;
+    const int kbsz = conv_kb(c, op);
+    const int nkb = conv_num_kblocks(c, op);
     // c->autotune == 1: latency mode (one stream).  >= 2: throughput mode -- the candidate is launched on that
     // many streams at once, which is how the kernels meet each other when several ExecutionContexts overlap
     // (BASELINE config: 4 contexts); deep pipelines that win alone can lose here because they hog shared memory.
@@ -631,11 +665,13 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                 L.out = tptr(r.out);
                 L.C = t.c, L.H = t.h, L.W = t.w, L.C_phys = t.c_phys;
                 L.k = int(r.k);  // 2: horizontal space-to-depth (tensor is [H, W/2, 8]; binding is [C, H, W])
-                if (r.k == 2) {
+                if (r.k == 2) {  // pad_ / stride = zero pixels written left / right of every packed row
                     const Binding& b = e->bindings[r.binding];
-                    if (!half || b.nd != 3 || b.dims[0] > 4 || t.c_phys != 8 || int(t.w) * 2 != b.dims[2] || int(t.h) != b.dims[1])
+                    if (!half || b.nd != 3 || b.dims[0] > 4 || t.c_phys != 8 || int(t.h) != b.dims[1] ||
+                        int(t.w) != b.dims[2] / 2 + int(r.pad_) + int(r.stride) || b.dims[2] % 2)
                         return fail(B2_EINVAL, "input cast %s: inconsistent space-to-depth geometry", op.name.c_str());
                     L.C = b.dims[0], L.W = b.dims[2];
+                    L.pad = int(r.pad_), L.stride = int(r.stride);
                 }
                 L.bytes = double(batch) * t.h * t.w * (t.c * 4.0 + t.c_phys * elt);
                 break;
@@ -663,8 +699,8 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                                    (kb64 || r.taps_phys % 2 == 0);
                 if (tc_ok) {
                     L.kind = L_CONV_TC;
-                    const int kbsz = kb64 ? 64 : 8;
-                    const int nkb = kb64 ? int(r.taps) * (int(r.cin_phys) / 64) : (int(r.taps_phys) + 7) / 8;
+                    const int kbsz = conv_kb(c, op);
+                    const int nkb = conv_num_kblocks(c, op);
                     ConvConfig cfg = pick_conv_config(M, int(r.cout_phys), nkb, kbsz, r.res >= 0, c, true);
                     if (cfg.bn == 0)  // a forced tile that does not divide this layer: fall back to the model
                         cfg = pick_conv_config(M, int(r.cout_phys), nkb, kbsz, r.res >= 0, c, false);
@@ -782,7 +818,7 @@ int run_launch(const b2_engine* e, const Launch& L, void* const* bindings, cudaS
     void* out = L.out_binding >= 0 ? bindings[L.out_binding] : L.out;
     switch (L.kind) {
         case L_INPUT_CAST:
-            if (L.k == 2) return b2k::launch_input_cast_s2d(static_cast<const float*>(in), out, L.N, L.C, L.H, L.W, s);
+            if (L.k == 2) return b2k::launch_input_cast_s2d(static_cast<const float*>(in), out, L.N, L.C, L.H, L.W, L.pad, L.stride, s);
             return b2k::launch_input_cast(static_cast<const float*>(in), out, L.N, L.C, L.H, L.W, L.C_phys, half, s);
         case L_OUTPUT_CAST:
             return b2k::launch_output_cast(in, static_cast<float*>(out), L.N, L.C, L.H, L.W, L.C_phys, half, s);
@@ -1000,6 +1036,7 @@ int b2_context_set_option(b2_context* c, const char* key, int value) {
     else if (k == "splits") c->force_splits = value;
     else if (k == "pdl_trigger") c->pdl_trigger = value;
     else if (k == "autotune") c->autotune = value;
+    else if (k == "no_fold") c->no_fold = value;
     else return fail(B2_EINVAL, "unknown option '%s'", key);
     drop_cached(c);
     return B2_OK;

@@ -172,37 +172,71 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 template <int BN, int STAGES>
 struct ConvCfg {
     static constexpr int A_STAGE = 128 * 64 * 2;  // 16 KiB: 128 rows x 64 K-elements
     static constexpr int B_STAGE = BN * 64 * 2;
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-    static constexpr int BAR_OFF = STAGES * (A_STAGE + B_STAGE);
-    static constexpr int BIAS_OFF = BAR_OFF + 256;
-    static constexpr int SMEM = BIAS_OFF + BN * 4 + 1024 /*alignment slack*/;
+    static constexpr int PIPE_BYTES = STAGES * (A_STAGE + B_STAGE);
+    static constexpr int TILE_BYTES = 128 * BN * 2;  // one fp16 output (or residual) tile
+    static_assert(TILE_BYTES <= PIPE_BYTES, "the output staging tile reuses the pipeline buffers");
 };
+
+// smem: [A stages][B stages][residual tile (optional)][barriers 256 B][bias BN x 4 B]; +1 KiB alignment slack
+__host__ __device__ constexpr int conv_smem_layout_bytes(int bn, int stages, bool residual) {
+    return stages * (128 * 64 * 2 + bn * 64 * 2) + (residual ? 128 * bn * 2 : 0) + 256 + bn * 4 + 1024;
+}
+
+// Byte offset of (row, 16-byte chunk) inside a TMA-swizzled fp16 tile whose rows are ROWB bytes (64 or 128):
+// the hardware XORs the chunk index with the row index (Swizzle<2|3,4,3>), which also makes one-row-per-thread
+// accesses bank-conflict free.
+template <int ROWB>
+__device__ __forceinline__ uint32_t swz_off(int row, int chunk) {
+    if (ROWB == 128) return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
+    return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
 
 template <int BN, int KB, int STAGES>
 __global__ void __launch_bounds__(128)
 conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
                  const ConvArgs p) {
     using Cfg = ConvCfg<BN, STAGES>;
-    constexpr int TPS = 64 / KB;            // TMA sub-tiles (filter taps) per stage; 1 when KB == 64
+    constexpr int TPS = 64 / KB;            // TMA sub-tiles per stage: 1 (KB=64), 2 (KB=32 row-folded stem), 8 (KB=8)
     constexpr int A_SUB = 128 * KB * 2;     // bytes of one A sub-tile
     constexpr int B_SUB = BN * KB * 2;
     constexpr int NG = BN / 32;             // 32-column groups of the accumulator
+    constexpr int OW = BN >= 64 ? 64 : 32;  // columns per output TMA box
+    constexpr int OROWB = OW * 2;           // bytes per staged output row (128 or 64)
+    constexpr int NBOX = BN / OW;
     constexpr uint32_t IDESC = make_idesc_f16(128, BN);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const bool has_res = p.residual != nullptr;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * Cfg::A_STAGE;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+    uint8_t* sOut = smem;                    // output staging reuses the (drained) pipeline buffers
+    uint8_t* sRes = smem + Cfg::PIPE_BYTES;  // residual tile, only when has_res
+    uint8_t* tail = sRes + (has_res ? Cfg::TILE_BYTES : 0);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* res_bar = accum_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
     uint32_t* last_flag = tmem_slot + 1;
-    float* s_bias = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF);
+    float* s_bias = reinterpret_cast<float*>(tail + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -221,16 +255,20 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int kb_begin = blockIdx.z * p.kb_per_split;
     const int kb_end = min(p.num_kblocks, kb_begin + p.kb_per_split);
     const int nk = kb_end - kb_begin;
+    const bool split = p.splits > 1;
 
     // ---------------- prologue: nothing here depends on the previous kernel's output ----------------
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
+        tma_prefetch_desc(&mapOut);
+        if (has_res) tma_prefetch_desc(&mapRes);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(accum_bar, 1);
+        mbar_init(res_bar, 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -246,21 +284,28 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (p.pdl_trigger == 0) pdl_launch_dependents();
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
+    auto sub_tiles = [&](int kb) -> int {  // TMA sub-tiles (filter taps / tap rows) in k-block kb
+        if (KB == 64) return 1;
+        const int n = p.taps_phys - kb * TPS;
+        return n > TPS ? TPS : n;
+    };
     auto stage_bytes = [&](int kb) -> uint32_t {
         if (KB == 64) return Cfg::A_STAGE + Cfg::B_STAGE;
-        int ntaps = p.taps_phys - kb * TPS;
-        ntaps = ntaps > TPS ? TPS : ntaps;
-        return static_cast<uint32_t>(ntaps * (A_SUB + B_SUB));
+        return static_cast<uint32_t>(sub_tiles(kb) * (A_SUB + B_SUB));
     };
     auto load_b = [&](int kb, int s) {  // weights: constant data, legal before pdl_wait()
         uint8_t* b_dst = sB + s * Cfg::B_STAGE;
         if (KB == 64) {
             tma_load_2d(&mapB, &full_bar[s], b_dst, kb * 64, n0);
         } else {
-            int ntaps = p.taps_phys - kb * TPS;
-            ntaps = ntaps > TPS ? TPS : ntaps;
-            for (int t = 0; t < ntaps; ++t) tma_load_2d(&mapB, &full_bar[s], b_dst + t * B_SUB, (kb * TPS + t) * KB, n0);
+            const int nt = sub_tiles(kb);
+            for (int t = 0; t < nt; ++t) tma_load_2d(&mapB, &full_bar[s], b_dst + t * B_SUB, (kb * TPS + t) * KB, n0);
         }
+    };
+    auto load_residual = [&]() {  // residual tile -> smem, same box geometry as the output store
+        mbar_expect_tx(res_bar, Cfg::TILE_BYTES);
+#pragma unroll
+        for (int b = 0; b < NBOX; ++b) tma_load_2d(&mapRes, res_bar, sRes + b * (128 * OROWB), n0 + b * OW, m0);
     };
 
     if (warp == 0) {
@@ -289,9 +334,8 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                            static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
                     }
                 } else {
-                    int ntaps = p.taps_phys - kb * TPS;
-                    ntaps = ntaps > TPS ? TPS : ntaps;
-                    for (int t = 0; t < ntaps; ++t) {
+                    const int nt = sub_tiles(kb);
+                    for (int t = 0; t < nt; ++t) {
                         const int tap = kb * TPS + t;
                         const int tap_a = tap < p.taps ? tap : p.taps - 1;  // padded tap: weights are zero
                         const int r = tap_a / p.kw;
@@ -309,6 +353,7 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             pdl_wait();
             if (dbg) dbg[2] = clock64();
             for (int i = 0; i < npre; ++i) load_a(kb_begin + i, i);
+            if (has_res && !split) load_residual();
             for (int i = npre; i < nk; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
@@ -337,10 +382,20 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         const uint64_t bd = make_smem_desc(b_addr + j * 32, 16, 1024, 2);
                         umma_f16(tmem_base, ad, bd, IDESC, (i > 0 || j > 0) ? 1u : 0u);
                     }
+                } else if (KB == 32) {
+                    // row-folded stem: each sub-tile is one filter row = 32 K-elements in 64-byte swizzled rows
+                    const int nt = sub_tiles(kb_begin + i);
+                    for (int t = 0; t < nt; ++t) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint64_t ad = make_smem_desc(a_addr + t * A_SUB + j * 32, 16, 512, 4);
+                            const uint64_t bd = make_smem_desc(b_addr + t * B_SUB + j * 32, 16, 512, 4);
+                            umma_f16(tmem_base, ad, bd, IDESC, (i > 0 || t > 0 || j > 0) ? 1u : 0u);
+                        }
+                    }
                 } else {
-                    int ntaps = p.taps_phys - (kb_begin + i) * TPS;
-                    ntaps = ntaps > TPS ? TPS : ntaps;
-                    for (int j = 0; j < ntaps / 2; ++j) {  // one K=16 step = two 8-channel taps
+                    const int nt = sub_tiles(kb_begin + i);
+                    for (int j = 0; j < nt / 2; ++j) {  // one K=16 step = two 8-channel taps
                         const uint64_t ad = make_smem_desc(a_addr + 2 * j * A_SUB, A_SUB, 128, 0);
                         const uint64_t bd = make_smem_desc(b_addr + 2 * j * B_SUB, B_SUB, 128, 0);
                         umma_f16(tmem_base, ad, bd, IDESC, (i > 0 || j > 0) ? 1u : 0u);
@@ -354,38 +409,31 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         __syncwarp();
     }
 
-    // ================= epilogue: TMEM -> registers -> bias/residual/ReLU -> fp16 NHWC =================
-    pdl_wait();  // residual reads and every global write below depend on the previous kernel
+    // ====== epilogue: TMEM -> registers -> bias/residual/ReLU -> fp16 -> swizzled smem tile -> TMA store ======
+    pdl_wait();  // every global access below depends on the previous kernel
     const int row = warp * 32 + lane;
-    const int m = m0 + row;
-    const bool valid = m < p.M;
-    const size_t off = static_cast<size_t>(m) * p.Cout + n0;
-    const bool split = p.splits > 1;
 
-    // residual prefetch: the loads overlap the tail of the MMA pipeline
-    uint4 res[NG * 4];
-    const bool has_res = p.residual != nullptr;
-    if (has_res && valid && !split) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
-#pragma unroll
-        for (int i = 0; i < NG * 4; ++i) res[i] = __ldg(rp + i);
-    }
-
-    mbar_wait(accum_bar, 0);
+    mbar_wait(accum_bar, 0);  // all MMAs retired: the pipeline buffers are free to become the output staging tile
     tc_fence_after();
-    __syncthreads();  // s_bias visible; every role has left its loop
+    __syncthreads();          // s_bias visible; every role has left its loop
     if (dbg && threadIdx.x == 64) dbg[5] = clock64();
     if (p.pdl_trigger == 1) pdl_launch_dependents();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
 
-    auto finish_group = [&](int g, float (&f)[32]) {  // bias + residual + relu + store for 32 columns
+    // bias + residual + relu for 32 columns of this thread's row, packed into the staging tile
+    auto finish_group = [&](int g, float (&f)[32]) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+            const int col = g * 32 + q * 8;       // column inside the BN-wide tile
+            const int box = col / OW;             // which 64- (or 32-) column TMA box
+            const int chunk = (col % OW) / 8;     // 16-byte chunk inside the box row
+            const uint32_t so = static_cast<uint32_t>(box * (128 * OROWB)) + swz_off<OROWB>(row, chunk);
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = f[q * 8 + i] + s_bias[g * 32 + q * 8 + i];
+            for (int i = 0; i < 8; ++i) v[i] = f[q * 8 + i] + s_bias[col + i];
             if (has_res) {
-                const __half2* r2 = reinterpret_cast<const __half2*>(&res[g * 4 + q]);
+                const uint4 rv = *reinterpret_cast<const uint4*>(sRes + so);
+                const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float2 rf = __half22float2(r2[i]);
@@ -401,11 +449,13 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
             for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-            *reinterpret_cast<uint4*>(p.out + off + g * 32 + q * 8) = o;
+            *reinterpret_cast<uint4*>(sOut + so) = o;
         }
     };
 
+    bool do_store = true;
     if (!split) {
+        if (has_res) mbar_wait(res_bar, 0);
         constexpr int GP = NG >= 2 ? 2 : 1;  // groups per TMEM round trip
 #pragma unroll
         for (int g0 = 0; g0 < NG; g0 += GP) {
@@ -413,14 +463,12 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < GP; ++j) tmem_ld32(taddr + (g0 + j) * 32, acc[j]);
             tmem_wait_ld();
-            if (valid) {
 #pragma unroll
-                for (int j = 0; j < GP; ++j) {
-                    float f[32];
+            for (int j = 0; j < GP; ++j) {
+                float f[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(acc[j][i]);
-                    finish_group(g0 + j, f);
-                }
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(acc[j][i]);
+                finish_group(g0 + j, f);
             }
         }
     } else {
@@ -442,44 +490,49 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             __threadfence();  // cumulative: orders the whole CTA's partial-tile stores before the arrival
             const int prev = atomicAdd(p.tile_counters + tile, 1);
             const uint32_t last = (prev == p.splits - 1) ? 1u : 0u;
-            if (last) p.tile_counters[tile] = 0;  // re-arm for the next launch
+            if (last) {
+                p.tile_counters[tile] = 0;  // re-arm for the next launch
+                if (has_res) load_residual();
+            }
             *last_flag = last;
         }
         __syncthreads();
-        if (*last_flag) {
+        do_store = *last_flag != 0;
+        if (do_store) {
             __threadfence();
-            if (has_res && valid) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+            if (has_res) mbar_wait(res_bar, 0);
 #pragma unroll
-                for (int i = 0; i < NG * 4; ++i) res[i] = __ldg(rp + i);
-            }
-            if (valid) {
+            for (int g = 0; g < NG; ++g) {
+                float f[32];
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    float f[32];
+                for (int i = 0; i < 32; ++i) f[i] = 0.f;
+                for (int sp = 0; sp < p.splits; ++sp) {
+                    const float4* src = reinterpret_cast<const float4*>(ws_tile + static_cast<size_t>(sp) * (128 * BN) +
+                                                                        static_cast<size_t>(row) * BN + g * 32);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = 0.f;
-                    for (int sp = 0; sp < p.splits; ++sp) {
-                        const float4* src = reinterpret_cast<const float4*>(ws_tile + static_cast<size_t>(sp) * (128 * BN) +
-                                                                            static_cast<size_t>(row) * BN + g * 32);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 t = __ldcg(src + q);
-                            f[4 * q] += t.x;
-                            f[4 * q + 1] += t.y;
-                            f[4 * q + 2] += t.z;
-                            f[4 * q + 3] += t.w;
-                        }
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 t = __ldcg(src + q);
+                        f[4 * q] += t.x;
+                        f[4 * q + 1] += t.y;
+                        f[4 * q + 2] += t.z;
+                        f[4 * q + 3] += t.w;
                     }
-                    finish_group(g, f);
                 }
+                finish_group(g, f);
             }
         }
     }
     if (dbg && threadIdx.x == 64) dbg[6] = clock64();
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (threadIdx.x == 0 && do_store) {
+        // rows >= M and nothing else are clipped by the tensor map; one bulk store per 64-column box
+#pragma unroll
+        for (int b = 0; b < NBOX; ++b) tma_store_2d(&mapOut, sOut + b * (128 * OROWB), n0 + b * OW, m0);
+        tma_store_commit_and_wait_read();  // smem must stay alive until the TMA has read it
+    }
     if (dbg && threadIdx.x == 64) {
         dbg[7] = clock64();
         unsigned long long gt;
@@ -510,30 +563,25 @@ static int launch_kernel(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStre
 template <int BN, int KB, int STAGES>
 static int launch_one(const ConvLaunch& L, cudaStream_t stream) {
     dim3 grid(L.grid_n, L.grid_m, L.args.splits);
-    return launch_kernel(conv_f16_tcgen05<BN, KB, STAGES>, grid, dim3(128), ConvCfg<BN, STAGES>::SMEM, stream, true, L.mapA,
-                         L.mapB, L.args);
+    const size_t smem = size_t(conv_smem_layout_bytes(BN, STAGES, L.args.residual != nullptr));
+    return launch_kernel(conv_f16_tcgen05<BN, KB, STAGES>, grid, dim3(128), smem, stream, true, L.mapA, L.mapB, L.mapOut,
+                         L.mapRes, L.args);
 }
 
 template <int BN, int KB, int STAGES>
 static int init_one() {
     return static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 ConvCfg<BN, STAGES>::SMEM));
+                                                 conv_smem_layout_bytes(BN, STAGES, true)));
 }
 
-int conv_smem_bytes(int bn, int stages) { return stages * (128 * 64 * 2 + bn * 64 * 2) + 256 + bn * 4 + 1024; }
-
-bool conv_tile_supported(int bn, int kb, int stages) {
-    if (kb != 64 && kb != 8) return false;
-    if (bn != 32 && bn != 64 && bn != 128) return false;
-    if (stages != 1 && stages != 2 && stages != 4 && stages != 8) return false;
-    return conv_smem_bytes(bn, stages) <= 227 * 1024 && !(bn == 128 && stages == 8);
-}
+int conv_smem_bytes(int bn, int stages) { return conv_smem_layout_bytes(bn, stages, true); }
 
 #define B2_FOR_EACH_CONV(X) \
     X(32, 64, 1) X(32, 64, 2) X(32, 64, 4) X(32, 64, 8) \
     X(64, 64, 1) X(64, 64, 2) X(64, 64, 4) X(64, 64, 8) \
     X(128, 64, 1) X(128, 64, 2) X(128, 64, 4) \
-    X(32, 8, 2) X(32, 8, 4) X(64, 8, 2) X(64, 8, 4) X(64, 8, 8) X(128, 8, 4)
+    X(32, 8, 2) X(32, 8, 4) X(64, 8, 2) X(64, 8, 4) X(64, 8, 8) X(128, 8, 4) \
+    X(32, 32, 2) X(32, 32, 4) X(64, 32, 1) X(64, 32, 2) X(64, 32, 4) X(128, 32, 2) X(128, 32, 4)
 
 int init_conv_kernels() {
     int e = 0;
@@ -686,39 +734,45 @@ int launch_input_cast(const float* src, void* dst, int N, int C, int H, int W, i
     return B2_LAUNCH_RC;
 }
 
-// fp32 NCHW -> fp16 [N, H, W/2, 8], channel = dw*4 + c: one 16-byte store per PAIR of input pixels
-__global__ void input_cast_s2d_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int N, int C, int H, int W) {
+// fp32 NCHW -> fp16 [N, H, pad_l + W/2 + pad_r, 8], channel = dw*4 + c: one 16-byte store per PAIR of input pixels;
+// the pad_l / pad_r border pixels are written as zeros (the stem's horizontal padding made physical)
+__global__ void input_cast_s2d_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int N, int C, int H, int W,
+                                      int pad_l, int pad_r) {
     pdl_launch_dependents();
     pdl_wait();
     const int W2 = W >> 1;
+    const int Wp = W2 + pad_l + pad_r;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (idx >= static_cast<long long>(N) * H * W2) return;
-    const int w2 = static_cast<int>(idx % W2);
-    const long long t = idx / W2;
+    if (idx >= static_cast<long long>(N) * H * Wp) return;
+    const int wp = static_cast<int>(idx % Wp);
+    const long long t = idx / Wp;
     const int h = static_cast<int>(t % H);
     const int n = static_cast<int>(t / H);
-    const float* s = src + (static_cast<size_t>(n) * C * H + h) * W + 2 * w2;
-    float f[8];
+    const int w2 = wp - pad_l;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (w2 >= 0 && w2 < W2) {
+        const float* s = src + (static_cast<size_t>(n) * C * H + h) * W + 2 * w2;
+        float f[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        float2 v = make_float2(0.f, 0.f);
-        if (c < C) v = __ldg(reinterpret_cast<const float2*>(s + static_cast<size_t>(c) * H * W));
-        f[c] = v.x;
-        f[4 + c] = v.y;
+        for (int c = 0; c < 4; ++c) {
+            float2 v = make_float2(0.f, 0.f);
+            if (c < C) v = __ldg(reinterpret_cast<const float2*>(s + static_cast<size_t>(c) * H * W));
+            f[c] = v.x;
+            f[4 + c] = v.y;
+        }
+        __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
     }
-    uint4 o;
-    __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
     dst[idx] = o;
 }
 
-int launch_input_cast_s2d(const float* src, void* dst, int N, int C, int H, int W, cudaStream_t stream) {
-    const long long total = static_cast<long long>(N) * H * (W / 2);
+int launch_input_cast_s2d(const float* src, void* dst, int N, int C, int H, int W, int pad_l, int pad_r, cudaStream_t stream) {
+    const long long total = static_cast<long long>(N) * H * (W / 2 + pad_l + pad_r);
     const int threads = 256;
     const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
     B2_LAUNCH_RC = launch_kernel(input_cast_s2d_kernel, dim3(blocks), dim3(threads), 0, stream, false, src,
-                                 reinterpret_cast<uint4*>(dst), N, C, H, W);
+                                 reinterpret_cast<uint4*>(dst), N, C, H, W, pad_l, pad_r);
     return B2_LAUNCH_RC;
 }
 

@@ -42,9 +42,12 @@ struct ConvArgs {
 struct ConvLaunch {
     CUtensorMap mapA;  // activations: 2-D tiled [M, Cin] or 4-D im2col (C, W, H, N)
     CUtensorMap mapB;  // weights: 2-D tiled [Cout_phys, Ktot]
+    CUtensorMap mapOut;  // output tile store: 2-D tiled [M, Cout_phys], box 128 x min(64, BN), swizzled
+    CUtensorMap mapRes;  // residual tile load: same geometry over the residual tensor (unused when no residual)
     ConvArgs args;
     int bn;            // N tile: 32 / 64 / 128
-    int kb;            // K elements per TMA sub-tile: 64 (SWIZZLE_128B) or 8 (no swizzle, Cin_phys == 8)
+    int kb;            // K elements per TMA sub-tile: 64 (SWIZZLE_128B), 32 (SWIZZLE_64B: stem with the filter
+                       // row folded into "channels" through an overlapping pixel stride) or 8 (no swizzle)
     int stages;        // smem pipeline depth: 1 / 2 / 4 / 8
     int grid_m, grid_n;
 };
@@ -76,8 +79,9 @@ int launch_conv_simt(const SimtConvArgs& a, bool half_storage, cudaStream_t stre
 // fp32 NCHW binding -> NHWC activations (zero-filled channel padding)
 int launch_input_cast(const float* src, void* dst, int N, int C, int H, int W, int C_phys,
                       bool half_storage, cudaStream_t stream);
-// fp32 NCHW binding -> fp16 [N, H, W/2, 8] with channel = dw*4 + c (horizontal space-to-depth, C <= 4)
-int launch_input_cast_s2d(const float* src, void* dst, int N, int C, int H, int W, cudaStream_t stream);
+// fp32 NCHW binding -> fp16 [N, H, pad_l + W/2 + pad_r, 8] with channel = dw*4 + c (horizontal space-to-depth, C <= 4;
+// border pixels zero)
+int launch_input_cast_s2d(const float* src, void* dst, int N, int C, int H, int W, int pad_l, int pad_r, cudaStream_t stream);
 // NHWC activations -> fp32 NCHW binding
 int launch_output_cast(const void* src, float* dst, int N, int C, int H, int W, int C_phys,
                        bool half_storage, cudaStream_t stream);

@@ -115,12 +115,12 @@ def test_builder_layouts():
     blob = builder.build_plan(low, builder.PREC_FP16, 2)
     cast = struct.unpack_from(fmt, blob, 128 + n_t * 96)
     rec = struct.unpack_from(fmt, blob, op_off)
-    assert cast[1] == builder.OP_INPUT_CAST and cast[6] == 2
+    assert cast[1] == builder.OP_INPUT_CAST and (cast[6], cast[7], cast[8]) == (2, 1, 2)  # s2d, right pad 1, left pad 2
     assert (rec[6], rec[7], rec[8], rec[11], rec[13], rec[15], rec[16]) == (7, 2, 3, 8, 8, 28, 28)
     assert rec[10] == 3 * 49  # algorithmic K of the original conv, for FLOP accounting
-    assert rec[21:25] == (4, 1, 2, 1)  # kw, stride_w, pad_w_lo, pad_w_hi
+    assert rec[21:25] == (4, 1, 0, 0)  # kw, stride_w, pad_w_lo, pad_w_hi (padding is physical)
     t0 = struct.unpack_from("<64sIIIIIi", blob, 128)
-    assert t0[2:6] == (8, 4, 8, 8)  # tensor `data`: h=8, w=8/2, c=8, c_phys=8
+    assert t0[2:6] == (8, 4 + 3, 8, 8)  # tensor `data`: h=8, w=2+8/2+1, c=8, c_phys=8
     assert builder.phys_channels(3, builder.PREC_FP16) == 8 and builder.phys_channels(1000, builder.PREC_FP16) == 1024
     assert builder.phys_channels(3, builder.PREC_FP32) == 3
 

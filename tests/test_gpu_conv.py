@@ -91,6 +91,16 @@ def test_programmatic_dependent_launch_modes(gpu, pdl, trigger):
         _check(64, 14, 64, 1, 1, batch=1, options={"pdl": 1})
 
 
+def test_row_folded_stem_equals_generic_tap_path(gpu):
+    # same plan, two A-operand strategies: one 64-byte TMA "pixel" per filter row (KB=32, SWIZZLE_64B) vs one
+    # 16-byte im2col load per tap (KB=8, no swizzle); K order is identical -> bit identical
+    a = _check(3, 64, 64, 7, 2, batch=2, options={"no_fold": 0})
+    b = _check(3, 64, 64, 7, 2, batch=2, options={"no_fold": 1})
+    np.testing.assert_array_equal(a, b)
+    _check(3, 30, 64, 3, 2, batch=1)   # 3x3/s2 stem variant: kw2 = 2 -> not foldable, generic path
+    _check(1, 28, 64, 5, 2, batch=3)   # single-channel input
+
+
 def test_im2col_tma_equals_tiled_tma_on_pointwise(gpu):
     a = _check(256, 28, 128, 1, 1, batch=2, options={"im2col": 0})
     b = _check(256, 28, 128, 1, 1, batch=2, options={"im2col": 1})
