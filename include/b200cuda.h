@@ -50,6 +50,9 @@ int b2_memcpy_h2d(void* dst, const void* src, size_t bytes, b2_stream_t stream);
 int b2_memcpy_d2h(void* dst, const void* src, size_t bytes, b2_stream_t stream);
 int b2_memcpy_d2d(void* dst, const void* src, size_t bytes, b2_stream_t stream);
 int b2_device_sync(void);
+/* cudaProfilerStart/Stop: lets `ncu --profile-from-start off` skip plan building and tactic autotuning */
+int b2_profiler_start(void);
+int b2_profiler_stop(void);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,8 @@ SYMBOLS = [
     ("b2_memcpy_d2h", _I, [_VP, _VP, _SZ, _VP]),
     ("b2_memcpy_d2d", _I, [_VP, _VP, _SZ, _VP]),
     ("b2_device_sync", _I, []),
+    ("b2_profiler_start", _I, []),
+    ("b2_profiler_stop", _I, []),
     # trtlab_host.h
     ("trt_manager_create", _I, [_I, _I, _I, _I, _I, _PVP]),
     ("trt_manager_destroy", None, [_VP]),

@@ -1,6 +1,7 @@
 // CUDA glue of the hot path (include/b200cuda.h): raw allocators, streams, events, async copies.
 // Counterpart of trtlab/cuda (reference trtlab/cuda/include/trtlab/cuda/memory/cuda_allocators.h:44-128,
 // sync.h:13-62, src/device_guard.cc:36-47, src/device_info.cc:66-132).
+#include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -158,6 +159,15 @@ int b2_memcpy_d2d(void* dst, const void* src, size_t bytes, b2_stream_t stream) 
 }
 int b2_device_sync(void) {
     B2G_CUDA(cudaDeviceSynchronize());
+    return B2_OK;
+}
+
+int b2_profiler_start(void) {
+    B2G_CUDA(cudaProfilerStart());
+    return B2_OK;
+}
+int b2_profiler_stop(void) {
+    B2G_CUDA(cudaProfilerStop());
     return B2_OK;
 }
 

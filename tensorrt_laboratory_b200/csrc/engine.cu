@@ -151,6 +151,19 @@ struct ConvConfig {
     int bn, stages, splits;
     double est_us;
 };
+// A pipeline deeper than the K loop is pure shared-memory cost: admit depths up to the smallest instantiated one
+// that covers the loop (or the deepest available when none does).
+static bool stage_depth_useful(int bn, int kb, int st, int kpc) {
+    const int stgs[4] = {1, 2, 4, 8};
+    int cover = 0, deepest = 0;
+    for (int s2 : stgs) {
+        if (!b2k::conv_config_exists(bn, kb, s2)) continue;
+        deepest = s2;
+        if (!cover && s2 >= kpc) cover = s2;
+    }
+    return st <= (cover ? cover : deepest);
+}
+
 
 struct b2_runtime {
     b2_alloc_fn alloc = nullptr;
@@ -419,7 +432,7 @@ ConvConfig pick_conv_config(int M, int cout_phys, int kblocks, int kb, bool resi
             for (int st : stgs) {
                 if (!b2k::conv_config_exists(bn, kb, st)) continue;
                 if (honor_forced && c->force_stages && st != c->force_stages) continue;
-                if (!(honor_forced && c->force_stages) && st > 1 && st / 2 >= kpc) continue;  // deeper than the loop is long
+                if (!(honor_forced && c->force_stages) && !stage_depth_useful(bn, kb, st, kpc)) continue;
                 const double smem = b2k::conv_smem_bytes(bn, st);
                 int per_sm = int(227.0 * 1024 / smem);
                 per_sm = std::min(per_sm, 512 / std::max(32, bn));
@@ -578,7 +591,7 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, Conv
             if (fixed_splits > 0 && sp != fixed_splits) continue;
             if (!b2k::conv_config_exists(bn, kbsz, st)) continue;
             const int kpc = (nkb + sp - 1) / sp;
-            if (st > 1 && st / 2 >= kpc) continue;
+            if (!stage_depth_useful(bn, kbsz, st, kpc)) continue;
             if (sp > 1 && (kbsz != 64 || tiles >= 100 || tiles > kMaxSplitTiles / 8 || kpc < 4 || tiles * sp > 160 ||
                            (sp - 1) * kpc >= nkb ||
                            size_t(tiles) * sp * 128 * bn * 4 > kSplitWorkspaceBytes))

@@ -23,7 +23,7 @@ RN50_CONVS = [
 
 
 def _check(cin, h, cout, k, stride, batch, relu=True, residual=False, options=None, seed=0):
-    pad = {1: 0, 3: 1, 7: 3}[k]
+    pad = {1: 0, 3: 1, 5: 2, 7: 3}[k]
     net, wts, low = helpers.conv_case(cin, h, h, cout, k, stride, pad, relu=relu, residual=residual, seed=seed)
     x = np.random.default_rng(seed + 1).standard_normal((batch, cin, h, h), dtype=np.float32)
     ref = lowered_forward_f16emu(low, x)
