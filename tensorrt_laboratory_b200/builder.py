@@ -64,6 +64,22 @@ def stem_s2d_transform(W: np.ndarray, k: int, pad: int, w_in: int):
     return W2, kw2, pad_lo, pad_hi
 
 
+def pack_weights_sw128(W: np.ndarray) -> np.ndarray:
+    """[Cout_phys, K] fp16 (K % 64 == 0, Cout_phys % 32 == 0) -> blocks [Cout/32][K/64][32 rows][128 B] whose bytes are
+    exactly what the kernel wants in shared memory for a 32-row x 64-K weight sub-tile under the 128-byte swizzle
+    (16-byte chunk j of row r sits at chunk j ^ (r % 8)).  One contiguous 4 KiB block = one `cp.async.bulk`, instead
+    of a 32-row tensor-map box that the TMA unit has to walk row by row."""
+    cout, K = W.shape
+    assert cout % 32 == 0 and K % 64 == 0 and W.dtype == np.float16
+    blk = W.reshape(cout // 32, 32, K // 64, 8, 8)            # [nb, r, kb, chunk, elem]
+    blk = blk.transpose(0, 2, 1, 3, 4)                         # [nb, kb, r, chunk, elem]
+    out = np.empty_like(blk)
+    r = np.arange(32)
+    for j in range(8):
+        out[:, :, r, j ^ (r % 8), :] = blk[:, :, r, j, :]
+    return np.ascontiguousarray(out).reshape(-1)
+
+
 def _name(s: str) -> bytes:
     b = s.encode()
     if len(b) > 63:
@@ -72,7 +88,8 @@ def _name(s: str) -> bytes:
 
 
 def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
-               outputs: Optional[Sequence[str]] = None, name: Optional[str] = None, stem_s2d: bool = True) -> bytes:
+               outputs: Optional[Sequence[str]] = None, name: Optional[str] = None, stem_s2d: bool = True,
+               pack_weights: bool = True) -> bytes:
     """Serialize ``lowered`` (from :func:`graph.lower` with weights) into a plan blob.
 
     ``outputs``: tensor names to expose as output bindings (default: the graph output).  4-D activation
@@ -153,9 +170,13 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
             W[:op["cout"], :taps, :cin_eff] = Wsrc.reshape(op["cout"], taps, cin_eff)
             bias = np.zeros(cout_phys, dtype=np.float32)
             bias[:op["cout"]] = op["bias"]
-            w_off, w_bytes = add_payload(W.astype(wdtype))
+            packed = precision == PREC_FP16 and cin_phys % 64 == 0 and cout_phys % 32 == 0 and pack_weights
+            if packed:
+                w_off, w_bytes = add_payload(pack_weights_sw128(W.astype(np.float16).reshape(cout_phys, taps_phys * cin_phys)))
+            else:
+                w_off, w_bytes = add_payload(W.astype(wdtype))
             b_off, b_bytes = add_payload(bias)
-            rec.update(type=OP_CONV, k=k, stride=op["stride"], pad=op["pad"], relu=int(op["relu"]),
+            rec.update(type=OP_CONV, k=k, stride=op["stride"], pad=op["pad"], relu=int(op["relu"]) | (2 if packed else 0),
                        cin=cin_eff, cout=op["cout"], cin_phys=cin_phys, cout_phys=cout_phys,
                        taps=taps, taps_phys=taps_phys, w_off=w_off, w_bytes=w_bytes, b_off=b_off, b_bytes=b_bytes)
             rec.update(extra)

@@ -172,6 +172,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// contiguous global -> shared bulk copy (no tensor map), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint64_t* bar, void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(map)),
@@ -296,7 +303,14 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     auto load_b = [&](int kb, int s) {  // weights: constant data, legal before pdl_wait()
         uint8_t* b_dst = sB + s * Cfg::B_STAGE;
         if (KB == 64) {
-            tma_load_2d(&mapB, &full_bar[s], b_dst, kb * 64, n0);
+            if (p.wpacked != nullptr) {  // BN/32 contiguous pre-swizzled 4 KiB blocks
+#pragma unroll
+                for (int j = 0; j < BN / 32; ++j)
+                    bulk_load_1d(&full_bar[s], b_dst + j * 4096,
+                                 p.wpacked + (static_cast<size_t>(n0 / 32 + j) * p.num_kblocks + kb) * 4096, 4096);
+            } else {
+                tma_load_2d(&mapB, &full_bar[s], b_dst, kb * 64, n0);
+            }
         } else {
             const int nt = sub_tiles(kb);
             for (int t = 0; t < nt; ++t) tma_load_2d(&mapB, &full_bar[s], b_dst + t * B_SUB, (kb * TPS + t) * KB, n0);
@@ -506,16 +520,22 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = 0.f;
-                for (int sp = 0; sp < p.splits; ++sp) {
-                    const float4* src = reinterpret_cast<const float4*>(ws_tile + static_cast<size_t>(sp) * (128 * BN) +
-                                                                        static_cast<size_t>(row) * BN + g * 32);
+                for (int sp = 0; sp < p.splits; sp += 2) {  // two partial tiles (16 x 16 B) in flight per step
+                    const float4* s0 = reinterpret_cast<const float4*>(ws_tile + static_cast<size_t>(sp) * (128 * BN) +
+                                                                       static_cast<size_t>(row) * BN + g * 32);
+                    const bool two = sp + 1 < p.splits;
+                    const float4* s1 = two ? s0 + (128 * BN) / 4 : s0;
+                    float4 t0[8], t1[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 t = __ldcg(src + q);
-                        f[4 * q] += t.x;
-                        f[4 * q + 1] += t.y;
-                        f[4 * q + 2] += t.z;
-                        f[4 * q + 3] += t.w;
+                    for (int q = 0; q < 8; ++q) t0[q] = __ldcg(s0 + q);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) t1[q] = two ? __ldcg(s1 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {  // fixed order: split sp, then split sp+1
+                        f[4 * q] = (f[4 * q] + t0[q].x) + t1[q].x;
+                        f[4 * q + 1] = (f[4 * q + 1] + t0[q].y) + t1[q].y;
+                        f[4 * q + 2] = (f[4 * q + 2] + t0[q].z) + t1[q].z;
+                        f[4 * q + 3] = (f[4 * q + 3] + t0[q].w) + t1[q].w;
                     }
                 }
                 finish_group(g, f);
@@ -654,6 +674,7 @@ __global__ void conv_simt_kernel(SimtConvArgs a) {
     }
     const T* in = reinterpret_cast<const T*>(a.in);
     const T* w = reinterpret_cast<const T*>(a.w) + static_cast<size_t>(co) * a.taps_phys * a.Cin_phys;
+    const int kblocks = a.taps_phys * a.Cin_phys / 64;
     acc_t acc = 0;
     for (int r = 0; r < a.kh; ++r) {
         const int hi = ho * a.stride_h - a.pad_h + r;
@@ -663,8 +684,19 @@ __global__ void conv_simt_kernel(SimtConvArgs a) {
             if (wi < 0 || wi >= a.W) continue;
             const T* ip = in + ((static_cast<size_t>(n) * a.H + hi) * a.W + wi) * a.Cin_phys;
             const T* wp = w + static_cast<size_t>(r * a.kw + s) * a.Cin_phys;
-            for (int c = 0; c < a.Cin; ++c)
-                acc += static_cast<acc_t>(to_f(ip[c])) * static_cast<acc_t>(to_f(wp[c]));
+            if (a.w_packed) {
+                const size_t kbase = static_cast<size_t>(r * a.kw + s) * a.Cin_phys;
+                for (int c = 0; c < a.Cin; ++c) {
+                    const size_t k = kbase + c;
+                    const size_t kk = k & 63;
+                    const size_t off = ((static_cast<size_t>(co >> 5) * kblocks + (k >> 6)) << 11) + (static_cast<size_t>(co & 31) << 6) +
+                                       ((((kk >> 3) ^ (co & 7))) << 3) + (kk & 7);  // in T (= 2-byte) elements
+                    acc += static_cast<acc_t>(to_f(ip[c])) * static_cast<acc_t>(to_f(reinterpret_cast<const T*>(a.w)[off]));
+                }
+            } else {
+                for (int c = 0; c < a.Cin; ++c)
+                    acc += static_cast<acc_t>(to_f(ip[c])) * static_cast<acc_t>(to_f(wp[c]));
+            }
         }
     }
     acc_t v = acc + static_cast<acc_t>(a.bias[co]);

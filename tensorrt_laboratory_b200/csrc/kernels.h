@@ -36,6 +36,8 @@ struct ConvArgs {
     float* workspace;        // splits > 1: [tile][split][128][BN] fp32 partial tiles
     int* tile_counters;      // splits > 1: one arrival counter per output tile (zero between launches)
     int pdl_trigger;         // 0: release the dependent kernel right after the prologue, 1: after the main loop
+    const uint8_t* wpacked;  // KB==64: weights as pre-swizzled 4 KiB blocks [Cout/32][num_kblocks][32][128 B] fetched with
+                             // cp.async.bulk (nullptr: fetch through mapB)
     long long* dbg;          // optional per-CTA phase timestamps (16 x int64 per CTA), nullptr in production
 };
 
@@ -73,6 +75,7 @@ struct SimtConvArgs {
     void* out;             // NHWC [N,Ho,Wo,Cout_phys]
     int N, H, W, Cin, Cin_phys, Ho, Wo, Cout, Cout_phys;
     int kh, kw, taps_phys, stride_h, stride_w, pad_h, pad_w, relu;
+    int w_packed;          // 1: `w` uses the pre-swizzled block layout (fp16 engines)
 };
 int launch_conv_simt(const SimtConvArgs& a, bool half_storage, cudaStream_t stream);
 

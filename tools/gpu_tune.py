@@ -33,7 +33,11 @@ def time_session(sess, iters=100):
 def main():
     configs = [parse(a) for a in sys.argv[1:]] or [{}]
     multi = os.environ.get("TUNE_MULTI", "1") != "0"
-    blob = builder.build_resnet_plan(50, builder.PREC_FP16, 8)
+    from tensorrt_laboratory_b200 import graph
+    net = graph.resnet_caffe(50)
+    low = graph.lower(net, weights.random_weights(net, 0))
+    pack = os.environ.get("TUNE_PACK", "1") != "0"
+    blob = builder.build_plan(low, builder.PREC_FP16, 8, pack_weights=pack)
     eng = capi.Engine(blob)
     x = weights.synthetic_input(8)
     ring = weights.synthetic_input(8, ring=8)
