@@ -65,14 +65,15 @@ def stem_s2d_transform(W: np.ndarray, k: int, pad: int, w_in: int):
 
 
 def pack_weights_sw128(W: np.ndarray) -> np.ndarray:
-    """[Cout_phys, K] fp16 (K % 64 == 0, Cout_phys % 32 == 0) -> blocks [Cout/32][K/64][32 rows][128 B] whose bytes are
-    exactly what the kernel wants in shared memory for a 32-row x 64-K weight sub-tile under the 128-byte swizzle
-    (16-byte chunk j of row r sits at chunk j ^ (r % 8)).  One contiguous 4 KiB block = one `cp.async.bulk`, instead
-    of a 32-row tensor-map box that the TMA unit has to walk row by row."""
+    """[Cout_phys, K] fp16 (K % 64 == 0, Cout_phys % 32 == 0) -> blocks [K/64][Cout/32][32 rows][128 B] whose bytes are
+    exactly what the kernel wants in shared memory for a 64-K weight sub-tile under the 128-byte swizzle (16-byte
+    chunk j of row r sits at chunk j ^ (r % 8)).  The N tile of ANY width BN in {32, 64, 128} for k-block kb is then
+    ONE contiguous run of BN*128 bytes = one `cp.async.bulk` instruction (instruction issue, ~200 cycles per TMA op
+    from a single thread, is what paces the main loop -- profiles/phase_timing)."""
     cout, K = W.shape
     assert cout % 32 == 0 and K % 64 == 0 and W.dtype == np.float16
     blk = W.reshape(cout // 32, 32, K // 64, 8, 8)            # [nb, r, kb, chunk, elem]
-    blk = blk.transpose(0, 2, 1, 3, 4)                         # [nb, kb, r, chunk, elem]
+    blk = blk.transpose(2, 0, 1, 3, 4)                         # [kb, nb, r, chunk, elem]
     out = np.empty_like(blk)
     r = np.arange(32)
     for j in range(8):

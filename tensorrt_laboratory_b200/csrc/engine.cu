@@ -417,7 +417,7 @@ int make_map_im2col(CUtensorMap* map, const void* base, int C, int W, int H, int
 ConvConfig pick_conv_config(int M, int cout_phys, int kblocks, int kb, bool residual, const b2_context* c, bool honor_forced) {
     const int m_tiles = (M + 127) / 128;
     ConvConfig best{0, 0, 1, 1e30};
-    const int bns[3] = {128, 64, 32};
+    const int bns[4] = {256, 128, 64, 32};
     const int stgs[4] = {1, 2, 4, 8};
     for (int bn : bns) {
         if (cout_phys % bn) continue;
@@ -432,9 +432,10 @@ ConvConfig pick_conv_config(int M, int cout_phys, int kblocks, int kb, bool resi
             if (splits > 1 && (splits - 1) * kpc >= kblocks) continue;  // an empty split
             for (int st : stgs) {
                 if (!b2k::conv_config_exists(bn, kb, st)) continue;
+                if (b2k::conv_smem_bytes(bn, st, residual) > 227 * 1024) continue;
                 if (honor_forced && c->force_stages && st != c->force_stages) continue;
                 if (!(honor_forced && c->force_stages) && !stage_depth_useful(bn, kb, st, kpc)) continue;
-                const double smem = b2k::conv_smem_bytes(bn, st);
+                const double smem = b2k::conv_smem_bytes(bn, st, residual);
                 int per_sm = int(227.0 * 1024 / smem);
                 per_sm = std::min(per_sm, 512 / std::max(32, bn));
                 per_sm = std::max(1, std::min(per_sm, 8));
@@ -582,7 +583,7 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, Conv
     }
     ConvConfig best = *best_out;
     double best_ms = 1e30;
-    const int bns[3] = {128, 64, 32};
+    const int bns[4] = {256, 128, 64, 32};
     const int stgs[4] = {1, 2, 4, 8};
     int status = B2_OK;
     const int iters = 12;
@@ -595,6 +596,7 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, Conv
         for (int st : stgs) {
             if (fixed_splits > 0 && sp != fixed_splits) continue;
             if (!b2k::conv_config_exists(bn, kbsz, st)) continue;
+            if (b2k::conv_smem_bytes(bn, st, r.res >= 0) > 227 * 1024) continue;
             const int kpc = (nkb + sp - 1) / sp;
             if (!stage_depth_useful(bn, kbsz, st, kpc)) continue;
             if (sp > 1 && (kbsz != 64 || tiles >= 100 || tiles > kMaxSplitTiles / 8 || kpc < 4 || tiles * sp > 160 ||
@@ -1150,6 +1152,7 @@ static const Launch* get_launch(b2_context* c, int batch, int i) {
 // with per-CTA phase timestamps enabled; `stamps` receives 16 int64 per CTA of the LAST repetition.
 int b2_context_debug_conv_timing(b2_context* c, int batch, int i, int reps, b2_stream_t stream_, long long* stamps,
                                  int cap_ctas, int* n_ctas) {
+    const int dbg_mode = env_int("B2_DBG_MODE", 0);
     Plan* plan = nullptr;
     if (!c || build_plan(c, batch, &plan)) return fail(B2_EINVAL, "no plan");
     if (i < 0 || i >= int(plan->launches.size()) || plan->launches[i].kind != L_CONV_TC) return fail(B2_EINVAL, "not a tcgen05 conv launch");
@@ -1161,6 +1164,7 @@ int b2_context_debug_conv_timing(b2_context* c, int batch, int i, int reps, b2_s
     B2_CUDA(cudaMalloc(&d, size_t(ctas) * 16 * sizeof(long long)));
     cudaMemset(d, 0, size_t(ctas) * 16 * sizeof(long long));
     cl.args.dbg = d;
+    cl.args.dbg_mode = dbg_mode;
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
     int rc = 0;
     for (int r = 0; r < reps && !rc; ++r) rc = b2k::launch_conv_f16_tcgen05(cl, s);

@@ -296,18 +296,18 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int n = p.taps_phys - kb * TPS;
         return n > TPS ? TPS : n;
     };
+    const bool skip_mma = p.dbg_mode & 1, skip_a = KB == 64 && (p.dbg_mode & 2), skip_b = KB == 64 && (p.dbg_mode & 4);
     auto stage_bytes = [&](int kb) -> uint32_t {
-        if (KB == 64) return Cfg::A_STAGE + Cfg::B_STAGE;
+        if (KB == 64) return (skip_a ? 0 : Cfg::A_STAGE) + (skip_b ? 0 : Cfg::B_STAGE);
         return static_cast<uint32_t>(sub_tiles(kb) * (A_SUB + B_SUB));
     };
     auto load_b = [&](int kb, int s) {  // weights: constant data, legal before pdl_wait()
+        if (skip_b) return;
         uint8_t* b_dst = sB + s * Cfg::B_STAGE;
         if (KB == 64) {
-            if (p.wpacked != nullptr) {  // BN/32 contiguous pre-swizzled 4 KiB blocks
-#pragma unroll
-                for (int j = 0; j < BN / 32; ++j)
-                    bulk_load_1d(&full_bar[s], b_dst + j * 4096,
-                                 p.wpacked + (static_cast<size_t>(n0 / 32 + j) * p.num_kblocks + kb) * 4096, 4096);
+            if (p.wpacked != nullptr) {  // one contiguous run of BN/32 pre-swizzled 4 KiB blocks
+                bulk_load_1d(&full_bar[s], b_dst,
+                             p.wpacked + (static_cast<size_t>(kb) * (p.Cout >> 5) + (n0 >> 5)) * 4096, BN * 128);
             } else {
                 tma_load_2d(&mapB, &full_bar[s], b_dst, kb * 64, n0);
             }
@@ -334,18 +334,31 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
             const int base_w = q0 * p.stride_w - p.pad_w;
             const int base_h = p0 * p.stride_h - p.pad_h;
-            auto load_a = [&](int kb, int s) {
+            // K-block -> (filter row r, filter column sx, channel block cb), advanced incrementally: integer division
+            // by a run-time value costs ~100 cycles and this thread's issue rate paces the whole main loop
+            int cur_cb = 0, cur_r = 0, cur_sx = 0;
+            if (KB == 64) {
+                const int tap0 = kb_begin / p.cblocks;
+                cur_cb = kb_begin - tap0 * p.cblocks;
+                cur_r = tap0 / p.kw;
+                cur_sx = tap0 - cur_r * p.kw;
+            }
+            auto load_a = [&](int kb, int s) {  // must be called with consecutive kb starting at kb_begin
+                if (skip_a) return;
                 uint8_t* a_dst = sA + s * Cfg::A_STAGE;
                 if (KB == 64) {
-                    const int tap = kb / p.cblocks;
-                    const int cb = kb - tap * p.cblocks;
                     if (p.a_mode == A_TILED) {
-                        tma_load_2d(&mapA, &full_bar[s], a_dst, cb * 64, m0);
+                        tma_load_2d(&mapA, &full_bar[s], a_dst, cur_cb * 64, m0);
                     } else {
-                        const int r = tap / p.kw;
-                        const int sx = tap - r * p.kw;
-                        tma_load_im2col_4d(&mapA, &full_bar[s], a_dst, cb * 64, base_w, base_h, img0,
-                                           static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+                        tma_load_im2col_4d(&mapA, &full_bar[s], a_dst, cur_cb * 64, base_w, base_h, img0,
+                                           static_cast<uint16_t>(cur_sx), static_cast<uint16_t>(cur_r));
+                    }
+                    if (++cur_cb == p.cblocks) {
+                        cur_cb = 0;
+                        if (++cur_sx == p.kw) {
+                            cur_sx = 0;
+                            ++cur_r;
+                        }
                     }
                 } else {
                     const int nt = sub_tiles(kb);
@@ -359,37 +372,55 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     }
                 }
             };
+            // For 64-wide K-blocks the weights have their own issuing thread (warp 3): one thread needs ~200 cycles
+            // per TMA instruction, which is what paces the main loop.
+            constexpr bool kSplitProducers = KB == 64;
             const int npre = nk < STAGES ? nk : STAGES;
             for (int i = 0; i < npre; ++i) {  // first ring pass: weights fly while the previous kernel drains
                 mbar_expect_tx(&full_bar[i], stage_bytes(kb_begin + i));
-                load_b(kb_begin + i, i);
+                if (!kSplitProducers) load_b(kb_begin + i, i);
             }
             pdl_wait();
             if (dbg) dbg[2] = clock64();
             for (int i = 0; i < npre; ++i) load_a(kb_begin + i, i);
             if (has_res && !split) load_residual();
+            long long tw = 0, te = 0, tl = 0;
             for (int i = npre; i < nk; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
+                long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                if (dbg) c0 = clock64();
                 mbar_wait(&empty_bar[s], ph ^ 1);
+                if (dbg) c1 = clock64();
                 mbar_expect_tx(&full_bar[s], stage_bytes(kb_begin + i));
+                if (dbg) c2 = clock64();
                 load_a(kb_begin + i, s);
-                load_b(kb_begin + i, s);
+                if (!kSplitProducers) load_b(kb_begin + i, s);
+                if (dbg) {
+                    c3 = clock64();
+                    tw += c1 - c0, te += c2 - c1, tl += c3 - c2;
+                }
             }
+            if (dbg) dbg[11] = tw, dbg[12] = te, dbg[13] = tl;
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
             // ================= MMA issuer =================
+            long long mw = 0, mi = 0;
             for (int i = 0; i < nk; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
+                long long m0c = 0, m1c = 0;
+                if (dbg) m0c = clock64();
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
+                if (dbg) m1c = clock64(), mw += m1c - m0c;
                 if (dbg && i == 0) dbg[3] = clock64();
                 const uint32_t a_addr = smem_u32(sA + s * Cfg::A_STAGE);
                 const uint32_t b_addr = smem_u32(sB + s * Cfg::B_STAGE);
-                if (KB == 64) {
+                if (skip_mma) {
+                } else if (KB == 64) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {  // 4 x (K = 16) inside one 128-byte swizzle row
                         const uint64_t ad = make_smem_desc(a_addr + j * 32, 16, 1024, 2);
@@ -416,9 +447,22 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     }
                 }
                 umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+                if (dbg) mi += clock64() - m1c;
             }
             umma_commit(accum_bar);  // accumulator complete
-            if (dbg) dbg[4] = clock64();
+            if (dbg) dbg[4] = clock64(), dbg[14] = mw, dbg[15] = mi;
+        }
+        __syncwarp();
+    }
+
+    else if (warp == 3 && KB == 64) {
+        if (lane == 0) {
+            // ================= weight producer: constants, so no dependency wait; only the ring's empty barriers ====
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % STAGES;
+                if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
+                load_b(kb_begin + i, s);
+            }
         }
         __syncwarp();
     }
@@ -590,16 +634,17 @@ static int launch_one(const ConvLaunch& L, cudaStream_t stream) {
 
 template <int BN, int KB, int STAGES>
 static int init_one() {
+    const int want = conv_smem_layout_bytes(BN, STAGES, true);
     return static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 conv_smem_layout_bytes(BN, STAGES, true)));
+                                                 want > 227 * 1024 ? conv_smem_layout_bytes(BN, STAGES, false) : want));
 }
 
-int conv_smem_bytes(int bn, int stages) { return conv_smem_layout_bytes(bn, stages, true); }
+int conv_smem_bytes(int bn, int stages, bool residual) { return conv_smem_layout_bytes(bn, stages, residual); }
 
 #define B2_FOR_EACH_CONV(X) \
     X(32, 64, 1) X(32, 64, 2) X(32, 64, 4) X(32, 64, 8) \
     X(64, 64, 1) X(64, 64, 2) X(64, 64, 4) X(64, 64, 8) \
-    X(128, 64, 1) X(128, 64, 2) X(128, 64, 4) \
+    X(128, 64, 1) X(128, 64, 2) X(128, 64, 4) X(256, 64, 2) X(256, 64, 4) \
     X(32, 8, 2) X(32, 8, 4) X(64, 8, 2) X(64, 8, 4) X(64, 8, 8) X(128, 8, 4) \
     X(32, 32, 2) X(32, 32, 4) X(64, 32, 1) X(64, 32, 2) X(64, 32, 4) X(128, 32, 2) X(128, 32, 4)
 
@@ -689,7 +734,7 @@ __global__ void conv_simt_kernel(SimtConvArgs a) {
                 for (int c = 0; c < a.Cin; ++c) {
                     const size_t k = kbase + c;
                     const size_t kk = k & 63;
-                    const size_t off = ((static_cast<size_t>(co >> 5) * kblocks + (k >> 6)) << 11) + (static_cast<size_t>(co & 31) << 6) +
+                    const size_t off = (((k >> 6) * static_cast<size_t>(a.Cout_phys >> 5) + static_cast<size_t>(co >> 5)) << 11) + (static_cast<size_t>(co & 31) << 6) +
                                        ((((kk >> 3) ^ (co & 7))) << 3) + (kk & 7);  // in T (= 2-byte) elements
                     acc += static_cast<acc_t>(to_f(ip[c])) * static_cast<acc_t>(to_f(reinterpret_cast<const T*>(a.w)[off]));
                 }

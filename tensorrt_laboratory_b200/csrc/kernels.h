@@ -36,8 +36,9 @@ struct ConvArgs {
     float* workspace;        // splits > 1: [tile][split][128][BN] fp32 partial tiles
     int* tile_counters;      // splits > 1: one arrival counter per output tile (zero between launches)
     int pdl_trigger;         // 0: release the dependent kernel right after the prologue, 1: after the main loop
-    const uint8_t* wpacked;  // KB==64: weights as pre-swizzled 4 KiB blocks [Cout/32][num_kblocks][32][128 B] fetched with
-                             // cp.async.bulk (nullptr: fetch through mapB)
+    const uint8_t* wpacked;  // KB==64: weights as pre-swizzled 4 KiB blocks [num_kblocks][Cout/32][32][128 B]; the BN-wide
+                             // tile of one k-block is one contiguous cp.async.bulk (nullptr: fetch through mapB)
+    int dbg_mode;            // bottleneck isolation (debug only): bit0 skip MMA issue, bit1 skip A loads, bit2 skip B loads
     long long* dbg;          // optional per-CTA phase timestamps (16 x int64 per CTA), nullptr in production
 };
 
@@ -47,7 +48,7 @@ struct ConvLaunch {
     CUtensorMap mapOut;  // output tile store: 2-D tiled [M, Cout_phys], box 128 x min(64, BN), swizzled
     CUtensorMap mapRes;  // residual tile load: same geometry over the residual tensor (unused when no residual)
     ConvArgs args;
-    int bn;            // N tile: 32 / 64 / 128
+    int bn;            // N tile: 32 / 64 / 128 / 256
     int kb;            // K elements per TMA sub-tile: 64 (SWIZZLE_128B), 32 (SWIZZLE_64B: stem with the filter
                        // row folded into "channels" through an overlapping pixel stride) or 8 (no swizzle)
     int stages;        // smem pipeline depth: 1 / 2 / 4 / 8
@@ -59,7 +60,7 @@ int launch_conv_f16_tcgen05(const ConvLaunch& L, cudaStream_t stream);
 // one-time: opt in to large dynamic shared memory for every instantiation
 int init_conv_kernels();
 bool conv_config_exists(int bn, int kb, int stages);  // is this (tile, K-chunk, depth) instantiated?
-int conv_smem_bytes(int bn, int stages);
+int conv_smem_bytes(int bn, int stages, bool residual);  // dynamic shared memory of one CTA
 // programmatic dependent launch on/off for every kernel of this library (default on)
 void set_pdl(bool on);
 bool get_pdl();

@@ -50,7 +50,7 @@ struct OpRec {  // 176 bytes
     int32_t binding;       // cast ops: binding index
     uint32_t k, stride, pad_;
     uint32_t relu;         // bit 0: fused ReLU.  bit 1 (convs): weights are stored as pre-swizzled 4 KiB blocks
-                           // [Cout/32][K/64][32 rows][128 B] (builder.pack_weights_sw128) instead of row-major [Cout][K]
+                           // [K/64][Cout/32][32 rows][128 B] (builder.pack_weights_sw128) instead of row-major [Cout][K]
     uint32_t ceil_mode;    // pools: Caffe ceil mode.  convs: algorithmic K (Cin*kh*kw of the ORIGINAL conv) when the
                            // builder re-expressed the layer (0 = cin*taps)
     uint32_t cin, cout, cin_phys, cout_phys, taps, taps_phys;

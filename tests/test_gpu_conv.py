@@ -51,10 +51,12 @@ def test_no_relu_keeps_negative_values(gpu):
     assert (got < 0).any()
 
 
-@pytest.mark.parametrize("bn", [32, 64, 128])
+@pytest.mark.parametrize("bn", [32, 64, 128, 256])
 def test_every_n_tile(gpu, bn):
     _check(64, 28, 256, 1, 1, batch=2, options={"bn": bn})
-    _check(3, 64, 128, 7, 2, batch=1, options={"bn": bn, "stages": 4})  # un-swizzled 8-channel K path
+    _check(128, 14, 256, 3, 1, batch=2, residual=True, options={"bn": bn, "stages": 2})
+    if bn <= 128:
+        _check(3, 64, 128, 7, 2, batch=1, options={"bn": bn, "stages": 4})  # row-folded stem path
 
 
 @pytest.mark.parametrize("stages", [1, 2, 4, 8])

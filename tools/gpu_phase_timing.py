@@ -44,7 +44,8 @@ def main():
             start_spread = (t[:, 8].max() - t[:, 8].min()) / 1e3
             sms = len(np.unique(t[:, 10]))
             print(f"{name[13:60]:48s} reps={reps} ctas={nct.value:4d} sms={sms:3d} span={span_us:6.2f}us cta={cta_us:5.2f}us startspread={start_spread:5.2f}us | "
-                  f"prolog={d(0,1):6.0f} depwait={d(1,2):6.0f} firstTMA={d(2,3):6.0f} mainloop={d(3,4):7.0f} accum={d(4,5):6.0f} epi={d(5,6):6.0f} tear={d(6,7):6.0f} cyc")
+                  f"prolog={d(0,1):6.0f} depwait={d(1,2):6.0f} firstTMA={d(2,3):6.0f} mainloop={d(3,4):7.0f} accum={d(4,5):6.0f} epi={d(5,6):6.0f} tear={d(6,7):6.0f} cyc"
+                  f" | prod: wait_empty={np.median(t[:,11]):7.0f} expect={np.median(t[:,12]):6.0f} tma={np.median(t[:,13]):6.0f}  mma: wait_full={np.median(t[:,14]):7.0f} issue+commit={np.median(t[:,15]):6.0f}")
     sess.close()
 
 
