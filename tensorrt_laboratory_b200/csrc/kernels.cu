@@ -59,6 +59,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// One lane of a CONVERGED warp.  Issuing TMA / tcgen05 instructions under `elect.sync` (instead of a divergent
+// `if (lane == 0)`) lets ptxas keep their operands in uniform registers; the divergent form wraps every such
+// instruction in an ELECT / R2UR / BRA.U.ANY waterfall loop that costs ~100 cycles per instruction.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -323,8 +338,8 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     };
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ================= TMA producer =================
+        {
+            // ================= TMA producer (whole warp converged, one elected lane issues) =================
             int img0 = 0, p0 = 0, q0 = 0;
             if (p.a_mode == A_IM2COL) {
                 img0 = m0 / p.HoWo;
@@ -376,14 +391,20 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             // per TMA instruction, which is what paces the main loop.
             constexpr bool kSplitProducers = KB == 64;
             const int npre = nk < STAGES ? nk : STAGES;
-            for (int i = 0; i < npre; ++i) {  // first ring pass: weights fly while the previous kernel drains
-                mbar_expect_tx(&full_bar[i], stage_bytes(kb_begin + i));
-                if (!kSplitProducers) load_b(kb_begin + i, i);
+            if (elect_one_sync()) {
+                for (int i = 0; i < npre; ++i) {  // first ring pass: weights fly while the previous kernel drains
+                    mbar_expect_tx(&full_bar[i], stage_bytes(kb_begin + i));
+                    if (!kSplitProducers) load_b(kb_begin + i, i);
+                }
             }
+            __syncwarp();
             pdl_wait();
-            if (dbg) dbg[2] = clock64();
-            for (int i = 0; i < npre; ++i) load_a(kb_begin + i, i);
-            if (has_res && !split) load_residual();
+            if (dbg && lane == 0) dbg[2] = clock64();
+            if (elect_one_sync()) {
+                for (int i = 0; i < npre; ++i) load_a(kb_begin + i, i);
+                if (has_res && !split) load_residual();
+            }
+            __syncwarp();
             long long tw = 0, te = 0, tl = 0;
             for (int i = npre; i < nk; ++i) {
                 const int s = i % STAGES;
@@ -392,21 +413,23 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 if (dbg) c0 = clock64();
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (dbg) c1 = clock64();
-                mbar_expect_tx(&full_bar[s], stage_bytes(kb_begin + i));
-                if (dbg) c2 = clock64();
-                load_a(kb_begin + i, s);
-                if (!kSplitProducers) load_b(kb_begin + i, s);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&full_bar[s], stage_bytes(kb_begin + i));
+                    load_a(kb_begin + i, s);
+                    if (!kSplitProducers) load_b(kb_begin + i, s);
+                }
+                __syncwarp();
                 if (dbg) {
                     c3 = clock64();
-                    tw += c1 - c0, te += c2 - c1, tl += c3 - c2;
+                    tw += c1 - c0, tl += c3 - c1;
                 }
             }
-            if (dbg) dbg[11] = tw, dbg[12] = te, dbg[13] = tl;
+            if (dbg && lane == 0) dbg[11] = tw, dbg[12] = te, dbg[13] = tl;
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ================= MMA issuer =================
+        {
+            // ================= MMA issuer (whole warp converged, one elected lane issues) =================
             long long mw = 0, mi = 0;
             for (int i = 0; i < nk; ++i) {
                 const int s = i % STAGES;
@@ -416,9 +439,10 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 if (dbg) m1c = clock64(), mw += m1c - m0c;
-                if (dbg && i == 0) dbg[3] = clock64();
+                if (dbg && i == 0 && lane == 0) dbg[3] = clock64();
                 const uint32_t a_addr = smem_u32(sA + s * Cfg::A_STAGE);
                 const uint32_t b_addr = smem_u32(sB + s * Cfg::B_STAGE);
+                if (elect_one_sync()) {
                 if (skip_mma) {
                 } else if (KB == 64) {
 #pragma unroll
@@ -447,24 +471,25 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     }
                 }
                 umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+                }
+                __syncwarp();
                 if (dbg) mi += clock64() - m1c;
             }
-            umma_commit(accum_bar);  // accumulator complete
-            if (dbg) dbg[4] = clock64(), dbg[14] = mw, dbg[15] = mi;
+            if (elect_one_sync()) umma_commit(accum_bar);  // accumulator complete
+            __syncwarp();
+            if (dbg && lane == 0) dbg[4] = clock64(), dbg[14] = mw, dbg[15] = mi;
         }
         __syncwarp();
     }
 
     else if (warp == 3 && KB == 64) {
-        if (lane == 0) {
-            // ================= weight producer: constants, so no dependency wait; only the ring's empty barriers ====
-            for (int i = 0; i < nk; ++i) {
-                const int s = i % STAGES;
-                if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
-                load_b(kb_begin + i, s);
-            }
+        // ================= weight producer: constants, so no dependency wait; only the ring's empty barriers ====
+        for (int i = 0; i < nk; ++i) {
+            const int s = i % STAGES;
+            if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
+            if (elect_one_sync()) load_b(kb_begin + i, s);
+            __syncwarp();
         }
-        __syncwarp();
     }
 
     // ====== epilogue: TMEM -> registers -> bias/residual/ReLU -> fp16 -> swizzled smem tile -> TMA store ======
