@@ -150,6 +150,7 @@ struct Plan {
 struct ConvConfig {
     int bn, stages, splits;
     double est_us;
+    int sps = 1;  // 64-wide K sub-blocks per pipeline stage
 };
 // A pipeline deeper than the K loop is pure shared-memory cost: admit depths up to the smallest instantiated one
 // that covers the loop (or the deepest available when none does).
@@ -217,6 +218,7 @@ struct b2_context {
     int force_bn = 0;
     int force_stages = 0;
     int force_splits = 0;
+    int force_sps = 0;
     int pdl_trigger = 1;
     int no_pack = 0;    // reserved (packed plans cannot fall back to the tensor-map weight path)
     int no_fold = 0;    // 1: run the stem through the generic 8-channel tap path instead of the row-folded one
@@ -492,6 +494,7 @@ int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& c
     const int nkb = conv_num_kblocks(c, op);
     cl.bn = cfg.bn;
     cl.stages = cfg.stages;
+    cl.sps = cfg.sps > 0 ? cfg.sps : 1;
     cl.grid_n = int(r.cout_phys) / cl.bn;
     b2k::ConvArgs& a = cl.args;
     a.splits = cfg.splits;
@@ -593,17 +596,20 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, Conv
         if (int(r.cout_phys) % bn) continue;
         const int tiles = m_tiles * (int(r.cout_phys) / bn);
         for (int sp : split_cands)
+        for (int sps = 1; sps <= 2; ++sps)
         for (int st : stgs) {
             if (fixed_splits > 0 && sp != fixed_splits) continue;
-            if (!b2k::conv_config_exists(bn, kbsz, st)) continue;
-            if (b2k::conv_smem_bytes(bn, st, r.res >= 0) > 227 * 1024) continue;
+            if (!b2k::conv_config_exists(bn, kbsz, st, sps)) continue;
+            if (b2k::conv_smem_bytes(bn, st, r.res >= 0, sps) > 227 * 1024) continue;
             const int kpc = (nkb + sp - 1) / sp;
-            if (!stage_depth_useful(bn, kbsz, st, kpc)) continue;
+            if (sps == 2 && kpc < 4) continue;  // double-width stages only pay on long K loops
+            if (sps == 1 && !stage_depth_useful(bn, kbsz, st, kpc)) continue;
+            if (sps == 2 && st * 2 > kpc + 2) continue;
             if (sp > 1 && (kbsz != 64 || tiles >= 100 || tiles > kMaxSplitTiles / 8 || kpc < 4 || tiles * sp > 160 ||
                            (sp - 1) * kpc >= nkb ||
                            size_t(tiles) * sp * 128 * bn * 4 > kSplitWorkspaceBytes))
                 continue;  // split-K only where the plain grid leaves SMs idle
-            ConvConfig cand{bn, st, sp, 0.0};
+            ConvConfig cand{bn, st, sp, 0.0, sps};
             b2k::ConvLaunch cl0;
             if ((status = make_conv_launch(c, op, batch, cand, &cl0))) break;
             // concurrent split-K launches must not share arrival counters or partial-tile storage
@@ -729,7 +735,10 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                     if (cfg.bn == 0)  // a forced tile that does not divide this layer: fall back to the model
                         cfg = pick_conv_config(M, int(r.cout_phys), nkb, kbsz, r.res >= 0, c, false);
                     if (cfg.bn == 0) return fail(B2_EINVAL, "conv %s: no kernel configuration", op.name.c_str());
-                    const bool forced = c->force_bn || c->force_stages || c->force_splits;
+                    if (c->force_sps == 2 && b2k::conv_config_exists(cfg.bn, kbsz, cfg.stages, 2) &&
+                        b2k::conv_smem_bytes(cfg.bn, cfg.stages, r.res >= 0, 2) <= 227 * 1024)
+                        cfg.sps = 2;
+                    const bool forced = c->force_bn || c->force_stages || c->force_splits || c->force_sps;
                     const int op_index = int(&op - &e->ops[0]);
                     if (!forced && c->autotune) {
                         bool have = false;
@@ -1007,6 +1016,7 @@ int b2_context_create(b2_engine* e, b2_context** out) {
     c->force_bn = env_int("B2_FORCE_BN", 0);
     c->force_stages = env_int("B2_FORCE_STAGES", 0);
     c->force_splits = env_int("B2_FORCE_SPLITS", 0);
+    c->force_sps = env_int("B2_FORCE_SPS", 0);
     c->pdl_trigger = env_int("B2_PDL_TRIGGER", 1);
     c->autotune = env_int("B2_AUTOTUNE", 4);
     if (getenv("B2_PDL")) b2k::set_pdl(env_int("B2_PDL", 1) != 0);
@@ -1059,6 +1069,7 @@ int b2_context_set_option(b2_context* c, const char* key, int value) {
     else if (k == "bn") c->force_bn = value;
     else if (k == "stages") c->force_stages = value;
     else if (k == "splits") c->force_splits = value;
+    else if (k == "sps") c->force_sps = value;
     else if (k == "pdl_trigger") c->pdl_trigger = value;
     else if (k == "autotune") c->autotune = value;
     else if (k == "no_fold") c->no_fold = value;
@@ -1183,7 +1194,8 @@ const char* b2_context_launch_name(b2_context* c, int batch, int i) {
     s = std::string(kinds[L->kind]) + ":" + L->name;
     if (L->kind == L_CONV_TC)
         s += " bn=" + std::to_string(L->conv.bn) + " kb=" + std::to_string(L->conv.kb) +
-             " st=" + std::to_string(L->conv.stages) + (L->conv.args.a_mode == b2k::A_TILED ? " tiled" : " im2col") +
+             " st=" + std::to_string(L->conv.stages) + "x" + std::to_string(L->conv.sps) +
+             (L->conv.args.a_mode == b2k::A_TILED ? " tiled" : " im2col") +
              " grid=" + std::to_string(L->conv.grid_n) + "x" + std::to_string(L->conv.grid_m) + "x" +
              std::to_string(L->conv.args.splits) + " kblk=" + std::to_string(L->conv.args.num_kblocks);
     return s.c_str();

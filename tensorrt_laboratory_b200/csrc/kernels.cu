@@ -205,10 +205,14 @@ __device__ __forceinline__ void tma_store_commit_and_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-template <int BN, int STAGES>
+// SPS = 64-wide K sub-blocks per pipeline stage (1 or 2): one mbarrier round trip (~150-200 cycles of wait +
+// commit on the single issuing thread) is then amortised over 128 K-elements instead of 64.
+template <int BN, int STAGES, int SPS = 1>
 struct ConvCfg {
-    static constexpr int A_STAGE = 128 * 64 * 2;  // 16 KiB: 128 rows x 64 K-elements
-    static constexpr int B_STAGE = BN * 64 * 2;
+    static constexpr int A_SUBBLK = 128 * 64 * 2;  // 16 KiB: 128 rows x 64 K-elements
+    static constexpr int B_SUBBLK = BN * 64 * 2;
+    static constexpr int A_STAGE = SPS * A_SUBBLK;
+    static constexpr int B_STAGE = SPS * B_SUBBLK;
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     static constexpr int PIPE_BYTES = STAGES * (A_STAGE + B_STAGE);
     static constexpr int TILE_BYTES = 128 * BN * 2;  // one fp16 output (or residual) tile
@@ -216,8 +220,8 @@ struct ConvCfg {
 };
 
 // smem: [A stages][B stages][residual tile (optional)][barriers 256 B][bias BN x 4 B]; +1 KiB alignment slack
-__host__ __device__ constexpr int conv_smem_layout_bytes(int bn, int stages, bool residual) {
-    return stages * (128 * 64 * 2 + bn * 64 * 2) + (residual ? 128 * bn * 2 : 0) + 256 + bn * 4 + 1024;
+__host__ __device__ constexpr int conv_smem_layout_bytes(int bn, int stages, bool residual, int sps = 1) {
+    return stages * sps * (128 * 64 * 2 + bn * 64 * 2) + (residual ? 128 * bn * 2 : 0) + 256 + bn * 4 + 1024;
 }
 
 // Byte offset of (row, 16-byte chunk) inside a TMA-swizzled fp16 tile whose rows are ROWB bytes (64 or 128):
@@ -229,12 +233,13 @@ __device__ __forceinline__ uint32_t swz_off(int row, int chunk) {
     return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
 
-template <int BN, int KB, int STAGES>
+template <int BN, int KB, int STAGES, int SPS>
 __global__ void __launch_bounds__(128)
 conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
                  const ConvArgs p) {
-    using Cfg = ConvCfg<BN, STAGES>;
+    static_assert(SPS == 1 || KB == 64, "multi-sub-block stages exist for the 64-wide K path only");
+    using Cfg = ConvCfg<BN, STAGES, SPS>;
     constexpr int TPS = 64 / KB;            // TMA sub-tiles per stage: 1 (KB=64), 2 (KB=32 row-folded stem), 8 (KB=8)
     constexpr int A_SUB = 128 * KB * 2;     // bytes of one A sub-tile
     constexpr int B_SUB = BN * KB * 2;
@@ -276,7 +281,11 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     const int kb_begin = blockIdx.z * p.kb_per_split;
     const int kb_end = min(p.num_kblocks, kb_begin + p.kb_per_split);
-    const int nk = kb_end - kb_begin;
+    const int nk = (kb_end - kb_begin + SPS - 1) / SPS;  // pipeline steps (each covers up to SPS 64-wide K-blocks)
+    auto subs_in_step = [&](int i) -> int {            // 64-wide K-blocks in pipeline step i
+        const int rem = (kb_end - kb_begin) - i * SPS;
+        return rem < SPS ? rem : SPS;
+    };
     const bool split = p.splits > 1;
 
     // ---------------- prologue: nothing here depends on the previous kernel's output ----------------
@@ -312,19 +321,26 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         return n > TPS ? TPS : n;
     };
     const bool skip_mma = p.dbg_mode & 1, skip_a = KB == 64 && (p.dbg_mode & 2), skip_b = KB == 64 && (p.dbg_mode & 4);
+    // step i of the pipeline covers K-blocks kb_begin + i*SPS ... ; `kb` below is always the FIRST K-block of a step
     auto stage_bytes = [&](int kb) -> uint32_t {
-        if (KB == 64) return (skip_a ? 0 : Cfg::A_STAGE) + (skip_b ? 0 : Cfg::B_STAGE);
+        if (KB == 64) {
+            const int ns = subs_in_step((kb - kb_begin) / SPS);
+            return static_cast<uint32_t>(ns * ((skip_a ? 0 : Cfg::A_SUBBLK) + (skip_b ? 0 : Cfg::B_SUBBLK)));
+        }
         return static_cast<uint32_t>(sub_tiles(kb) * (A_SUB + B_SUB));
     };
     auto load_b = [&](int kb, int s) {  // weights: constant data, legal before pdl_wait()
         if (skip_b) return;
         uint8_t* b_dst = sB + s * Cfg::B_STAGE;
         if (KB == 64) {
-            if (p.wpacked != nullptr) {  // one contiguous run of BN/32 pre-swizzled 4 KiB blocks
-                bulk_load_1d(&full_bar[s], b_dst,
-                             p.wpacked + (static_cast<size_t>(kb) * (p.Cout >> 5) + (n0 >> 5)) * 4096, BN * 128);
-            } else {
-                tma_load_2d(&mapB, &full_bar[s], b_dst, kb * 64, n0);
+            const int ns = subs_in_step((kb - kb_begin) / SPS);
+            for (int u = 0; u < ns; ++u) {
+                if (p.wpacked != nullptr) {  // one contiguous run of BN/32 pre-swizzled 4 KiB blocks
+                    bulk_load_1d(&full_bar[s], b_dst + u * Cfg::B_SUBBLK,
+                                 p.wpacked + (static_cast<size_t>(kb + u) * (p.Cout >> 5) + (n0 >> 5)) * 4096, BN * 128);
+                } else {
+                    tma_load_2d(&mapB, &full_bar[s], b_dst + u * Cfg::B_SUBBLK, (kb + u) * 64, n0);
+                }
             }
         } else {
             const int nt = sub_tiles(kb);
@@ -362,17 +378,20 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 if (skip_a) return;
                 uint8_t* a_dst = sA + s * Cfg::A_STAGE;
                 if (KB == 64) {
-                    if (p.a_mode == A_TILED) {
-                        tma_load_2d(&mapA, &full_bar[s], a_dst, cur_cb * 64, m0);
-                    } else {
-                        tma_load_im2col_4d(&mapA, &full_bar[s], a_dst, cur_cb * 64, base_w, base_h, img0,
-                                           static_cast<uint16_t>(cur_sx), static_cast<uint16_t>(cur_r));
-                    }
-                    if (++cur_cb == p.cblocks) {
-                        cur_cb = 0;
-                        if (++cur_sx == p.kw) {
-                            cur_sx = 0;
-                            ++cur_r;
+                    const int ns = subs_in_step((kb - kb_begin) / SPS);
+                    for (int u = 0; u < ns; ++u) {
+                        if (p.a_mode == A_TILED) {
+                            tma_load_2d(&mapA, &full_bar[s], a_dst + u * Cfg::A_SUBBLK, cur_cb * 64, m0);
+                        } else {
+                            tma_load_im2col_4d(&mapA, &full_bar[s], a_dst + u * Cfg::A_SUBBLK, cur_cb * 64, base_w, base_h, img0,
+                                               static_cast<uint16_t>(cur_sx), static_cast<uint16_t>(cur_r));
+                        }
+                        if (++cur_cb == p.cblocks) {
+                            cur_cb = 0;
+                            if (++cur_sx == p.kw) {
+                                cur_sx = 0;
+                                ++cur_r;
+                            }
                         }
                     }
                 } else {
@@ -393,15 +412,15 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int npre = nk < STAGES ? nk : STAGES;
             if (elect_one_sync()) {
                 for (int i = 0; i < npre; ++i) {  // first ring pass: weights fly while the previous kernel drains
-                    mbar_expect_tx(&full_bar[i], stage_bytes(kb_begin + i));
-                    if (!kSplitProducers) load_b(kb_begin + i, i);
+                    mbar_expect_tx(&full_bar[i], stage_bytes(kb_begin + i * SPS));
+                    if (!kSplitProducers) load_b(kb_begin + i * SPS, i);
                 }
             }
             __syncwarp();
             pdl_wait();
             if (dbg && lane == 0) dbg[2] = clock64();
             if (elect_one_sync()) {
-                for (int i = 0; i < npre; ++i) load_a(kb_begin + i, i);
+                for (int i = 0; i < npre; ++i) load_a(kb_begin + i * SPS, i);
                 if (has_res && !split) load_residual();
             }
             __syncwarp();
@@ -414,9 +433,9 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (dbg) c1 = clock64();
                 if (elect_one_sync()) {
-                    mbar_expect_tx(&full_bar[s], stage_bytes(kb_begin + i));
-                    load_a(kb_begin + i, s);
-                    if (!kSplitProducers) load_b(kb_begin + i, s);
+                    mbar_expect_tx(&full_bar[s], stage_bytes(kb_begin + i * SPS));
+                    load_a(kb_begin + i * SPS, s);
+                    if (!kSplitProducers) load_b(kb_begin + i * SPS, s);
                 }
                 __syncwarp();
                 if (dbg) {
@@ -445,11 +464,17 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 if (elect_one_sync()) {
                 if (skip_mma) {
                 } else if (KB == 64) {
+                    const int ns = subs_in_step(i);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {  // 4 x (K = 16) inside one 128-byte swizzle row
-                        const uint64_t ad = make_smem_desc(a_addr + j * 32, 16, 1024, 2);
-                        const uint64_t bd = make_smem_desc(b_addr + j * 32, 16, 1024, 2);
-                        umma_f16(tmem_base, ad, bd, IDESC, (i > 0 || j > 0) ? 1u : 0u);
+                    for (int u = 0; u < SPS; ++u) {
+                        if (u < ns) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {  // 4 x (K = 16) inside one 128-byte swizzle row
+                                const uint64_t ad = make_smem_desc(a_addr + u * Cfg::A_SUBBLK + j * 32, 16, 1024, 2);
+                                const uint64_t bd = make_smem_desc(b_addr + u * Cfg::B_SUBBLK + j * 32, 16, 1024, 2);
+                                umma_f16(tmem_base, ad, bd, IDESC, (i > 0 || u > 0 || j > 0) ? 1u : 0u);
+                            }
+                        }
                     }
                 } else if (KB == 32) {
                     // row-folded stem: each sub-tile is one filter row = 32 K-elements in 64-byte swizzled rows
@@ -487,7 +512,7 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         for (int i = 0; i < nk; ++i) {
             const int s = i % STAGES;
             if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
-            if (elect_one_sync()) load_b(kb_begin + i, s);
+            if (elect_one_sync()) load_b(kb_begin + i * SPS, s);
             __syncwarp();
         }
     }
@@ -649,50 +674,52 @@ static int launch_kernel(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStre
     return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, args...));
 }
 
-template <int BN, int KB, int STAGES>
+template <int BN, int KB, int STAGES, int SPS>
 static int launch_one(const ConvLaunch& L, cudaStream_t stream) {
     dim3 grid(L.grid_n, L.grid_m, L.args.splits);
-    const size_t smem = size_t(conv_smem_layout_bytes(BN, STAGES, L.args.residual != nullptr));
-    return launch_kernel(conv_f16_tcgen05<BN, KB, STAGES>, grid, dim3(128), smem, stream, true, L.mapA, L.mapB, L.mapOut,
+    const size_t smem = size_t(conv_smem_layout_bytes(BN, STAGES, L.args.residual != nullptr, SPS));
+    return launch_kernel(conv_f16_tcgen05<BN, KB, STAGES, SPS>, grid, dim3(128), smem, stream, true, L.mapA, L.mapB, L.mapOut,
                          L.mapRes, L.args);
 }
 
-template <int BN, int KB, int STAGES>
+template <int BN, int KB, int STAGES, int SPS>
 static int init_one() {
-    const int want = conv_smem_layout_bytes(BN, STAGES, true);
-    return static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 want > 227 * 1024 ? conv_smem_layout_bytes(BN, STAGES, false) : want));
+    const int want = conv_smem_layout_bytes(BN, STAGES, true, SPS);
+    return static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES, SPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 want > 227 * 1024 ? conv_smem_layout_bytes(BN, STAGES, false, SPS) : want));
 }
 
-int conv_smem_bytes(int bn, int stages, bool residual) { return conv_smem_layout_bytes(bn, stages, residual); }
+int conv_smem_bytes(int bn, int stages, bool residual, int sps) { return conv_smem_layout_bytes(bn, stages, residual, sps); }
 
+// instantiated (BN, KB, STAGES, SPS) configurations
 #define B2_FOR_EACH_CONV(X) \
-    X(32, 64, 1) X(32, 64, 2) X(32, 64, 4) X(32, 64, 8) \
-    X(64, 64, 1) X(64, 64, 2) X(64, 64, 4) X(64, 64, 8) \
-    X(128, 64, 1) X(128, 64, 2) X(128, 64, 4) X(256, 64, 2) X(256, 64, 4) \
-    X(32, 8, 2) X(32, 8, 4) X(64, 8, 2) X(64, 8, 4) X(64, 8, 8) X(128, 8, 4) \
-    X(32, 32, 2) X(32, 32, 4) X(64, 32, 1) X(64, 32, 2) X(64, 32, 4) X(128, 32, 2) X(128, 32, 4)
+    X(32, 64, 1, 1) X(32, 64, 2, 1) X(32, 64, 4, 1) X(32, 64, 8, 1) \
+    X(64, 64, 1, 1) X(64, 64, 2, 1) X(64, 64, 4, 1) X(64, 64, 8, 1) \
+    X(128, 64, 1, 1) X(128, 64, 2, 1) X(128, 64, 4, 1) X(256, 64, 2, 1) X(256, 64, 4, 1) \
+    X(32, 64, 2, 2) X(32, 64, 4, 2) X(64, 64, 2, 2) X(64, 64, 4, 2) X(128, 64, 2, 2) X(256, 64, 2, 2) \
+    X(32, 8, 2, 1) X(32, 8, 4, 1) X(64, 8, 2, 1) X(64, 8, 4, 1) X(64, 8, 8, 1) X(128, 8, 4, 1) \
+    X(32, 32, 2, 1) X(32, 32, 4, 1) X(64, 32, 1, 1) X(64, 32, 2, 1) X(64, 32, 4, 1) X(128, 32, 2, 1) X(128, 32, 4, 1)
 
 int init_conv_kernels() {
     int e = 0;
-#define B2_INIT(BN_, KB_, ST_) \
-    if ((e = init_one<BN_, KB_, ST_>())) return e;
+#define B2_INIT(BN_, KB_, ST_, SPS_) \
+    if ((e = init_one<BN_, KB_, ST_, SPS_>())) return e;
     B2_FOR_EACH_CONV(B2_INIT)
 #undef B2_INIT
     return 0;
 }
 
 int launch_conv_f16_tcgen05(const ConvLaunch& L, cudaStream_t stream) {
-#define B2_CASE(BN_, KB_, ST_) \
-    if (L.bn == BN_ && L.kb == KB_ && L.stages == ST_) return launch_one<BN_, KB_, ST_>(L, stream);
+#define B2_CASE(BN_, KB_, ST_, SPS_) \
+    if (L.bn == BN_ && L.kb == KB_ && L.stages == ST_ && L.sps == SPS_) return launch_one<BN_, KB_, ST_, SPS_>(L, stream);
     B2_FOR_EACH_CONV(B2_CASE)
 #undef B2_CASE
     return static_cast<int>(cudaErrorInvalidValue);
 }
 
-bool conv_config_exists(int bn, int kb, int stages) {
-#define B2_HAS(BN_, KB_, ST_) \
-    if (bn == BN_ && kb == KB_ && stages == ST_) return true;
+bool conv_config_exists(int bn, int kb, int stages, int sps) {
+#define B2_HAS(BN_, KB_, ST_, SPS_) \
+    if (bn == BN_ && kb == KB_ && stages == ST_ && sps == SPS_) return true;
     B2_FOR_EACH_CONV(B2_HAS)
 #undef B2_HAS
     return false;

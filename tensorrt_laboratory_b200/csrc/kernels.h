@@ -52,6 +52,7 @@ struct ConvLaunch {
     int kb;            // K elements per TMA sub-tile: 64 (SWIZZLE_128B), 32 (SWIZZLE_64B: stem with the filter
                        // row folded into "channels" through an overlapping pixel stride) or 8 (no swizzle)
     int stages;        // smem pipeline depth: 1 / 2 / 4 / 8
+    int sps;           // 64-wide K sub-blocks per pipeline stage: 1 or 2 (KB == 64 only)
     int grid_m, grid_n;
 };
 
@@ -59,8 +60,8 @@ struct ConvLaunch {
 int launch_conv_f16_tcgen05(const ConvLaunch& L, cudaStream_t stream);
 // one-time: opt in to large dynamic shared memory for every instantiation
 int init_conv_kernels();
-bool conv_config_exists(int bn, int kb, int stages);  // is this (tile, K-chunk, depth) instantiated?
-int conv_smem_bytes(int bn, int stages, bool residual);  // dynamic shared memory of one CTA
+bool conv_config_exists(int bn, int kb, int stages, int sps = 1);  // is this configuration instantiated?
+int conv_smem_bytes(int bn, int stages, bool residual, int sps = 1);  // dynamic shared memory of one CTA
 // programmatic dependent launch on/off for every kernel of this library (default on)
 void set_pdl(bool on);
 bool get_pdl();

@@ -65,6 +65,17 @@ def test_every_pipeline_depth(gpu, stages):
     _check(128, 28, 128, 3, 1, batch=2, options={"bn": 64, "stages": stages})
 
 
+@pytest.mark.parametrize("bn,stages", [(32, 2), (64, 2), (64, 4), (128, 2), (256, 2)])
+def test_double_width_pipeline_stages(gpu, bn, stages):
+    # 128 K-elements per mbarrier round trip; 9 (odd) and 18 K-blocks exercise the half-filled last stage
+    a = _check(64, 28, 256, 3, 1, batch=2, options={"bn": bn, "stages": stages, "sps": 2})
+    b = _check(64, 28, 256, 3, 1, batch=2, options={"bn": bn, "stages": stages, "sps": 1})
+    np.testing.assert_array_equal(a, b)
+    _check(128, 14, 256, 3, 1, batch=2, residual=True, options={"bn": bn, "stages": stages, "sps": 2})
+    if bn == 64:
+        _check(512, 7, 512, 3, 1, batch=2, options={"bn": 64, "stages": 2, "sps": 2, "splits": 3})
+
+
 @pytest.mark.parametrize("splits", [2, 3, 4, 8])  # 8: bn 64 keeps tiles*splits within the workspace bound
 def test_split_k_matches_oracle_and_is_deterministic(gpu, splits):
     # res5-like: M = 2*7*7 = 98 (one ragged tile), K = 4608 -> 72 k-blocks
