@@ -278,7 +278,10 @@ def run_b200(args):
     roofline = {
         "bound": "tensor", "kernel": "conv_f16_tcgen05 (all %d conv launches of one forward pass)" % n_conv,
         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-        "traffic": None, "peak_source": peak_src,
+        # DRAM bytes (read+write) of the 53 conv launches of ONE forward pass = one step, from the committed ncu pass
+        # profiles/ncu_metrics_r1f_kernel_v4.csv (cold L2; outputs stay L2-resident inside each kernel)
+        "traffic": 267.7e6, "traffic_source": "profiles/ncu_metrics_r1f_kernel_v4.csv",
+        "peak_source": peak_src,
         "flops_per_step": conv_flops, "conv_share_of_step": conv_share,
         "hbm_view": {"algorithmic_bytes_per_step": ALGO_BYTES_PER_STEP,
                      "achieved_gbs": ALGO_BYTES_PER_STEP / (ms_per_step * 1e-3) / 1e9, "peak_gbs": peak_hbm},

@@ -107,7 +107,9 @@ int b2_context_nb_launches(b2_context* c, int batch);
 /* knobs: "graph"=0/1 replay the forward as a cached CUDA graph (default 1); "simt"=0/1 force the
  * SIMT reference kernels instead of the tcgen05 path (debug); "bn"/"stages"/"splits" force the conv tile,
  * pipeline depth and split-K factor (0 = cost model); "pdl"=0/1 programmatic dependent launch (process-wide);
- * "pdl_trigger"=0/1 release point of the dependent kernel; returns B2_EINVAL for unknown keys */
+ * "pdl_trigger"=0/1 release point of the dependent kernel; "autotune"=0 (cost model) / 1 (latency) / N>=2 (N-stream
+ * throughput, default 4) on-device tactic selection; "sps"=2 double-width pipeline stages; returns B2_EINVAL for
+ * unknown keys.  Environment: B2_TUNE_CACHE=<file> persists tuned tactics across processes (timing cache). */
 int b2_context_set_option(b2_context* c, const char* key, int value);
 
 /* per-layer device timing of one forward (serialised launches, CUDA events): fills up to `cap`

@@ -191,6 +191,7 @@ struct b2_engine {
     double flops_per_item = 0;
     std::mutex tune_mutex;
     std::map<std::pair<int, int>, ConvConfig> tuned;  // (op index, batch) -> measured-best configuration
+    bool tune_cache_loaded = false;
     bool half() const { return precision == B2_PREC_FP16; }
 };
 
@@ -664,6 +665,30 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, Conv
     return B2_OK;
 }
 
+// ---- tactic cache file (B2_TUNE_CACHE=<path>): the analogue of a TensorRT timing cache.  One line per tuned conv:
+//      <engine name> <op index> <batch> <bn> <stages> <splits> <sps>
+void tune_cache_load(b2_engine* e) {
+    if (e->tune_cache_loaded) return;
+    e->tune_cache_loaded = true;
+    const char* path = getenv("B2_TUNE_CACHE");
+    if (!path) return;
+    FILE* f = fopen(path, "r");
+    if (!f) return;
+    char name[128];
+    int op, batch, bn, st, sp, sps;
+    while (fscanf(f, "%127s %d %d %d %d %d %d", name, &op, &batch, &bn, &st, &sp, &sps) == 7)
+        if (e->name == name && op >= 0 && op < int(e->ops.size())) e->tuned[{op, batch}] = ConvConfig{bn, st, sp, 0.0, sps};
+    fclose(f);
+}
+void tune_cache_append(const b2_engine* e, int op, int batch, const ConvConfig& cfg) {
+    const char* path = getenv("B2_TUNE_CACHE");
+    if (!path) return;
+    FILE* f = fopen(path, "a");
+    if (!f) return;
+    fprintf(f, "%s %d %d %d %d %d %d\n", e->name.c_str(), op, batch, cfg.bn, cfg.stages, cfg.splits, cfg.sps);
+    fclose(f);
+}
+
 // ---- per-batch launch plan ---------------------------------------------------------------------
 int build_plan(b2_context* c, int batch, Plan** out) {
     b2_engine* e = c->e;
@@ -744,6 +769,7 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                         bool have = false;
                         {
                             std::lock_guard<std::mutex> lock(e->tune_mutex);
+                            tune_cache_load(e);
                             auto it = e->tuned.find({op_index, batch});
                             if (it != e->tuned.end()) cfg = it->second, have = true;
                         }
@@ -764,6 +790,7 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                                     if (rc) return rc;
                                     std::lock_guard<std::mutex> lock(e->tune_mutex);
                                     e->tuned[{op_index, e->max_batch}] = top;
+                                    tune_cache_append(e, op_index, e->max_batch, top);
                                 }
                                 splits = top.splits;
                             }
@@ -771,6 +798,7 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                             if (rc) return rc;
                             std::lock_guard<std::mutex> lock(e->tune_mutex);
                             e->tuned[{op_index, batch}] = cfg;
+                            tune_cache_append(e, op_index, batch, cfg);
                         }
                     }
                     int rc = make_conv_launch(c, op, batch, cfg, &L.conv);
