@@ -190,6 +190,7 @@ struct b2_engine {
     bool inspect_only = false;
     double flops_per_item = 0;
     std::mutex tune_mutex;
+    std::mutex tune_run_mutex;  // serialises on-device tactic timing across contexts of this engine
     std::map<std::pair<int, int>, ConvConfig> tuned;  // (op index, batch) -> measured-best configuration
     bool tune_cache_loaded = false;
     bool half() const { return precision == B2_PREC_FP16; }
@@ -770,6 +771,13 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                         {
                             std::lock_guard<std::mutex> lock(e->tune_mutex);
                             tune_cache_load(e);
+                            auto it = e->tuned.find({op_index, batch});
+                            if (it != e->tuned.end()) cfg = it->second, have = true;
+                        }
+                        std::unique_lock<std::mutex> run_lock(e->tune_run_mutex, std::defer_lock);
+                        if (!have) {  // one context tunes at a time; the others then find the result cached
+                            run_lock.lock();
+                            std::lock_guard<std::mutex> lock(e->tune_mutex);
                             auto it = e->tuned.find({op_index, batch});
                             if (it != e->tuned.end()) cfg = it->second, have = true;
                         }
