@@ -151,6 +151,7 @@ struct ConvConfig {
     int bn, stages, splits;
     double est_us;
     int sps = 1;  // 64-wide K sub-blocks per pipeline stage
+    int ws = 0;   // > 0: persistent warp-specialised kernel with this many CTAs
 };
 // A pipeline deeper than the K loop is pure shared-memory cost: admit depths up to the smallest instantiated one
 // that covers the loop (or the deepest available when none does).
@@ -221,6 +222,7 @@ struct b2_context {
     int force_stages = 0;
     int force_splits = 0;
     int force_sps = 0;
+    int force_ws = 0;   // 1: only the persistent warp-specialised tactic where it applies, -1: never
     int pdl_trigger = 1;
     int no_pack = 0;    // reserved (packed plans cannot fall back to the tensor-map weight path)
     int no_fold = 0;    // 1: run the stem through the generic 8-channel tap path instead of the row-folded one
@@ -498,6 +500,9 @@ int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& c
     cl.stages = cfg.stages;
     cl.sps = cfg.sps > 0 ? cfg.sps : 1;
     cl.grid_n = int(r.cout_phys) / cl.bn;
+    cl.ws_ctas = cfg.ws;
+    cl.args.tiles_m = cl.grid_m;
+    cl.args.tiles_n = cl.grid_n;
     b2k::ConvArgs& a = cl.args;
     a.splits = cfg.splits;
     a.kb_per_split = (nkb + cfg.splits - 1) / cfg.splits;
@@ -594,16 +599,30 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, Conv
     const int iters = 12;
     const int m_tiles = (M + 127) / 128;
     const int split_cands[4] = {1, 2, 4, 8};
+    std::vector<ConvConfig> candidates;
     for (int bn : bns) {
         if (int(r.cout_phys) % bn) continue;
         const int tiles = m_tiles * (int(r.cout_phys) / bn);
+        for (int ws = 0; ws <= 1; ++ws)
         for (int sp : split_cands)
         for (int sps = 1; sps <= 2; ++sps)
         for (int st : stgs) {
             if (fixed_splits > 0 && sp != fixed_splits) continue;
+            if (ws) {  // persistent warp-specialised tactic: 64-wide K, packed weights, no split-K
+                if (c->force_ws < 0 || kbsz != 64 || !(r.relu & 2) || sp != 1) continue;
+                if (!b2k::conv_ws_config_exists(bn, st, sps) || b2k::conv_ws_smem(bn, st, sps, r.res >= 0) > 227 * 1024) continue;
+                if (sps == 2 && nkb < 4) continue;
+            } else {
+            if (c->force_ws > 0 && kbsz == 64 && (r.relu & 2)) continue;
             if (!b2k::conv_config_exists(bn, kbsz, st, sps)) continue;
             if (b2k::conv_smem_bytes(bn, st, r.res >= 0, sps) > 227 * 1024) continue;
+            }
             const int kpc = (nkb + sp - 1) / sp;
+            if (ws) {
+                candidates.push_back(ConvConfig{bn, st, 1, 0.0, sps, std::min(tiles, 148)});
+                if (tiles > 74) candidates.push_back(ConvConfig{bn, st, 1, 0.0, sps, 74});  // half the SMs per stream
+                continue;
+            }
             if (sps == 2 && kpc < 4) continue;  // double-width stages only pay on long K loops
             if (sps == 1 && !stage_depth_useful(bn, kbsz, st, kpc)) continue;
             if (sps == 2 && st * 2 > kpc + 2) continue;
@@ -611,7 +630,13 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, Conv
                            (sp - 1) * kpc >= nkb ||
                            size_t(tiles) * sp * 128 * bn * 4 > kSplitWorkspaceBytes))
                 continue;  // split-K only where the plain grid leaves SMs idle
-            ConvConfig cand{bn, st, sp, 0.0, sps};
+            candidates.push_back(ConvConfig{bn, st, sp, 0.0, sps, 0});
+        }
+    }
+    for (const ConvConfig& cand : candidates) {
+        {
+            const int bn = cand.bn, st = cand.stages, sp = cand.splits;
+            const int tiles = m_tiles * (int(r.cout_phys) / bn);
             b2k::ConvLaunch cl0;
             if ((status = make_conv_launch(c, op, batch, cand, &cl0))) break;
             // concurrent split-K launches must not share arrival counters or partial-tile storage
@@ -667,7 +692,7 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, Conv
 }
 
 // ---- tactic cache file (B2_TUNE_CACHE=<path>): the analogue of a TensorRT timing cache.  One line per tuned conv:
-//      <engine name> <op index> <batch> <bn> <stages> <splits> <sps>
+//      <engine name> <op index> <batch> <bn> <stages> <splits> <sps> <persistent CTAs or 0>
 void tune_cache_load(b2_engine* e) {
     if (e->tune_cache_loaded) return;
     e->tune_cache_loaded = true;
@@ -676,9 +701,9 @@ void tune_cache_load(b2_engine* e) {
     FILE* f = fopen(path, "r");
     if (!f) return;
     char name[128];
-    int op, batch, bn, st, sp, sps;
-    while (fscanf(f, "%127s %d %d %d %d %d %d", name, &op, &batch, &bn, &st, &sp, &sps) == 7)
-        if (e->name == name && op >= 0 && op < int(e->ops.size())) e->tuned[{op, batch}] = ConvConfig{bn, st, sp, 0.0, sps};
+    int op, batch, bn, st, sp, sps, ws;
+    while (fscanf(f, "%127s %d %d %d %d %d %d %d", name, &op, &batch, &bn, &st, &sp, &sps, &ws) == 8)
+        if (e->name == name && op >= 0 && op < int(e->ops.size())) e->tuned[{op, batch}] = ConvConfig{bn, st, sp, 0.0, sps, ws};
     fclose(f);
 }
 void tune_cache_append(const b2_engine* e, int op, int batch, const ConvConfig& cfg) {
@@ -686,7 +711,7 @@ void tune_cache_append(const b2_engine* e, int op, int batch, const ConvConfig& 
     if (!path) return;
     FILE* f = fopen(path, "a");
     if (!f) return;
-    fprintf(f, "%s %d %d %d %d %d %d\n", e->name.c_str(), op, batch, cfg.bn, cfg.stages, cfg.splits, cfg.sps);
+    fprintf(f, "%s %d %d %d %d %d %d %d\n", e->name.c_str(), op, batch, cfg.bn, cfg.stages, cfg.splits, cfg.sps, cfg.ws);
     fclose(f);
 }
 
@@ -764,6 +789,10 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                     if (c->force_sps == 2 && b2k::conv_config_exists(cfg.bn, kbsz, cfg.stages, 2) &&
                         b2k::conv_smem_bytes(cfg.bn, cfg.stages, r.res >= 0, 2) <= 227 * 1024)
                         cfg.sps = 2;
+                    if (c->force_ws > 0 && kbsz == 64 && (r.relu & 2) && cfg.splits == 1 &&
+                        b2k::conv_ws_config_exists(cfg.bn, cfg.stages, cfg.sps) &&
+                        b2k::conv_ws_smem(cfg.bn, cfg.stages, cfg.sps, r.res >= 0) <= 227 * 1024)
+                        cfg.ws = std::min(((M + 127) / 128) * (int(r.cout_phys) / cfg.bn), c->force_ws > 1 ? c->force_ws : 148);
                     const bool forced = c->force_bn || c->force_stages || c->force_splits || c->force_sps;
                     const int op_index = int(&op - &e->ops[0]);
                     if (!forced && c->autotune) {
@@ -1053,6 +1082,7 @@ int b2_context_create(b2_engine* e, b2_context** out) {
     c->force_stages = env_int("B2_FORCE_STAGES", 0);
     c->force_splits = env_int("B2_FORCE_SPLITS", 0);
     c->force_sps = env_int("B2_FORCE_SPS", 0);
+    c->force_ws = env_int("B2_FORCE_WS", 0);
     c->pdl_trigger = env_int("B2_PDL_TRIGGER", 1);
     c->autotune = env_int("B2_AUTOTUNE", 4);
     if (getenv("B2_PDL")) b2k::set_pdl(env_int("B2_PDL", 1) != 0);
@@ -1106,6 +1136,7 @@ int b2_context_set_option(b2_context* c, const char* key, int value) {
     else if (k == "stages") c->force_stages = value;
     else if (k == "splits") c->force_splits = value;
     else if (k == "sps") c->force_sps = value;
+    else if (k == "ws") c->force_ws = value;
     else if (k == "pdl_trigger") c->pdl_trigger = value;
     else if (k == "autotune") c->autotune = value;
     else if (k == "no_fold") c->no_fold = value;
@@ -1231,6 +1262,7 @@ const char* b2_context_launch_name(b2_context* c, int batch, int i) {
     if (L->kind == L_CONV_TC)
         s += " bn=" + std::to_string(L->conv.bn) + " kb=" + std::to_string(L->conv.kb) +
              " st=" + std::to_string(L->conv.stages) + "x" + std::to_string(L->conv.sps) +
+             (L->conv.ws_ctas ? " ws=" + std::to_string(L->conv.ws_ctas) : std::string()) +
              (L->conv.args.a_mode == b2k::A_TILED ? " tiled" : " im2col") +
              " grid=" + std::to_string(L->conv.grid_n) + "x" + std::to_string(L->conv.grid_m) + "x" +
              std::to_string(L->conv.args.splits) + " kblk=" + std::to_string(L->conv.args.num_kblocks);

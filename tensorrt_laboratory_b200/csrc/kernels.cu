@@ -250,7 +250,9 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     constexpr uint32_t IDESC = make_idesc_f16(128, BN);
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1 KiB alignment by OFFSETTING the __shared__ array (a uintptr_t round trip would turn every later access into a
+    // generic LD.E / ST.E instead of LDS / STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const bool has_res = p.residual != nullptr;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * Cfg::A_STAGE;
@@ -655,6 +657,282 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
 }
 
+// =================================================================================================
+// conv_f16_tcgen05_ws -- persistent, warp-specialised variant (a TACTIC next to the one-tile-per-CTA kernel).
+//   gridDim.x CTAs walk the tile list with a static stride.  8 warps:
+//     warp 0  activation producer (TMA, also the residual tile)      warp 1  MMA issuer
+//     warp 2  weight producer (cp.async.bulk) + TMEM owner           warp 3  idle
+//     warps 4-7  epilogue (TMEM lane quadrant = warp % 4)
+//   Two TMEM accumulators: the epilogue of tile i (TMEM -> regs -> swizzled smem -> TMA store) overlaps the loads
+//   and MMAs of tile i+1; the prologue (barrier init, TMEM alloc) and the first TMA round trip are paid once per CTA
+//   instead of once per tile.  64-channel K-blocks with packed weights only; no split-K.
+// =================================================================================================
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__host__ __device__ constexpr int conv_ws_smem_bytes(int bn, int stages, int sps, bool residual) {
+    return stages * sps * (128 * 64 * 2 + bn * 64 * 2) + 128 * bn * 2 + (residual ? 128 * bn * 2 : 0) + 256 + 1024;
+}
+
+template <int BN, int STAGES, int SPS>
+__global__ void __launch_bounds__(256)
+conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapOut,
+                    const __grid_constant__ CUtensorMap mapRes, const ConvArgs p) {
+    constexpr int A_SUBBLK = 128 * 64 * 2;
+    constexpr int B_SUBBLK = BN * 64 * 2;
+    constexpr int A_STAGE = SPS * A_SUBBLK;
+    constexpr int B_STAGE = SPS * B_SUBBLK;
+    constexpr int PIPE_BYTES = STAGES * (A_STAGE + B_STAGE);
+    constexpr int TILE_BYTES = 128 * BN * 2;
+    constexpr int NG = BN / 32;
+    constexpr int OW = BN >= 64 ? 64 : 32;
+    constexpr int OROWB = OW * 2;
+    constexpr int NBOX = BN / OW;
+    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators (power of two for BN in {32..256})
+    constexpr uint32_t IDESC = make_idesc_f16(128, BN);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const bool has_res = p.residual != nullptr;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE;
+    uint8_t* sOut = smem + PIPE_BYTES;
+    uint8_t* sRes = sOut + TILE_BYTES;
+    uint8_t* tail = sRes + (has_res ? TILE_BYTES : 0);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;   // [2]
+    uint64_t* acc_empty = acc_full + 2;        // [2]
+    uint64_t* res_full = acc_empty + 2;
+    uint64_t* res_empty = res_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int nsteps = (p.num_kblocks + SPS - 1) / SPS;  // pipeline steps per tile
+    auto subs_in_step = [&](int i) -> int {
+        const int rem = p.num_kblocks - i * SPS;
+        return rem < SPS ? rem : SPS;
+    };
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapOut);
+        if (has_res) tma_prefetch_desc(&mapRes);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 1);
+        }
+        mbar_init(res_full, 1);
+        mbar_init(res_empty, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (p.pdl_trigger == 0) pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ================= activation producer =================
+        pdl_wait();
+        int g = 0;   // global pipeline step counter of this CTA (across tiles)
+        int lt = 0;  // local tile counter
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const int mt = tile / p.tiles_n;
+            const int nt = tile - mt * p.tiles_n;
+            const int m0 = mt * 128, n0 = nt * BN;
+            int img0 = 0, p0 = 0, q0 = 0;
+            if (p.a_mode == A_IM2COL) {
+                img0 = m0 / p.HoWo;
+                const int rem = m0 - img0 * p.HoWo;
+                p0 = rem / p.Wo;
+                q0 = rem - p0 * p.Wo;
+            }
+            const int base_w = q0 * p.stride_w - p.pad_w;
+            const int base_h = p0 * p.stride_h - p.pad_h;
+            if (has_res) {  // residual tile of THIS tile: wait until the epilogue has consumed the previous one
+                mbar_wait(res_empty, (lt & 1) ^ 1);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(res_full, TILE_BYTES);
+#pragma unroll
+                    for (int b = 0; b < NBOX; ++b) tma_load_2d(&mapRes, res_full, sRes + b * (128 * OROWB), n0 + b * OW, m0);
+                }
+                __syncwarp();
+            }
+            int cur_cb = 0, cur_r = 0, cur_sx = 0;
+            for (int i = 0; i < nsteps; ++i, ++g) {
+                const int s = g % STAGES;
+                mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+                if (elect_one_sync()) {
+                    const int ns = subs_in_step(i);
+                    mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(ns * (A_SUBBLK + B_SUBBLK)));
+                    uint8_t* a_dst = sA + s * A_STAGE;
+                    for (int u = 0; u < ns; ++u) {
+                        if (p.a_mode == A_TILED)
+                            tma_load_2d(&mapA, &full_bar[s], a_dst + u * A_SUBBLK, cur_cb * 64, m0);
+                        else
+                            tma_load_im2col_4d(&mapA, &full_bar[s], a_dst + u * A_SUBBLK, cur_cb * 64, base_w, base_h, img0,
+                                               static_cast<uint16_t>(cur_sx), static_cast<uint16_t>(cur_r));
+                        if (++cur_cb == p.cblocks) {
+                            cur_cb = 0;
+                            if (++cur_sx == p.kw) {
+                                cur_sx = 0;
+                                ++cur_r;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 2) {
+        // ================= weight producer (constants: no dependency wait) =================
+        int g = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int nt = tile % p.tiles_n;
+            const int n0 = nt * BN;
+            for (int i = 0; i < nsteps; ++i, ++g) {
+                const int s = g % STAGES;
+                if (g >= STAGES) mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+                if (elect_one_sync()) {
+                    const int ns = subs_in_step(i);
+                    for (int u = 0; u < ns; ++u)
+                        bulk_load_1d(&full_bar[s], sB + s * B_STAGE + u * B_SUBBLK,
+                                     p.wpacked + (static_cast<size_t>(i * SPS + u) * (p.Cout >> 5) + (n0 >> 5)) * 4096, BN * 128);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        int g = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const int b = lt & 1;
+            mbar_wait(&acc_empty[b], ((lt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(b * BN);
+            for (int i = 0; i < nsteps; ++i, ++g) {
+                const int s = g % STAGES;
+                mbar_wait(&full_bar[s], (g / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + s * A_STAGE);
+                const uint32_t b_addr = smem_u32(sB + s * B_STAGE);
+                if (elect_one_sync()) {
+                    const int ns = subs_in_step(i);
+#pragma unroll
+                    for (int u = 0; u < SPS; ++u) {
+                        if (u < ns) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint64_t ad = make_smem_desc(a_addr + u * A_SUBBLK + j * 32, 16, 1024, 2);
+                                const uint64_t bd = make_smem_desc(b_addr + u * B_SUBBLK + j * 32, 16, 1024, 2);
+                                umma_f16(tmem_d, ad, bd, IDESC, (i > 0 || u > 0 || j > 0) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                    if (i == nsteps - 1) umma_commit(&acc_full[b]);
+                }
+                __syncwarp();
+            }
+        }
+        if (p.pdl_trigger == 1) pdl_launch_dependents();
+    } else if (warp >= 4) {
+        // ================= epilogue (4 warps = 128 threads, one accumulator row each) =================
+        pdl_wait();
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        const bool e0 = (threadIdx.x == 128);
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const int mt = tile / p.tiles_n;
+            const int nt = tile - mt * p.tiles_n;
+            const int m0 = mt * 128, n0 = nt * BN;
+            const int b = lt & 1;
+            mbar_wait(&acc_full[b], (lt >> 1) & 1);
+            tc_fence_after();
+            if (has_res) mbar_wait(res_full, lt & 1);
+            // (A) the previous tile's TMA store has finished READING the staging tile (e0 waited before arriving)
+            named_bar_sync(1, 128);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(b * BN);
+            const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0);
+            constexpr int GP = NG >= 2 ? 2 : 1;
+#pragma unroll
+            for (int g0 = 0; g0 < NG; g0 += GP) {
+                uint32_t acc[GP][32];
+#pragma unroll
+                for (int j = 0; j < GP; ++j) tmem_ld32(taddr + (g0 + j) * 32, acc[j]);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < GP; ++j) {
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const int col = (g0 + j) * 32 + qq * 8;
+                        const int box = col / OW;
+                        const int chunk = (col % OW) / 8;
+                        const uint32_t so = static_cast<uint32_t>(box * (128 * OROWB)) + swz_off<OROWB>(row, chunk);
+                        const float4 b0 = __ldg(bias4 + col / 4), b1 = __ldg(bias4 + col / 4 + 1);
+                        float v[8];
+                        v[0] = __uint_as_float(acc[j][qq * 8 + 0]) + b0.x;
+                        v[1] = __uint_as_float(acc[j][qq * 8 + 1]) + b0.y;
+                        v[2] = __uint_as_float(acc[j][qq * 8 + 2]) + b0.z;
+                        v[3] = __uint_as_float(acc[j][qq * 8 + 3]) + b0.w;
+                        v[4] = __uint_as_float(acc[j][qq * 8 + 4]) + b1.x;
+                        v[5] = __uint_as_float(acc[j][qq * 8 + 5]) + b1.y;
+                        v[6] = __uint_as_float(acc[j][qq * 8 + 6]) + b1.z;
+                        v[7] = __uint_as_float(acc[j][qq * 8 + 7]) + b1.w;
+                        if (has_res) {
+                            const uint4 rv = *reinterpret_cast<const uint4*>(sRes + so);
+                            const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 rf = __half22float2(r2[i]);
+                                v[2 * i] += rf.x;
+                                v[2 * i + 1] += rf.y;
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
+                        }
+                        uint4 o;
+                        __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                        *reinterpret_cast<uint4*>(sOut + so) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            // (B) every epilogue thread has drained its TMEM rows, read its residual row and staged its output row
+            named_bar_sync(2, 128);
+            if (e0) {
+                mbar_arrive(&acc_empty[b]);        // accumulator b may be overwritten by tile lt+2
+                if (has_res) mbar_arrive(res_empty);  // residual buffer may be refilled
+#pragma unroll
+                for (int bx = 0; bx < NBOX; ++bx) tma_store_2d(&mapOut, sOut + bx * (128 * OROWB), n0 + bx * OW, m0);
+                tma_store_commit_and_wait_read();  // before (A) of the next tile lets anyone overwrite sOut
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 static bool g_use_pdl = true;
 void set_pdl(bool on) { g_use_pdl = on; }
 bool get_pdl() { return g_use_pdl; }
@@ -700,8 +978,12 @@ int conv_smem_bytes(int bn, int stages, bool residual, int sps) { return conv_sm
     X(32, 8, 2, 1) X(32, 8, 4, 1) X(64, 8, 2, 1) X(64, 8, 4, 1) X(64, 8, 8, 1) X(128, 8, 4, 1) \
     X(32, 32, 2, 1) X(32, 32, 4, 1) X(64, 32, 1, 1) X(64, 32, 2, 1) X(64, 32, 4, 1) X(128, 32, 2, 1) X(128, 32, 4, 1)
 
+int init_conv_ws_kernels();
+int launch_conv_f16_tcgen05_ws(const ConvLaunch& L, cudaStream_t stream);
+
 int init_conv_kernels() {
-    int e = 0;
+    int e = init_conv_ws_kernels();
+    if (e) return e;
 #define B2_INIT(BN_, KB_, ST_, SPS_) \
     if ((e = init_one<BN_, KB_, ST_, SPS_>())) return e;
     B2_FOR_EACH_CONV(B2_INIT)
@@ -710,12 +992,57 @@ int init_conv_kernels() {
 }
 
 int launch_conv_f16_tcgen05(const ConvLaunch& L, cudaStream_t stream) {
+    if (L.ws_ctas > 0) return launch_conv_f16_tcgen05_ws(L, stream);
 #define B2_CASE(BN_, KB_, ST_, SPS_) \
     if (L.bn == BN_ && L.kb == KB_ && L.stages == ST_ && L.sps == SPS_) return launch_one<BN_, KB_, ST_, SPS_>(L, stream);
     B2_FOR_EACH_CONV(B2_CASE)
 #undef B2_CASE
     return static_cast<int>(cudaErrorInvalidValue);
 }
+
+// instantiated persistent (BN, STAGES, SPS) configurations
+#define B2_FOR_EACH_CONV_WS(X) \
+    X(32, 4, 1) X(64, 2, 1) X(64, 4, 1) X(64, 2, 2) X(64, 4, 2) X(128, 2, 1) X(128, 4, 1) X(128, 2, 2) X(256, 2, 1)
+
+template <int BN, int STAGES, int SPS>
+static int launch_one_ws(const ConvLaunch& L, cudaStream_t stream) {
+    const size_t smem = size_t(conv_ws_smem_bytes(BN, STAGES, SPS, L.args.residual != nullptr));
+    return launch_kernel(conv_f16_tcgen05_ws<BN, STAGES, SPS>, dim3(L.ws_ctas), dim3(256), smem, stream, true, L.mapA, L.mapOut,
+                         L.mapRes, L.args);
+}
+
+int init_conv_ws_kernels() {
+    int e = 0;
+#define B2_INIT_WS(BN_, ST_, SPS_)                                                                                        \
+    {                                                                                                                     \
+        const int want = conv_ws_smem_bytes(BN_, ST_, SPS_, true);                                                        \
+        e = static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05_ws<BN_, ST_, SPS_>,                                    \
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
+                                                  want > 227 * 1024 ? conv_ws_smem_bytes(BN_, ST_, SPS_, false) : want)); \
+        if (e) return e;                                                                                                  \
+    }
+    B2_FOR_EACH_CONV_WS(B2_INIT_WS)
+#undef B2_INIT_WS
+    return 0;
+}
+
+int launch_conv_f16_tcgen05_ws(const ConvLaunch& L, cudaStream_t stream) {
+#define B2_CASE_WS(BN_, ST_, SPS_) \
+    if (L.bn == BN_ && L.stages == ST_ && L.sps == SPS_) return launch_one_ws<BN_, ST_, SPS_>(L, stream);
+    B2_FOR_EACH_CONV_WS(B2_CASE_WS)
+#undef B2_CASE_WS
+    return static_cast<int>(cudaErrorInvalidValue);
+}
+
+bool conv_ws_config_exists(int bn, int stages, int sps) {
+#define B2_HAS_WS(BN_, ST_, SPS_) \
+    if (bn == BN_ && stages == ST_ && sps == SPS_) return true;
+    B2_FOR_EACH_CONV_WS(B2_HAS_WS)
+#undef B2_HAS_WS
+    return false;
+}
+
+int conv_ws_smem(int bn, int stages, int sps, bool residual) { return conv_ws_smem_bytes(bn, stages, sps, residual); }
 
 bool conv_config_exists(int bn, int kb, int stages, int sps) {
 #define B2_HAS(BN_, KB_, ST_, SPS_) \

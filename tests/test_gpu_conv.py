@@ -76,6 +76,23 @@ def test_double_width_pipeline_stages(gpu, bn, stages):
         _check(512, 7, 512, 3, 1, batch=2, options={"bn": 64, "stages": 2, "sps": 2, "splits": 3})
 
 
+@pytest.mark.parametrize("bn,stages,sps", [(32, 4, 1), (64, 2, 1), (64, 4, 2), (128, 2, 1), (128, 2, 2), (256, 2, 1)])
+def test_persistent_warp_specialised_tactic(gpu, bn, stages, sps):
+    """conv_f16_tcgen05_ws: persistent CTAs, separate epilogue warps, double-buffered TMEM.  Same K order as the
+    one-tile-per-CTA kernel -> bit-identical results."""
+    opts = {"bn": bn, "stages": stages, "sps": sps}
+    # many tiles per CTA (M = 4*56*56 = 12544 -> 98 m-tiles x n-tiles on <= 148 CTAs), 1x1 tiled A, fused residual
+    a = _check(64, 56, 256, 1, 1, batch=4, residual=True, options=dict(opts, ws=1))
+    b = _check(64, 56, 256, 1, 1, batch=4, residual=True, options=dict(opts, ws=-1))
+    np.testing.assert_array_equal(a, b)
+    # im2col 3x3 with a ragged last tile and 18 K-blocks
+    a = _check(128, 14, 256, 3, 1, batch=3, options=dict(opts, ws=1))
+    b = _check(128, 14, 256, 3, 1, batch=3, options=dict(opts, ws=-1))
+    np.testing.assert_array_equal(a, b)
+    # forced small grid: every CTA walks several tiles, both TMEM accumulators and barrier phases wrap many times
+    _check(256, 28, 256, 1, 2, batch=4, relu=False, options=dict(opts, ws=7))
+
+
 @pytest.mark.parametrize("splits", [2, 3, 4, 8])  # 8: bn 64 keeps tiles*splits within the workspace bound
 def test_split_k_matches_oracle_and_is_deterministic(gpu, splits):
     # res5-like: M = 2*7*7 = 98 (one ragged tile), K = 4608 -> 72 k-blocks
