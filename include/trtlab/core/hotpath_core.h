@@ -32,6 +32,7 @@
 #include <iostream>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <queue>
 #include <sstream>
 #include <stdexcept>
@@ -252,6 +253,115 @@ class Pool : public std::enable_shared_from_this<Pool<T>> {
     std::queue<std::shared_ptr<T>> m_Items;
     std::mutex m_Mutex;
     std::condition_variable m_Cv;
+};
+
+// ---- CyclicAllocator<MemoryType>: a ring of equally sized segments, each a bump stack.  Allocate() hands out
+//      a shared handle; a segment is recycled only after the allocator has moved past it AND every handle cut
+//      from it is gone (behaviour pinned by trtlab/core/tests/test_cyclic_allocator.cc:57-125).  Allocate()
+//      blocks while every segment is still referenced -- natural back-pressure for a request pipeline.
+//      MemoryType needs: static void* Allocate(size_t), static void Free(void*), static size_t DefaultAlignment().
+struct Malloc {
+    static const char* TypeName() { return "Malloc"; }
+    static constexpr size_t DefaultAlignment() { return 64; }
+    static void* Allocate(size_t bytes) { return std::aligned_alloc(64, (bytes + 63) / 64 * 64); }
+    static void Free(void* p) { std::free(p); }
+};
+
+template <typename MemoryType>
+class CyclicAllocator {
+    struct Segment {
+        explicit Segment(size_t bytes) : base(static_cast<char*>(MemoryType::Allocate(bytes))) {
+            if (!base) throw std::bad_alloc();
+        }
+        ~Segment() { MemoryType::Free(base); }
+        char* base;
+        size_t used = 0;
+    };
+    struct State {  // outlives the allocator while handles are still out
+        std::mutex mutex;
+        std::condition_variable cv;
+        std::queue<std::unique_ptr<Segment>> idle;
+        size_t to_drop = 0;  // DropSegment() requests not yet honoured
+    };
+
+  public:
+    using Descriptor = std::shared_ptr<void>;
+
+    CyclicAllocator(size_t segments, size_t bytes_per_segment)
+        : m_State(std::make_shared<State>()), m_SegmentSize(Align(bytes_per_segment, Alignment())) {
+        if (segments == 0) throw std::invalid_argument("CyclicAllocator needs at least one segment");
+        for (size_t i = 0; i < segments; i++) AddSegment();
+    }
+    CyclicAllocator(const CyclicAllocator&) = delete;
+    CyclicAllocator& operator=(const CyclicAllocator&) = delete;
+
+    static constexpr size_t Alignment() { return MemoryType::DefaultAlignment(); }
+    size_t MaxAllocationSize() const { return m_SegmentSize; }
+
+    void AddSegment() {
+        auto seg = std::make_unique<Segment>(m_SegmentSize);
+        {
+            std::lock_guard<std::mutex> l(m_State->mutex);
+            m_State->idle.push(std::move(seg));
+        }
+        m_State->cv.notify_one();
+    }
+    // removes one idle segment now, or the next one that comes back
+    void DropSegment() {
+        std::lock_guard<std::mutex> l(m_State->mutex);
+        if (!m_State->idle.empty()) m_State->idle.pop();
+        else m_State->to_drop++;
+    }
+
+    // blocks until a segment with room is available; throws std::length_error if size can never fit
+    Descriptor Allocate(size_t size) {
+        const size_t need = Align(size ? size : 1, Alignment());
+        if (need > m_SegmentSize) throw std::length_error("allocation larger than a CyclicAllocator segment");
+        std::lock_guard<std::mutex> serial(m_AllocMutex);
+        if (m_Current && m_Current->used + need > m_SegmentSize) m_Current.reset();  // detach; recycles at refcount 0
+        if (!m_Current) m_Current = NextSegment();
+        char* p = m_Current->base + m_Current->used;
+        m_Current->used += need;
+        return Descriptor(m_Current, p);  // aliasing: shares the segment's lifetime, points at the slice
+    }
+
+    size_t AvailableSegments() {
+        std::lock_guard<std::mutex> serial(m_AllocMutex);
+        std::lock_guard<std::mutex> l(m_State->mutex);
+        return m_State->idle.size() + (m_Current ? 1 : 0);
+    }
+    size_t AvailableBytes() {
+        std::lock_guard<std::mutex> serial(m_AllocMutex);
+        std::lock_guard<std::mutex> l(m_State->mutex);
+        return m_State->idle.size() * m_SegmentSize + (m_Current ? m_SegmentSize - m_Current->used : 0);
+    }
+
+  private:
+    std::shared_ptr<Segment> NextSegment() {
+        std::unique_lock<std::mutex> l(m_State->mutex);
+        m_State->cv.wait(l, [this] { return !m_State->idle.empty(); });
+        std::unique_ptr<Segment> seg = std::move(m_State->idle.front());
+        m_State->idle.pop();
+        auto state = m_State;
+        return std::shared_ptr<Segment>(seg.release(), [state](Segment* s) {
+            std::unique_ptr<Segment> back(s);
+            back->used = 0;
+            {
+                std::lock_guard<std::mutex> g(state->mutex);
+                if (state->to_drop) {
+                    state->to_drop--;
+                    return;  // `back` frees the memory
+                }
+                state->idle.push(std::move(back));
+            }
+            state->cv.notify_one();
+        });
+    }
+
+    std::shared_ptr<State> m_State;
+    const size_t m_SegmentSize;
+    std::mutex m_AllocMutex;
+    std::shared_ptr<Segment> m_Current;
 };
 
 // ---- AsyncCompute: user completion function + promise of its result ----------------------------

@@ -242,6 +242,38 @@ class FixedBuffers : public Buffers {
     std::unique_ptr<MemoryStack<DeviceMemoryType>> m_DeviceStack;
 };
 
+// Buffers whose slices come from two rings of segments instead of two rewinding stacks (buffers.h:122-154):
+// Reset() does not rewind anything -- the slices cut for a request are released when the Buffers comes back to
+// the pool, and a segment is reused once everything cut from it has been released.
+template <typename HostMemoryType, typename DeviceMemoryType>
+class CyclicBuffers : public Buffers {
+  public:
+    using HostAllocatorType = std::unique_ptr<CyclicAllocator<HostMemoryType>>;
+    using DeviceAllocatorType = std::unique_ptr<CyclicAllocator<DeviceMemoryType>>;
+    using HostDescriptor = typename CyclicAllocator<HostMemoryType>::Descriptor;
+    using DeviceDescriptor = typename CyclicAllocator<DeviceMemoryType>::Descriptor;
+
+    CyclicBuffers(HostAllocatorType host, DeviceAllocatorType device)
+        : m_HostAllocator(std::move(host)), m_DeviceAllocator(std::move(device)) {}
+    ~CyclicBuffers() override {}
+
+  protected:
+    void* AllocateHost(size_t size) final override {
+        m_Held.push_back(m_HostAllocator->Allocate(size));
+        return m_Held.back().get();
+    }
+    void* AllocateDevice(size_t size) final override {
+        m_Held.push_back(m_DeviceAllocator->Allocate(size));
+        return m_Held.back().get();
+    }
+    void Reset() final override { m_Held.clear(); }
+
+  private:
+    HostAllocatorType m_HostAllocator;
+    DeviceAllocatorType m_DeviceAllocator;
+    std::vector<std::shared_ptr<void>> m_Held;  // descriptors of the request in flight
+};
+
 class Bindings {
   public:
     virtual ~Bindings();

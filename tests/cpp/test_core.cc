@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <thread>
 
 #include "trtlab/core/hotpath_core.h"
@@ -109,6 +110,63 @@ static void test_async_compute() {
     EXPECT(threw);
 }
 
+// CyclicAllocator: segment accounting and recycling (cases of trtlab/core/tests/test_cyclic_allocator.cc)
+static void test_cyclic_allocator() {
+    const size_t mb = 1024 * 1024;
+    CyclicAllocator<Malloc> ring(5, mb);
+    EXPECT(ring.AvailableSegments() == 5);
+    EXPECT(ring.AvailableBytes() == 5 * mb);
+    ring.AddSegment();
+    EXPECT(ring.AvailableSegments() == 6);
+    ring.DropSegment();
+    EXPECT(ring.AvailableSegments() == 5);
+    {
+        auto a = ring.Allocate(1);
+        EXPECT(reinterpret_cast<uintptr_t>(a.get()) % ring.Alignment() == 0);
+        EXPECT(ring.AvailableBytes() == 5 * mb - ring.Alignment());
+    }
+    // released, but the current segment is only recycled once the allocator has moved past it
+    EXPECT(ring.AvailableBytes() == 5 * mb - ring.Alignment());
+    {
+        auto big = ring.Allocate(mb);  // does not fit behind `a` -> segment 0 detached (and recycled: no handles)
+        EXPECT(ring.AvailableSegments() == 5);
+        EXPECT(ring.AvailableBytes() == 4 * mb);
+        auto next = ring.Allocate(mb / 2);  // segment 1 full -> detached but still referenced by `big`
+        EXPECT(ring.AvailableSegments() == 4);
+        EXPECT(ring.AvailableBytes() == 3 * mb + mb / 2);
+    }
+    EXPECT(ring.AvailableSegments() == 5);  // `big` released its segment
+    bool threw = false;
+    try {
+        ring.Allocate(mb + 1);
+    } catch (const std::length_error&) {
+        threw = true;
+    }
+    EXPECT(threw);
+
+    // back-pressure: with every segment referenced, Allocate() blocks until a handle is dropped
+    CyclicAllocator<Malloc> two(2, 4096);
+    auto h0 = two.Allocate(4096);
+    auto h1 = two.Allocate(4096);
+    std::atomic<bool> got{false};
+    std::thread t([&] {
+        auto h2 = two.Allocate(4096);
+        got = true;
+    });
+    std::this_thread::sleep_for(std::chrono::milliseconds(50));
+    EXPECT(!got.load());
+    h0.reset();
+    t.join();
+    EXPECT(got.load());
+    // handles may outlive the allocator
+    std::shared_ptr<void> survivor;
+    {
+        CyclicAllocator<Malloc> tmp(1, 4096);
+        survivor = tmp.Allocate(128);
+    }
+    std::memset(survivor.get(), 0xab, 128);
+}
+
 static void test_bytes() {
     EXPECT(BytesToString(512) == "512 B");
     EXPECT(BytesToString(1536) == "1.5 KiB");
@@ -131,6 +189,7 @@ int main() {
     test_thread_pool();
     test_async_compute();
     test_bytes();
+    test_cyclic_allocator();
     std::printf("ALL OK\n");
     return 0;
 }
