@@ -152,6 +152,8 @@ struct ConvConfig {
     double est_us;
     int sps = 1;  // 64-wide K sub-blocks per pipeline stage
     int ws = 0;   // > 0: persistent warp-specialised kernel with this many CTAs
+    int cn = 1;   // CTAs per cluster along N sharing the activation tile by TMA multicast (1 = no cluster)
+    int halo = 0; // 1: 3x3 halo kernel (input block resident in smem, taps = shifted views)
 };
 // A pipeline deeper than the K loop is pure shared-memory cost: admit depths up to the smallest instantiated one
 // that covers the loop (or the deepest available when none does).
@@ -166,6 +168,8 @@ static bool stage_depth_useful(int bn, int kb, int st, int kpc) {
     return st <= (cover ? cover : deepest);
 }
 
+
+constexpr int kHaloStagesTag = 2;  // reported pipeline depth of the halo kernel (its A ring)
 
 struct b2_runtime {
     b2_alloc_fn alloc = nullptr;
@@ -222,6 +226,8 @@ struct b2_context {
     int force_stages = 0;
     int force_splits = 0;
     int force_sps = 0;
+    int force_halo = 0; // 1: the 3x3 halo kernel wherever it applies, -1: never
+    int force_cn = 0;   // > 0: this cluster size wherever it divides the N-tile count, -1: never cluster
     int force_ws = 0;   // 1: only the persistent warp-specialised tactic where it applies, -1: never
     int pdl_trigger = 1;
     int no_pack = 0;    // reserved (packed plans cannot fall back to the tensor-map weight path)
@@ -392,6 +398,20 @@ int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t out
     return B2_OK;
 }
 
+// NHWC activation tensor as a 4-D tiled map {C, W, H, N} with a {64 ch, box_w, box_h, 1} box (3x3 halo kernel)
+int make_map_nhwc(CUtensorMap* map, const void* base, int C, int W, int H, int N, uint32_t box_w, uint32_t box_h) {
+    cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
+    cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(C) * 2 * W, cuuint64_t(C) * 2 * W * H};
+    cuuint32_t box[4] = {64, box_w, box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(B2_ECUDA, "cuTensorMapEncodeTiled(4-D) failed (%d) C=%d W=%d H=%d N=%d box=%u,%u", int(r), C, W, H, N, box_w, box_h);
+    return B2_OK;
+}
+
 // `pix_bytes` / `row_bytes` / `img_bytes`: global strides of the W, H, N modes.  The row-folded stem passes a pixel
 // stride SMALLER than the C extent (overlapping windows): each "pixel" of the map is then kw real pixels.
 int make_map_im2col(CUtensorMap* map, const void* base, int C, int W, int H, int N, uint64_t pix_bytes,
@@ -480,6 +500,20 @@ int conv_num_kblocks(const b2_context* c, const Op& op) {
     return (int(r.taps_phys) + 7) / 8;
 }
 
+// 3x3 / stride 1 / pad 1 on 64-channel blocks with packed weights and no fused residual: the halo kernel applies.
+// Returns the rows per tile R (0 = not applicable).
+int conv_halo_rows(const b2_context* c, const Op& op) {
+    const b2plan::OpRec& r = op.r;
+    const Tensor& ti = c->e->tensors[r.in];
+    const Tensor& to = c->e->tensors[r.out];
+    if (r.cin_phys % 64 || r.cout_phys % 64 || op.kh() != 3 || op.kw() != 3 || op.sh() != 1 || op.sw() != 1 || op.ph() != 1 ||
+        op.pw_lo() != 1 || op.pw_hi() != 1 || r.res >= 0 || !(r.relu & 2) || c->no_pack || ti.h != to.h || ti.w != to.w)
+        return 0;
+    const int wp = int(to.w) + 2;
+    if (wp > 128) return 0;
+    return std::min(128 / wp, int(to.h));
+}
+
 // Fill a ConvLaunch (kernel arguments + TMA tensor maps) for one conv op under a given configuration.
 int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& cfg, b2k::ConvLaunch* out) {
     b2_engine* e = c->e;
@@ -501,6 +535,8 @@ int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& c
     cl.sps = cfg.sps > 0 ? cfg.sps : 1;
     cl.grid_n = int(r.cout_phys) / cl.bn;
     cl.ws_ctas = cfg.ws;
+    cl.cn = (cfg.cn > 1 && cfg.ws == 0 && cl.kb == 64 && cl.grid_n % cfg.cn == 0) ? cfg.cn : 1;
+    cl.args.cn = cl.cn;
     cl.args.tiles_m = cl.grid_m;
     cl.args.tiles_n = cl.grid_n;
     b2k::ConvArgs& a = cl.args;
@@ -530,17 +566,31 @@ int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& c
     const bool tiled = r.k == 1 && op.kw() == 1 && r.stride == 1 && op.sw() == 1 && r.pad_ == 0 && op.pw_lo() == 0 &&
                        op.pw_hi() == 0 && kb64 && !c->force_im2col;
     a.a_mode = tiled ? b2k::A_TILED : b2k::A_IM2COL;
+    if (cfg.halo) {
+        const int R = conv_halo_rows(c, op);
+        if (!R || !b2k::conv_halo_config_exists(cl.bn) || b2k::conv_halo_smem(cl.bn, int(to.w), R) > 227 * 1024)
+            return fail(B2_EINVAL, "conv %s: the halo tactic does not apply", op.name.c_str());
+        cl.halo = 1;
+        cl.ws_ctas = 0, cl.cn = 1, a.cn = 1, a.splits = 1, cl.stages = kHaloStagesTag, cl.sps = 1;
+        a.halo_rows = R;
+        cl.grid_m = batch * ((int(to.h) + R - 1) / R);
+        int rc = make_map_nhwc(&cl.mapA, tptr(r.in), int(r.cin_phys), int(ti.w), int(ti.h), batch, uint32_t(ti.w) + 2, uint32_t(R) + 2);
+        if (rc) return rc;
+        rc = make_map_nhwc(&cl.mapOut, tptr(r.out), int(r.cout_phys), int(to.w), int(to.h), batch, uint32_t(to.w) + 2, uint32_t(R));
+        cl.mapB = cl.mapA, cl.mapRes = cl.mapOut;
+        return rc;
+    }
     const CUtensorMapSwizzle swz = kb64 ? CU_TENSOR_MAP_SWIZZLE_128B : (fold ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
     const uint64_t pix = uint64_t(r.cin_phys) * 2, rowb = uint64_t(ti.w) * pix, imgb = uint64_t(ti.h) * rowb;
     int rc;
     if (tiled)
-        rc = make_map_2d(&cl.mapA, tptr(r.in), r.cin_phys, uint64_t(M), 64, 128, swz);
+        rc = make_map_2d(&cl.mapA, tptr(r.in), r.cin_phys, uint64_t(M), 64, uint32_t(128 / cl.cn), swz);
     else if (fold)  // kw pixels x 8 channels = 32 contiguous K-elements per window; windows advance by ONE pixel
         rc = make_map_im2col(&cl.mapA, tptr(r.in), int(r.cin_phys) * op.kw(), int(ti.w) - op.kw() + 1, int(ti.h), batch, pix,
                              rowb, imgb, op.kh(), 1, op.sh(), 1, op.ph(), 0, 0, 32, 128, swz);
     else
         rc = make_map_im2col(&cl.mapA, tptr(r.in), int(r.cin_phys), int(ti.w), int(ti.h), batch, pix, rowb, imgb, op.kh(),
-                             op.kw(), op.sh(), op.sw(), op.ph(), op.pw_lo(), op.pw_hi(), uint32_t(cl.kb), 128, swz);
+                             op.kw(), op.sh(), op.sw(), op.ph(), op.pw_lo(), op.pw_hi(), uint32_t(cl.kb), uint32_t(128 / cl.cn), swz);
     if (rc) return rc;
     if (r.relu & 2)  // packed weights are not addressable as a [Cout][K] matrix; mapB stays a valid dummy
         cl.mapB = cl.mapA;
@@ -560,7 +610,8 @@ int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& c
 // Tactic selection, the role TensorRT's builder plays for the reference's engines: time every instantiated
 // (N tile, pipeline depth) on THIS device with the layer's real shapes and keep the fastest.  Runs once per
 // (engine, layer, batch); results are shared by all contexts of the engine.
-int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, ConvConfig* best_out) {
+// fixed_halo: -1 free choice, 0 never, 1 only the halo kernel (decided once at max batch: it changes the summation order)
+int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, int fixed_halo, ConvConfig* best_out) {
     b2_engine* e = c->e;
     const b2plan::OpRec& r = op.r;
     const Tensor& to = e->tensors[r.out];
@@ -619,8 +670,8 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, Conv
             }
             const int kpc = (nkb + sp - 1) / sp;
             if (ws) {
-                candidates.push_back(ConvConfig{bn, st, 1, 0.0, sps, std::min(tiles, 148)});
-                if (tiles > 74) candidates.push_back(ConvConfig{bn, st, 1, 0.0, sps, 74});  // half the SMs per stream
+                candidates.push_back(ConvConfig{bn, st, 1, 0.0, sps, std::min(tiles, 148), 1});
+                if (tiles > 74) candidates.push_back(ConvConfig{bn, st, 1, 0.0, sps, 74, 1});  // half the SMs per stream
                 continue;
             }
             if (sps == 2 && kpc < 4) continue;  // double-width stages only pay on long K loops
@@ -630,8 +681,27 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, Conv
                            (sp - 1) * kpc >= nkb ||
                            size_t(tiles) * sp * 128 * bn * 4 > kSplitWorkspaceBytes))
                 continue;  // split-K only where the plain grid leaves SMs idle
-            candidates.push_back(ConvConfig{bn, st, sp, 0.0, sps, 0});
+            const bool cn_forced_here = c->force_cn > 1 && kbsz == 64 && (int(r.cout_phys) / bn) % c->force_cn == 0;
+            if (!cn_forced_here) candidates.push_back(ConvConfig{bn, st, sp, 0.0, sps, 0, 1});
+            if (kbsz == 64 && c->force_cn >= 0)  // clusters along N that multicast the activation tile
+                for (int cn = 2; cn <= 4; cn *= 2)
+                    if ((int(r.cout_phys) / bn) % cn == 0 && (!c->force_cn || cn == c->force_cn))
+                        candidates.push_back(ConvConfig{bn, st, sp, 0.0, sps, 0, cn});
         }
+    }
+    if (fixed_halo != 0 && c->force_halo >= 0 && (fixed_splits <= 1)) {
+        const int R = conv_halo_rows(c, op);
+        std::vector<ConvConfig> halo_cands;
+        if (R)
+            for (int bn : bns)
+                if (int(r.cout_phys) % bn == 0 && b2k::conv_halo_config_exists(bn) &&
+                    b2k::conv_halo_smem(bn, int(to.w), R) <= 227 * 1024) {
+                    ConvConfig hc{bn, kHaloStagesTag, 1, 0.0, 1, 0, 1};
+                    hc.halo = 1;
+                    halo_cands.push_back(hc);
+                }
+        if (!halo_cands.empty() && (c->force_halo > 0 || fixed_halo > 0)) candidates.clear();
+        candidates.insert(candidates.end(), halo_cands.begin(), halo_cands.end());
     }
     for (const ConvConfig& cand : candidates) {
         {
@@ -692,7 +762,7 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, Conv
 }
 
 // ---- tactic cache file (B2_TUNE_CACHE=<path>): the analogue of a TensorRT timing cache.  One line per tuned conv:
-//      <engine name> <op index> <batch> <bn> <stages> <splits> <sps> <persistent CTAs or 0>
+//      <engine name> <op index> <batch> <bn> <stages> <splits> <sps> <persistent CTAs or 0> <cluster size> <halo 0/1>
 void tune_cache_load(b2_engine* e) {
     if (e->tune_cache_loaded) return;
     e->tune_cache_loaded = true;
@@ -701,9 +771,13 @@ void tune_cache_load(b2_engine* e) {
     FILE* f = fopen(path, "r");
     if (!f) return;
     char name[128];
-    int op, batch, bn, st, sp, sps, ws;
-    while (fscanf(f, "%127s %d %d %d %d %d %d %d", name, &op, &batch, &bn, &st, &sp, &sps, &ws) == 8)
-        if (e->name == name && op >= 0 && op < int(e->ops.size())) e->tuned[{op, batch}] = ConvConfig{bn, st, sp, 0.0, sps, ws};
+    int op, batch, bn, st, sp, sps, ws, cn, halo;
+    while (fscanf(f, "%127s %d %d %d %d %d %d %d %d %d", name, &op, &batch, &bn, &st, &sp, &sps, &ws, &cn, &halo) == 10)
+        if (e->name == name && op >= 0 && op < int(e->ops.size())) {
+            ConvConfig cfg{bn, st, sp, 0.0, sps, ws, cn};
+            cfg.halo = halo;
+            e->tuned[{op, batch}] = cfg;
+        }
     fclose(f);
 }
 void tune_cache_append(const b2_engine* e, int op, int batch, const ConvConfig& cfg) {
@@ -711,7 +785,8 @@ void tune_cache_append(const b2_engine* e, int op, int batch, const ConvConfig& 
     if (!path) return;
     FILE* f = fopen(path, "a");
     if (!f) return;
-    fprintf(f, "%s %d %d %d %d %d %d %d\n", e->name.c_str(), op, batch, cfg.bn, cfg.stages, cfg.splits, cfg.sps, cfg.ws);
+    fprintf(f, "%s %d %d %d %d %d %d %d %d %d\n", e->name.c_str(), op, batch, cfg.bn, cfg.stages, cfg.splits, cfg.sps, cfg.ws, cfg.cn,
+            cfg.halo);
     fclose(f);
 }
 
@@ -793,6 +868,10 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                         b2k::conv_ws_config_exists(cfg.bn, cfg.stages, cfg.sps) &&
                         b2k::conv_ws_smem(cfg.bn, cfg.stages, cfg.sps, r.res >= 0) <= 227 * 1024)
                         cfg.ws = std::min(((M + 127) / 128) * (int(r.cout_phys) / cfg.bn), c->force_ws > 1 ? c->force_ws : 148);
+                    if (c->force_halo > 0 && conv_halo_rows(c, op) && b2k::conv_halo_config_exists(cfg.bn) && cfg.splits == 1 &&
+                        b2k::conv_halo_smem(cfg.bn, int(to.w), conv_halo_rows(c, op)) <= 227 * 1024)
+                        cfg.halo = 1, cfg.ws = 0, cfg.cn = 1;
+                    if (c->force_cn > 1 && kbsz == 64 && cfg.ws == 0 && !cfg.halo && (int(r.cout_phys) / cfg.bn) % c->force_cn == 0) cfg.cn = c->force_cn;
                     const bool forced = c->force_bn || c->force_stages || c->force_splits || c->force_sps;
                     const int op_index = int(&op - &e->ops[0]);
                     if (!forced && c->autotune) {
@@ -813,7 +892,7 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                         if (!have) {
                             // The split-K factor fixes the fp32 summation order, so it is chosen ONCE, at max batch,
                             // and reused for every batch size: an image's result does not depend on its batch.
-                            int splits = 0;
+                            int splits = 0, halo = -1;
                             if (batch != e->max_batch) {
                                 ConvConfig top = cfg;
                                 bool have_top = false;
@@ -823,15 +902,16 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                                     if (it != e->tuned.end()) top = it->second, have_top = true;
                                 }
                                 if (!have_top) {
-                                    int rc = autotune_conv(c, op, e->max_batch, 0, &top);
+                                    int rc = autotune_conv(c, op, e->max_batch, 0, -1, &top);
                                     if (rc) return rc;
                                     std::lock_guard<std::mutex> lock(e->tune_mutex);
                                     e->tuned[{op_index, e->max_batch}] = top;
                                     tune_cache_append(e, op_index, e->max_batch, top);
                                 }
                                 splits = top.splits;
+                                halo = top.halo;
                             }
-                            int rc = autotune_conv(c, op, batch, splits, &cfg);
+                            int rc = autotune_conv(c, op, batch, splits, halo, &cfg);
                             if (rc) return rc;
                             std::lock_guard<std::mutex> lock(e->tune_mutex);
                             e->tuned[{op_index, batch}] = cfg;
@@ -1083,6 +1163,8 @@ int b2_context_create(b2_engine* e, b2_context** out) {
     c->force_splits = env_int("B2_FORCE_SPLITS", 0);
     c->force_sps = env_int("B2_FORCE_SPS", 0);
     c->force_ws = env_int("B2_FORCE_WS", 0);
+    c->force_cn = env_int("B2_FORCE_CN", 0);
+    c->force_halo = env_int("B2_FORCE_HALO", 0);
     c->pdl_trigger = env_int("B2_PDL_TRIGGER", 1);
     c->autotune = env_int("B2_AUTOTUNE", 4);
     if (getenv("B2_PDL")) b2k::set_pdl(env_int("B2_PDL", 1) != 0);
@@ -1137,6 +1219,8 @@ int b2_context_set_option(b2_context* c, const char* key, int value) {
     else if (k == "splits") c->force_splits = value;
     else if (k == "sps") c->force_sps = value;
     else if (k == "ws") c->force_ws = value;
+    else if (k == "cn") c->force_cn = value;
+    else if (k == "halo") c->force_halo = value;
     else if (k == "pdl_trigger") c->pdl_trigger = value;
     else if (k == "autotune") c->autotune = value;
     else if (k == "no_fold") c->no_fold = value;
@@ -1263,6 +1347,7 @@ const char* b2_context_launch_name(b2_context* c, int batch, int i) {
         s += " bn=" + std::to_string(L->conv.bn) + " kb=" + std::to_string(L->conv.kb) +
              " st=" + std::to_string(L->conv.stages) + "x" + std::to_string(L->conv.sps) +
              (L->conv.ws_ctas ? " ws=" + std::to_string(L->conv.ws_ctas) : std::string()) +
+             (L->conv.cn > 1 ? " cn=" + std::to_string(L->conv.cn) : std::string()) + (L->conv.halo ? " halo" : "") +
              (L->conv.args.a_mode == b2k::A_TILED ? " tiled" : " im2col") +
              " grid=" + std::to_string(L->conv.grid_n) + "x" + std::to_string(L->conv.grid_m) + "x" +
              std::to_string(L->conv.args.splits) + " kblk=" + std::to_string(L->conv.args.num_kblocks);

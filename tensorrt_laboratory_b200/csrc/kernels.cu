@@ -104,6 +104,33 @@ __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* map, uint6
         : "memory");
 }
 
+// ---- thread-block clusters: one L2 read of an activation slice lands in the smem of every CTA of the cluster ----
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c, int w, int h,
+                                                       int n, uint16_t off_w, uint16_t off_h, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h),
+        "r"(n), "h"(off_w), "h"(off_h), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
                  "r"(ncols)
@@ -131,6 +158,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 // mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// the same arrival delivered to the barrier at this smem offset in every CTA of `mask` (cluster ranks)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
                  : "memory");
 }
 
@@ -289,6 +324,13 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         return rem < SPS ? rem : SPS;
     };
     const bool split = p.splits > 1;
+    // Cluster of `cn` CTAs along N (same 128 output pixels, different output-channel tiles): every CTA fetches 1/cn of
+    // each activation sub-block and multicasts it to all of them, so L2 serves the tile once per cluster instead of once
+    // per CTA.  A stage may be refilled only when EVERY CTA has consumed it -> the MMA warps multicast their stage
+    // release and the empty barriers count cn arrivals.
+    const int cn = (KB == 64) ? p.cn : 1;
+    const uint32_t crank = cn > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = static_cast<uint16_t>((1u << cn) - 1u);
 
     // ---------------- prologue: nothing here depends on the previous kernel's output ----------------
     if (threadIdx.x == 0) {
@@ -298,7 +340,7 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (has_res) tma_prefetch_desc(&mapRes);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], static_cast<uint32_t>(cn));
         }
         mbar_init(accum_bar, 1);
         mbar_init(res_bar, 1);
@@ -308,6 +350,7 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (cn > 1) cluster_sync_all();  // peers' barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (warp == 3) {  // bias -> smem while the pipeline spins up; published by the pre-epilogue barrier
@@ -359,9 +402,13 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         {
             // ================= TMA producer (whole warp converged, one elected lane issues) =================
             int img0 = 0, p0 = 0, q0 = 0;
+            const int slice_rows = 128 / cn;                 // rows of the A tile this CTA fetches (all of them: cn == 1)
+            int ms = m0 + static_cast<int>(crank) * slice_rows;  // first output pixel of the slice
+            const uint32_t slice_off = crank * static_cast<uint32_t>(slice_rows) * 128u;  // 128-byte swizzled rows
             if (p.a_mode == A_IM2COL) {
-                img0 = m0 / p.HoWo;
-                const int rem = m0 - img0 * p.HoWo;
+                if (ms >= p.M) ms = 0;  // slice entirely past the last pixel: its rows are never stored, fetch valid ones
+                img0 = ms / p.HoWo;
+                const int rem = ms - img0 * p.HoWo;
                 p0 = rem / p.Wo;
                 q0 = rem - p0 * p.Wo;
             }
@@ -382,7 +429,14 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 if (KB == 64) {
                     const int ns = subs_in_step((kb - kb_begin) / SPS);
                     for (int u = 0; u < ns; ++u) {
-                        if (p.a_mode == A_TILED) {
+                        if (cn > 1) {
+                            if (p.a_mode == A_TILED) {
+                                tma_load_2d_mc(&mapA, &full_bar[s], a_dst + u * Cfg::A_SUBBLK + slice_off, cur_cb * 64, ms, cmask);
+                            } else {
+                                tma_load_im2col_4d_mc(&mapA, &full_bar[s], a_dst + u * Cfg::A_SUBBLK + slice_off, cur_cb * 64, base_w,
+                                                      base_h, img0, static_cast<uint16_t>(cur_sx), static_cast<uint16_t>(cur_r), cmask);
+                            }
+                        } else if (p.a_mode == A_TILED) {
                             tma_load_2d(&mapA, &full_bar[s], a_dst + u * Cfg::A_SUBBLK, cur_cb * 64, m0);
                         } else {
                             tma_load_im2col_4d(&mapA, &full_bar[s], a_dst + u * Cfg::A_SUBBLK, cur_cb * 64, base_w, base_h, img0,
@@ -497,7 +551,8 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         umma_f16(tmem_base, ad, bd, IDESC, (i > 0 || j > 0) ? 1u : 0u);
                     }
                 }
-                umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+                if (cn > 1) umma_commit_mc(&empty_bar[s], cmask);  // every producer of the cluster hears it
+                else umma_commit(&empty_bar[s]);                   // frees the smem stage when these MMAs retire
                 }
                 __syncwarp();
                 if (dbg) mi += clock64() - m1c;
@@ -648,6 +703,16 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
         for (int b = 0; b < NBOX; ++b) tma_store_2d(&mapOut, sOut + b * (128 * OROWB), n0 + b * OW, m0);
         tma_store_commit_and_wait_read();  // smem must stay alive until the TMA has read it
+    }
+    if (cn > 1) {
+        // peers arrive on THIS CTA's empty barriers when their MMAs retire: hear the last release of every stage before
+        // the shared memory can go to another CTA, then leave together
+        if (warp == 1) {
+            const int first = nk > STAGES ? nk - STAGES : 0;
+            for (int i = first; i < nk; ++i) mbar_wait(&empty_bar[i % STAGES], (i / STAGES) & 1);
+        }
+        __syncthreads();
+        cluster_sync_all();
     }
     if (dbg && threadIdx.x == 64) {
         dbg[7] = clock64();
@@ -933,31 +998,254 @@ conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// =================================================================================================
+// conv3x3_halo_tcgen05 -- 3x3 / stride 1 / pad 1 convolution that brings every input pixel into shared memory ONCE per
+//   (tile, 64-channel block) instead of once per filter tap.
+//
+//   The tile is R whole output rows of one image in PADDED coordinates: accumulator row m' = hh*(W+2) + ww.  One 4-D
+//   TMA box {64 ch, W+2, R+2, 1} starting at (w = -1, h = h0-1) lands the halo block in smem as (R+2)*(W+2) pixel rows
+//   of 128 B (SWIZZLE_128B); out-of-image pixels are zero-filled by the TMA, which IS the convolution's padding.  The A
+//   operand of tap (r, s) is the same block read from pixel row r*(W+2)+s on: a start-address offset in the UMMA
+//   descriptor (the 128B swizzle is a function of the absolute smem address, so a row shift keeps it consistent).
+//   Columns ww = W, W+1 of every row compute garbage that the output TMA store (box {BN, W+2, R, 1} at w = 0) clips.
+//   A traffic per tile and channel block: (R+2)(W+2) pixel rows instead of 9 x 128.
+//
+//   warp 0 = halo producer, warp 1 = MMA issuer, warp 2 = TMEM owner, warp 3 = weight producer, all 4 = epilogue.
+//   K order: channel block outer, tap inner (the im2col kernel runs tap outer) -- same products, different fp32
+//   summation order.
+// =================================================================================================
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+constexpr int kHaloAStages = 2;
+__host__ __device__ constexpr int halo_b_stages(int bn) { return bn >= 256 ? 3 : 4; }
+// bytes of one A stage: the loaded halo block, but never less than what the farthest tap's 128-row window touches
+__host__ __device__ constexpr int halo_a_stage_bytes(int w, int r) {
+    const int loaded = (r + 2) * (w + 2);
+    const int touched = 128 + 2 * (w + 2) + 2;
+    const int rows = loaded > touched ? loaded : touched;
+    return (rows * 128 + 1023) / 1024 * 1024;
+}
+__host__ __device__ constexpr int halo_smem_bytes(int bn, int w, int r) {
+    return kHaloAStages * halo_a_stage_bytes(w, r) + halo_b_stages(bn) * bn * 128 + 256 + bn * 4 + 1024;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(128)
+conv3x3_halo_tcgen05(const __grid_constant__ CUtensorMap mapIn, const __grid_constant__ CUtensorMap mapOut, const ConvArgs p) {
+    constexpr int NB = halo_b_stages(BN);
+    constexpr int B_BLK = BN * 128;  // one tap of one 64-channel block: BN rows of 128 B (pre-swizzled)
+    constexpr int NG = BN / 32;
+    constexpr int OW = 64;
+    constexpr int NBOX = BN / OW;
+    constexpr uint32_t IDESC = make_idesc_f16(128, BN);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int W = p.Wo, Wp = p.Wo + 2, R = p.halo_rows;
+    const int a_stage = halo_a_stage_bytes(W, R);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + kHaloAStages * a_stage;
+    uint8_t* sOut = smem;  // staging reuses the drained rings
+    uint8_t* tail = sB + NB * B_BLK;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* a_empty = a_full + kHaloAStages;
+    uint64_t* b_full = a_empty + kHaloAStages;
+    uint64_t* b_empty = b_full + NB;
+    uint64_t* accum_bar = b_empty + NB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    float* s_bias = reinterpret_cast<float*>(tail + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int Ho = p.HoWo / p.Wo;
+    const int tiles_per_img = (Ho + R - 1) / R;
+    const int img = blockIdx.y / tiles_per_img;
+    const int h0 = (blockIdx.y - img * tiles_per_img) * R;
+    const int cblocks = p.cblocks;
+    const int nsteps = cblocks * 9;  // weight blocks, in (cb, tap) order
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapIn);
+        tma_prefetch_desc(&mapOut);
+        for (int s = 0; s < kHaloAStages; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < NB; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (p.pdl_trigger == 0) pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ================= halo producer =================
+        const uint32_t halo_bytes = static_cast<uint32_t>((R + 2) * Wp * 128);
+        pdl_wait();
+        for (int cb = 0; cb < cblocks; ++cb) {
+            const int s = cb % kHaloAStages;
+            if (cb >= kHaloAStages) mbar_wait(&a_empty[s], ((cb / kHaloAStages) & 1) ^ 1);
+            if (elect_one_sync()) {
+                mbar_expect_tx(&a_full[s], halo_bytes);
+                tma_load_4d(&mapIn, &a_full[s], sA + s * a_stage, cb * 64, -1, h0 - 1, img);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        for (int cb = 0; cb < cblocks; ++cb) {
+            const int sa = cb % kHaloAStages;
+            mbar_wait(&a_full[sa], (cb / kHaloAStages) & 1);
+            const uint32_t a_base = smem_u32(sA + sa * a_stage);
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+                const int i = cb * 9 + tap;
+                const int sb = i % NB;
+                mbar_wait(&b_full[sb], (i / NB) & 1);
+                tc_fence_after();
+                const int r = tap / 3, sx = tap - r * 3;
+                const uint32_t a_addr = a_base + static_cast<uint32_t>((r * Wp + sx) * 128);
+                const uint32_t b_addr = smem_u32(sB + sb * B_BLK);
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        // descriptor "base offset" stays 0: the swizzle pattern is anchored at the 1024-aligned stage base
+                        // (measured: setting it to (addr >> 7) & 7 for the shifted start gives wrong results)
+                        const uint64_t ad = make_smem_desc(a_addr + j * 32, 16, 1024, 2);
+                        const uint64_t bd = make_smem_desc(b_addr + j * 32, 16, 1024, 2);
+                        umma_f16(tmem_base, ad, bd, IDESC, (i > 0 || j > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&b_empty[sb]);
+                    if (tap == 8) umma_commit(&a_empty[sa]);
+                }
+                __syncwarp();
+            }
+        }
+        if (elect_one_sync()) umma_commit(accum_bar);
+        __syncwarp();
+    } else if (warp == 3) {
+        // ================= weight producer (constants: no dependency wait) =================
+        for (int i = lane; i < BN; i += 32) s_bias[i] = __ldg(p.bias + n0 + i);
+        for (int i = 0; i < nsteps; ++i) {
+            const int sb = i % NB;
+            if (i >= NB) mbar_wait(&b_empty[sb], ((i / NB) & 1) ^ 1);
+            const int cb = i / 9, tap = i - cb * 9;
+            const int kb = tap * cblocks + cb;  // the packed weights are laid out tap-major
+            if (elect_one_sync()) {
+                mbar_expect_tx(&b_full[sb], B_BLK);
+                bulk_load_1d(&b_full[sb], sB + sb * B_BLK, p.wpacked + (static_cast<size_t>(kb) * (p.Cout >> 5) + (n0 >> 5)) * 4096,
+                             B_BLK);
+            }
+            __syncwarp();
+        }
+    }
+
+    // ====== epilogue: TMEM -> registers -> bias/ReLU -> fp16 -> swizzled smem tile -> 4-D TMA store ======
+    pdl_wait();
+    const int row = warp * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    __syncthreads();
+    if (p.pdl_trigger == 1) pdl_launch_dependents();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + g * 32, acc);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int col = g * 32 + q * 8;
+            const int box = col / OW;
+            const int chunk = (col % OW) / 8;
+            const uint32_t so = static_cast<uint32_t>(box * (128 * 128)) + swz_off<128>(row, chunk);
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i] = __uint_as_float(acc[q * 8 + i]) + s_bias[col + i];
+                if (p.relu) v[i] = fmaxf(v[i], 0.0f);
+            }
+            uint4 o;
+            __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            *reinterpret_cast<uint4*>(sOut + so) = o;
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, BN);
+    if (threadIdx.x == 0) {
+        // box {64 ch, W+2, R, 1} at w = 0: the two garbage columns of every row and rows past H are clipped
+#pragma unroll
+        for (int b = 0; b < NBOX; ++b) tma_store_4d(&mapOut, sOut + b * (128 * 128), n0 + b * OW, 0, h0, img);
+        tma_store_commit_and_wait_read();
+    }
+}
+
 static bool g_use_pdl = true;
 void set_pdl(bool on) { g_use_pdl = on; }
 bool get_pdl() { return g_use_pdl; }
 
 template <typename Kern, typename... Args>
-static int launch_kernel(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+static int launch_kernel_cluster(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, unsigned cluster_x,
+                                 Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    if (pdl && g_use_pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = (pdl && g_use_pdl) ? 1 : 0;
+    cfg.numAttrs = n;
     return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, args...));
+}
+template <typename Kern, typename... Args>
+static int launch_kernel(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+    return launch_kernel_cluster(kern, grid, block, smem, stream, pdl, 1u, args...);
 }
 
 template <int BN, int KB, int STAGES, int SPS>
 static int launch_one(const ConvLaunch& L, cudaStream_t stream) {
     dim3 grid(L.grid_n, L.grid_m, L.args.splits);
     const size_t smem = size_t(conv_smem_layout_bytes(BN, STAGES, L.args.residual != nullptr, SPS));
-    return launch_kernel(conv_f16_tcgen05<BN, KB, STAGES, SPS>, grid, dim3(128), smem, stream, true, L.mapA, L.mapB, L.mapOut,
-                         L.mapRes, L.args);
+    if (L.cn > 1 && (KB != 64 || L.grid_n % L.cn != 0 || L.args.cn != L.cn)) return static_cast<int>(cudaErrorInvalidValue);
+    return launch_kernel_cluster(conv_f16_tcgen05<BN, KB, STAGES, SPS>, grid, dim3(128), smem, stream, true,
+                                 static_cast<unsigned>(L.cn > 1 ? L.cn : 1), L.mapA, L.mapB, L.mapOut, L.mapRes, L.args);
 }
 
 template <int BN, int KB, int STAGES, int SPS>
@@ -978,12 +1266,35 @@ int conv_smem_bytes(int bn, int stages, bool residual, int sps) { return conv_sm
     X(32, 8, 2, 1) X(32, 8, 4, 1) X(64, 8, 2, 1) X(64, 8, 4, 1) X(64, 8, 8, 1) X(128, 8, 4, 1) \
     X(32, 32, 2, 1) X(32, 32, 4, 1) X(64, 32, 1, 1) X(64, 32, 2, 1) X(64, 32, 4, 1) X(128, 32, 2, 1) X(128, 32, 4, 1)
 
+int conv_halo_smem(int bn, int w, int r) { return halo_smem_bytes(bn, w, r); }
+bool conv_halo_config_exists(int bn) { return bn == 64 || bn == 128 || bn == 256; }
+static int init_conv_halo_kernels() {
+    int e;
+    if ((e = static_cast<int>(cudaFuncSetAttribute(conv3x3_halo_tcgen05<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))) return e;
+    if ((e = static_cast<int>(cudaFuncSetAttribute(conv3x3_halo_tcgen05<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))) return e;
+    if ((e = static_cast<int>(cudaFuncSetAttribute(conv3x3_halo_tcgen05<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)))) return e;
+    return 0;
+}
+static int launch_conv_halo(const ConvLaunch& L, cudaStream_t stream) {
+    const int R = L.args.halo_rows;
+    const size_t smem = size_t(halo_smem_bytes(L.bn, L.args.Wo, R));
+    if (smem > 227 * 1024 || R < 1 || R * (L.args.Wo + 2) > 128) return static_cast<int>(cudaErrorInvalidValue);
+    dim3 grid(L.grid_n, L.grid_m, 1);
+    switch (L.bn) {
+        case 64: return launch_kernel(conv3x3_halo_tcgen05<64>, grid, dim3(128), smem, stream, true, L.mapA, L.mapOut, L.args);
+        case 128: return launch_kernel(conv3x3_halo_tcgen05<128>, grid, dim3(128), smem, stream, true, L.mapA, L.mapOut, L.args);
+        case 256: return launch_kernel(conv3x3_halo_tcgen05<256>, grid, dim3(128), smem, stream, true, L.mapA, L.mapOut, L.args);
+    }
+    return static_cast<int>(cudaErrorInvalidValue);
+}
+
 int init_conv_ws_kernels();
 int launch_conv_f16_tcgen05_ws(const ConvLaunch& L, cudaStream_t stream);
 
 int init_conv_kernels() {
     int e = init_conv_ws_kernels();
     if (e) return e;
+    if ((e = init_conv_halo_kernels())) return e;
 #define B2_INIT(BN_, KB_, ST_, SPS_) \
     if ((e = init_one<BN_, KB_, ST_, SPS_>())) return e;
     B2_FOR_EACH_CONV(B2_INIT)
@@ -992,6 +1303,7 @@ int init_conv_kernels() {
 }
 
 int launch_conv_f16_tcgen05(const ConvLaunch& L, cudaStream_t stream) {
+    if (L.halo) return launch_conv_halo(L, stream);
     if (L.ws_ctas > 0) return launch_conv_f16_tcgen05_ws(L, stream);
 #define B2_CASE(BN_, KB_, ST_, SPS_) \
     if (L.bn == BN_ && L.kb == KB_ && L.stages == ST_ && L.sps == SPS_) return launch_one<BN_, KB_, ST_, SPS_>(L, stream);

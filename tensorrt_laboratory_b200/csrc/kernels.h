@@ -38,6 +38,8 @@ struct ConvArgs {
     int pdl_trigger;         // 0: release the dependent kernel right after the prologue, 1: after the main loop
     const uint8_t* wpacked;  // KB==64: weights as pre-swizzled 4 KiB blocks [num_kblocks][Cout/32][32][128 B]; the BN-wide
                              // tile of one k-block is one contiguous cp.async.bulk (nullptr: fetch through mapB)
+    int halo_rows;           // halo variant: output rows R per tile (tile = R rows x (Wo+2) padded columns of one image)
+    int cn;                  // CTAs per cluster along N sharing one activation tile by TMA multicast (1 = no cluster)
     int tiles_m, tiles_n;    // persistent variant: output tile grid (128-row x BN-column tiles)
     int dbg_mode;            // bottleneck isolation (debug only): bit0 skip MMA issue, bit1 skip A loads, bit2 skip B loads
     long long* dbg;          // optional per-CTA phase timestamps (16 x int64 per CTA), nullptr in production
@@ -55,6 +57,8 @@ struct ConvLaunch {
     int stages;        // smem pipeline depth: 1 / 2 / 4 / 8
     int sps;           // 64-wide K sub-blocks per pipeline stage: 1 or 2 (KB == 64 only)
     int grid_m, grid_n;
+    int cn;            // cluster size along N (1, 2 or 4; KB == 64 only): mapA's box is then 128/cn rows
+    int halo;          // 1: conv3x3_halo_tcgen05 (3x3 s1 p1; mapA / mapOut are 4-D tiled {C, W, H, N} maps; grid_m = N * ceil(H/R))
     int ws_ctas;       // > 0: persistent warp-specialised variant with this many CTAs (0: one tile per CTA)
 };
 
@@ -64,6 +68,8 @@ int launch_conv_f16_tcgen05(const ConvLaunch& L, cudaStream_t stream);
 int init_conv_kernels();
 bool conv_config_exists(int bn, int kb, int stages, int sps = 1);  // is this configuration instantiated?
 int conv_smem_bytes(int bn, int stages, bool residual, int sps = 1);  // dynamic shared memory of one CTA
+bool conv_halo_config_exists(int bn);                                // 3x3 halo variant
+int conv_halo_smem(int bn, int w, int r);
 bool conv_ws_config_exists(int bn, int stages, int sps);             // persistent warp-specialised variant
 int conv_ws_smem(int bn, int stages, int sps, bool residual);
 // programmatic dependent launch on/off for every kernel of this library (default on)

@@ -31,12 +31,17 @@ def conv_case(cin, h, w, cout, k, stride, pad, relu=True, residual=False, seed=0
     return net, wts, graph.lower(net, wts)
 
 
+LAST_LAUNCH_NAMES = []  # launch names (kernel + tactic) of the most recent run_engine call
+
+
 def run_engine(lowered, x, precision, options=None, outputs=None, max_batch=None):
     blob = builder.build_plan(lowered, precision, max_batch or x.shape[0], outputs=outputs)
     eng = capi.Engine(blob)
     sess = capi.Session(eng, options)
     try:
         out = sess.infer(x)
+        n = sess.nb_launches(x.shape[0])
+        LAST_LAUNCH_NAMES[:] = [capi.load().b2_context_launch_name(sess.ctx, x.shape[0], i).decode() for i in range(n)]
     finally:
         sess.close()
         eng.destroy()

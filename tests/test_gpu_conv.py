@@ -93,6 +93,39 @@ def test_persistent_warp_specialised_tactic(gpu, bn, stages, sps):
     _check(256, 28, 256, 1, 2, batch=4, relu=False, options=dict(opts, ws=7))
 
 
+@pytest.mark.parametrize("cin,h,cout,bn", [(64, 56, 64, 64), (128, 28, 128, 128), (256, 14, 256, 64), (256, 14, 256, 256),
+                                            (512, 7, 512, 128), (64, 20, 128, 64), (64, 126, 64, 64)])
+def test_halo_3x3_tactic(gpu, cin, h, cout, bn):
+    """conv3x3_halo_tcgen05: the input block of a tile is loaded once and the nine taps are shifted views of it.  Covers
+    every ResNet 3x3 geometry (R = 2, 4, 8, 7 rows per tile), ragged last row-tiles (14 = 8 + 6, 20 = 5*4), the widest
+    row the tile holds (W + 2 = 128) and every N tile."""
+    batch = 1 if h > 100 else 3
+    _check(cin, h, cout, 3, 1, batch=batch, options={"bn": bn, "halo": 1})
+    assert any(" halo" in n for n in helpers.LAST_LAUNCH_NAMES), helpers.LAST_LAUNCH_NAMES
+    _check(cin, h, cout, 3, 1, batch=batch, relu=False, options={"bn": bn, "halo": 1}, seed=3)
+
+
+@pytest.mark.parametrize("cn,bn,stages,sps", [(2, 64, 2, 1), (4, 64, 4, 2), (2, 128, 2, 1), (4, 32, 4, 1), (2, 64, 1, 1)])
+def test_cluster_multicast_tactic(gpu, cn, bn, stages, sps):
+    """Clusters of `cn` CTAs along N: every CTA fetches 1/cn of each activation sub-block and multicasts it; stage
+    release is multicast back.  The MMAs are the same as without clusters -> bit-identical results."""
+    opts = {"bn": bn, "stages": stages, "sps": sps}
+    # 1x1 tiled A, fused residual, ragged last m-tile (M = 3*28*28 = 2352 = 18.4 tiles)
+    a = _check(128, 28, 512, 1, 1, batch=3, residual=True, options=dict(opts, cn=cn))
+    assert any(f" cn={cn}" in n for n in helpers.LAST_LAUNCH_NAMES), helpers.LAST_LAUNCH_NAMES
+    b = _check(128, 28, 512, 1, 1, batch=3, residual=True, options=dict(opts, cn=-1))
+    assert not any(" cn=" in n for n in helpers.LAST_LAUNCH_NAMES)
+    np.testing.assert_array_equal(a, b)
+    # im2col 3x3, 18 K-blocks (barrier phases wrap), last tile has slices that start past the final pixel
+    a = _check(128, 14, 256, 3, 1, batch=2, options=dict(opts, cn=cn))
+    b = _check(128, 14, 256, 3, 1, batch=2, options=dict(opts, cn=-1))
+    np.testing.assert_array_equal(a, b)
+    # strided 1x1 through im2col mode + split-K inside a cluster
+    _check(256, 14, 512, 1, 2, batch=2, relu=False, options=dict(opts, cn=cn))
+    if bn == 64 and sps == 1 and stages == 2:
+        _check(512, 7, 512, 3, 1, batch=2, options=dict(opts, cn=cn, splits=2))
+
+
 @pytest.mark.parametrize("splits", [2, 3, 4, 8])  # 8: bn 64 keeps tiles*splits within the workspace bound
 def test_split_k_matches_oracle_and_is_deterministic(gpu, splits):
     # res5-like: M = 2*7*7 = 98 (one ragged tile), K = 4608 -> 72 k-blocks

@@ -2,7 +2,8 @@
 """Throughput of ResNet-50 fp16 b=8 (inputs resident) as a function of (a) the number of streams the on-device
 tactic autotuner loads the GPU with and (b) the number of concurrent ExecutionContexts.  Each autotune setting is
 tuned once into its own tactic-cache file (B2_TUNE_CACHE), then replayed with every context count.
-usage: python tools/gpu_ctx_sweep.py [autotune values, default 4,8,16] [context counts, default 1,2,4,8,16]"""
+usage: python tools/gpu_ctx_sweep.py [autotune values, default 4,8,16] [context counts, default 1,2,4,8,16] [ENV=V,ENV=V ...]
+Every further argument is a set of extra environment settings (e.g. B2_FORCE_CN=2) swept as its own variant."""
 import collections
 import json
 import os
@@ -21,13 +22,20 @@ def main():
     low = graph.lower(net, weights.random_weights(net, 0))
     blob = builder.build_plan(low, builder.PREC_FP16, 8)
     ring = weights.synthetic_input(8, ring=8)
-    for t in tunes:
-        cache = os.path.join(out_dir, f"tactics_autotune{t}.txt")
+    variants = [dict(kv.split("=") for kv in a.split(",")) for a in sys.argv[3:]] or [{}]
+    for var in variants:
+      for t in tunes:
+        for k in list(os.environ):
+            if k.startswith("B2_FORCE_"):
+                del os.environ[k]
+        os.environ.update(var)
+        tag = "".join(f"_{k[3:].lower()}{v}" for k, v in var.items())
+        cache = os.path.join(out_dir, f"tactics_autotune{t}{tag}.txt")
         if os.path.exists(cache):
             os.remove(cache)
         os.environ["B2_TUNE_CACHE"] = cache
         os.environ["B2_AUTOTUNE"] = str(t)
-        rec = {"autotune_streams": t}
+        rec = {"autotune_streams": t, "env": var}
         for n in ctxs:
             steps = 100 * max(n, 2)
             ms, _ = capi.device_throughput(blob, n, 8, steps, 20, ring)
@@ -36,6 +44,7 @@ def main():
         rec["bn"] = dict(collections.Counter(f[3] for f in fields))
         rec["stages"] = dict(collections.Counter(f[4] + "x" + f[6] for f in fields))
         rec["splits"] = dict(collections.Counter(f[5] for f in fields))
+        rec["cn"] = dict(collections.Counter(f[8] for f in fields))
         print(json.dumps(rec), flush=True)
 
 
