@@ -11,6 +11,7 @@
 //   reference: trtlab/tensorrt/src/{runtime,model,execution_context,workspace}.cc
 #pragma once
 
+#include <atomic>
 #include <chrono>
 #include <functional>
 #include <future>
@@ -322,7 +323,20 @@ class Bindings {
 // ------------------------------------------------------------------------------------------------
 class ExecutionContext {
   public:
-    explicit ExecutionContext(size_t workspace_bytes);
+    // One activation arena and the completion event of the forward pass that used it last.  Several tokens may share
+    // a lane: their forward passes are ordered ON THE DEVICE (cudaStreamWaitEvent), so the host can enqueue request
+    // n+1 of a lane while request n still runs and the lane never waits for a host round trip between requests.
+    struct Lane {
+        explicit Lane(size_t workspace_bytes);
+        ~Lane();
+        void* workspace;
+        size_t bytes;
+        std::mutex mutex;
+        cudaEvent_t last_done;  // nullptr until the lane has been used
+    };
+
+    explicit ExecutionContext(size_t workspace_bytes);        // a lane of its own (the reference's token)
+    explicit ExecutionContext(std::shared_ptr<Lane> lane);    // one of several tokens queued on `lane`
     virtual ~ExecutionContext();
     DELETE_COPYABILITY(ExecutionContext);
 
@@ -337,8 +351,7 @@ class ExecutionContext {
 
   private:
     std::shared_ptr<IExecutionContext> m_Context;
-    void* m_Workspace;
-    size_t m_WorkspaceBytes;
+    std::shared_ptr<Lane> m_Lane;
     cudaEvent_t m_Start, m_Done;
 };
 
@@ -372,6 +385,10 @@ class InferenceManager : public ::trtlab::Resources {
     void ForEachModel(std::function<void(const Model&)>);
 
     int MaxExecConcurrency() const;
+    static int EnqueueDepth();
+    // device time of finished forward passes (fed by InferRunner's post stage)
+    void RecordComputeTime(double seconds);
+    double MeanComputeTime(bool reset);  // tokens queued per execution lane (TRTLAB_ENQUEUE_DEPTH, default 2)
     int MaxCopyConcurrency() const;
 
     // CUDA's current device is per thread and defaults to 0: pipeline stages running on pool threads adopt the
@@ -381,6 +398,8 @@ class InferenceManager : public ::trtlab::Resources {
 
   private:
     int m_Device;
+    std::atomic<uint64_t> m_ComputeNs{0};
+    std::atomic<uint64_t> m_ComputeCount{0};
     int m_MaxExecutions;
     int m_MaxBuffers;
     size_t m_HostStackSize;
@@ -457,7 +476,7 @@ struct InferRunner : public AsyncComputeWrapper<void(std::shared_ptr<Bindings>&)
             bindings->CopyFromDevice(bindings->OutputBindings());                  // D2H
             resources->AcquireThreadPool("post").enqueue([resources, bindings, trt_ctx, Post]() mutable {
                 resources->ActivateDevice();
-                trt_ctx->Synchronize();
+                resources->RecordComputeTime(trt_ctx->Synchronize());
                 trt_ctx.reset();  // returns both pool tokens
                 bindings->Synchronize();
                 (*Post)(bindings);
@@ -496,7 +515,8 @@ enum InferBenchKey {
     kLatencyP50,
     kLatencyP90,
     kLatencyP99,
-    kLatencyMax
+    kLatencyMax,
+    kGpuComputeTimePerBatch  // mean device time of one forward pass (start/done events of its ExecutionContext)
 };
 
 class InferBench {

@@ -92,7 +92,7 @@ SYMBOLS = [
 
 BENCH_KEYS = ["kMaxExecConcurrency", "kMaxCopyConcurrency", "kBatchSize", "kWalltime", "kBatchesComputed",
               "kBatchesPerSecond", "kInferencesPerSecond", "kSecondsPerBatch", "kExecutionTimePerBatch",
-              "kLatencyP50", "kLatencyP90", "kLatencyP99", "kLatencyMax"]
+              "kLatencyP50", "kLatencyP90", "kLatencyP99", "kLatencyMax", "kGpuComputeTimePerBatch"]
 
 
 class B2Error(RuntimeError):

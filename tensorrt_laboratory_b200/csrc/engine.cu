@@ -568,7 +568,7 @@ int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& c
     a.a_mode = tiled ? b2k::A_TILED : b2k::A_IM2COL;
     if (cfg.halo) {
         const int R = conv_halo_rows(c, op);
-        if (!R || !b2k::conv_halo_config_exists(cl.bn) || b2k::conv_halo_smem(cl.bn, int(to.w), R) > 227 * 1024)
+        if (!R || !b2k::conv_halo_config_exists(cl.bn) || int(r.cin_phys) / 64 > 8 || b2k::conv_halo_smem(cl.bn, int(to.w), R, int(r.cin_phys) / 64) > 227 * 1024)
             return fail(B2_EINVAL, "conv %s: the halo tactic does not apply", op.name.c_str());
         cl.halo = 1;
         cl.ws_ctas = 0, cl.cn = 1, a.cn = 1, a.splits = 1, cl.stages = kHaloStagesTag, cl.sps = 1;
@@ -695,7 +695,7 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, int 
         if (R)
             for (int bn : bns)
                 if (int(r.cout_phys) % bn == 0 && b2k::conv_halo_config_exists(bn) &&
-                    b2k::conv_halo_smem(bn, int(to.w), R) <= 227 * 1024) {
+                    int(r.cin_phys) / 64 <= 8 && b2k::conv_halo_smem(bn, int(to.w), R, int(r.cin_phys) / 64) <= 227 * 1024) {
                     ConvConfig hc{bn, kHaloStagesTag, 1, 0.0, 1, 0, 1};
                     hc.halo = 1;
                     halo_cands.push_back(hc);
@@ -869,7 +869,7 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                         b2k::conv_ws_smem(cfg.bn, cfg.stages, cfg.sps, r.res >= 0) <= 227 * 1024)
                         cfg.ws = std::min(((M + 127) / 128) * (int(r.cout_phys) / cfg.bn), c->force_ws > 1 ? c->force_ws : 148);
                     if (c->force_halo > 0 && conv_halo_rows(c, op) && b2k::conv_halo_config_exists(cfg.bn) && cfg.splits == 1 &&
-                        b2k::conv_halo_smem(cfg.bn, int(to.w), conv_halo_rows(c, op)) <= 227 * 1024)
+                        int(r.cin_phys) / 64 <= 8 && b2k::conv_halo_smem(cfg.bn, int(to.w), conv_halo_rows(c, op), int(r.cin_phys) / 64) <= 227 * 1024)
                         cfg.halo = 1, cfg.ws = 0, cfg.cn = 1;
                     if (c->force_cn > 1 && kbsz == 64 && cfg.ws == 0 && !cfg.halo && (int(r.cout_phys) / cfg.bn) % c->force_cn == 0) cfg.cn = c->force_cn;
                     const bool forced = c->force_bn || c->force_stages || c->force_splits || c->force_sps;
@@ -909,7 +909,6 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                                     tune_cache_append(e, op_index, e->max_batch, top);
                                 }
                                 splits = top.splits;
-                                halo = top.halo;
                             }
                             int rc = autotune_conv(c, op, batch, splits, halo, &cfg);
                             if (rc) return rc;

@@ -1011,8 +1011,9 @@ conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_const
 //   A traffic per tile and channel block: (R+2)(W+2) pixel rows instead of 9 x 128.
 //
 //   warp 0 = halo producer, warp 1 = MMA issuer, warp 2 = TMEM owner, warp 3 = weight producer, all 4 = epilogue.
-//   K order: channel block outer, tap inner (the im2col kernel runs tap outer) -- same products, different fp32
-//   summation order.
+//   The halo blocks of ALL channel blocks stay resident, so the K loop runs tap outer / channel block inner exactly
+//   like the im2col kernel: same products in the same fp32 summation order -> bit-identical results, whichever of the
+//   two tactics the tuner picks.
 // =================================================================================================
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -1027,7 +1028,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
                  : "memory");
 }
 
-constexpr int kHaloAStages = 2;
+constexpr int kHaloMaxCBlocks = 8;
 __host__ __device__ constexpr int halo_b_stages(int bn) { return bn >= 256 ? 3 : 4; }
 // bytes of one A stage: the loaded halo block, but never less than what the farthest tap's 128-row window touches
 __host__ __device__ constexpr int halo_a_stage_bytes(int w, int r) {
@@ -1036,8 +1037,8 @@ __host__ __device__ constexpr int halo_a_stage_bytes(int w, int r) {
     const int rows = loaded > touched ? loaded : touched;
     return (rows * 128 + 1023) / 1024 * 1024;
 }
-__host__ __device__ constexpr int halo_smem_bytes(int bn, int w, int r) {
-    return kHaloAStages * halo_a_stage_bytes(w, r) + halo_b_stages(bn) * bn * 128 + 256 + bn * 4 + 1024;
+__host__ __device__ constexpr int halo_smem_bytes(int bn, int w, int r, int cblocks) {
+    return cblocks * halo_a_stage_bytes(w, r) + halo_b_stages(bn) * bn * 128 + 256 + bn * 4 + 1024;
 }
 
 template <int BN>
@@ -1054,13 +1055,13 @@ conv3x3_halo_tcgen05(const __grid_constant__ CUtensorMap mapIn, const __grid_con
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int W = p.Wo, Wp = p.Wo + 2, R = p.halo_rows;
     const int a_stage = halo_a_stage_bytes(W, R);
+    const int cblocks = p.cblocks;
     uint8_t* sA = smem;
-    uint8_t* sB = smem + kHaloAStages * a_stage;
-    uint8_t* sOut = smem;  // staging reuses the drained rings
+    uint8_t* sB = smem + cblocks * a_stage;
+    uint8_t* sOut = smem;  // staging reuses the drained buffers
     uint8_t* tail = sB + NB * B_BLK;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
-    uint64_t* a_empty = a_full + kHaloAStages;
-    uint64_t* b_full = a_empty + kHaloAStages;
+    uint64_t* b_full = a_full + kHaloMaxCBlocks;
     uint64_t* b_empty = b_full + NB;
     uint64_t* accum_bar = b_empty + NB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
@@ -1073,16 +1074,12 @@ conv3x3_halo_tcgen05(const __grid_constant__ CUtensorMap mapIn, const __grid_con
     const int tiles_per_img = (Ho + R - 1) / R;
     const int img = blockIdx.y / tiles_per_img;
     const int h0 = (blockIdx.y - img * tiles_per_img) * R;
-    const int cblocks = p.cblocks;
-    const int nsteps = cblocks * 9;  // weight blocks, in (cb, tap) order
+    const int nsteps = cblocks * 9;  // weight blocks, in (tap, cb) order = the packed layout's K order
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapIn);
         tma_prefetch_desc(&mapOut);
-        for (int s = 0; s < kHaloAStages; ++s) {
-            mbar_init(&a_full[s], 1);
-            mbar_init(&a_empty[s], 1);
-        }
+        for (int s = 0; s < cblocks; ++s) mbar_init(&a_full[s], 1);
         for (int s = 0; s < NB; ++s) {
             mbar_init(&b_full[s], 1);
             mbar_init(&b_empty[s], 1);
@@ -1102,29 +1099,27 @@ conv3x3_halo_tcgen05(const __grid_constant__ CUtensorMap mapIn, const __grid_con
         // ================= halo producer =================
         const uint32_t halo_bytes = static_cast<uint32_t>((R + 2) * Wp * 128);
         pdl_wait();
-        for (int cb = 0; cb < cblocks; ++cb) {
-            const int s = cb % kHaloAStages;
-            if (cb >= kHaloAStages) mbar_wait(&a_empty[s], ((cb / kHaloAStages) & 1) ^ 1);
-            if (elect_one_sync()) {
-                mbar_expect_tx(&a_full[s], halo_bytes);
-                tma_load_4d(&mapIn, &a_full[s], sA + s * a_stage, cb * 64, -1, h0 - 1, img);
+        if (elect_one_sync()) {
+            for (int cb = 0; cb < cblocks; ++cb) {
+                mbar_expect_tx(&a_full[cb], halo_bytes);
+                tma_load_4d(&mapIn, &a_full[cb], sA + cb * a_stage, cb * 64, -1, h0 - 1, img);
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        for (int cb = 0; cb < cblocks; ++cb) {
-            const int sa = cb % kHaloAStages;
-            mbar_wait(&a_full[sa], (cb / kHaloAStages) & 1);
-            const uint32_t a_base = smem_u32(sA + sa * a_stage);
+        int i = 0;
 #pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
-                const int i = cb * 9 + tap;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, sx = tap - r * 3;
+            const uint32_t tap_off = static_cast<uint32_t>((r * Wp + sx) * 128);
+#pragma unroll 1
+            for (int cb = 0; cb < cblocks; ++cb, ++i) {
                 const int sb = i % NB;
+                if (tap == 0) mbar_wait(&a_full[cb], 0);
                 mbar_wait(&b_full[sb], (i / NB) & 1);
                 tc_fence_after();
-                const int r = tap / 3, sx = tap - r * 3;
-                const uint32_t a_addr = a_base + static_cast<uint32_t>((r * Wp + sx) * 128);
+                const uint32_t a_addr = smem_u32(sA + cb * a_stage) + tap_off;
                 const uint32_t b_addr = smem_u32(sB + sb * B_BLK);
                 if (elect_one_sync()) {
 #pragma unroll
@@ -1136,7 +1131,6 @@ conv3x3_halo_tcgen05(const __grid_constant__ CUtensorMap mapIn, const __grid_con
                         umma_f16(tmem_base, ad, bd, IDESC, (i > 0 || j > 0) ? 1u : 0u);
                     }
                     umma_commit(&b_empty[sb]);
-                    if (tap == 8) umma_commit(&a_empty[sa]);
                 }
                 __syncwarp();
             }
@@ -1149,11 +1143,9 @@ conv3x3_halo_tcgen05(const __grid_constant__ CUtensorMap mapIn, const __grid_con
         for (int i = 0; i < nsteps; ++i) {
             const int sb = i % NB;
             if (i >= NB) mbar_wait(&b_empty[sb], ((i / NB) & 1) ^ 1);
-            const int cb = i / 9, tap = i - cb * 9;
-            const int kb = tap * cblocks + cb;  // the packed weights are laid out tap-major
             if (elect_one_sync()) {
                 mbar_expect_tx(&b_full[sb], B_BLK);
-                bulk_load_1d(&b_full[sb], sB + sb * B_BLK, p.wpacked + (static_cast<size_t>(kb) * (p.Cout >> 5) + (n0 >> 5)) * 4096,
+                bulk_load_1d(&b_full[sb], sB + sb * B_BLK, p.wpacked + (static_cast<size_t>(i) * (p.Cout >> 5) + (n0 >> 5)) * 4096,
                              B_BLK);
             }
             __syncwarp();
@@ -1266,7 +1258,7 @@ int conv_smem_bytes(int bn, int stages, bool residual, int sps) { return conv_sm
     X(32, 8, 2, 1) X(32, 8, 4, 1) X(64, 8, 2, 1) X(64, 8, 4, 1) X(64, 8, 8, 1) X(128, 8, 4, 1) \
     X(32, 32, 2, 1) X(32, 32, 4, 1) X(64, 32, 1, 1) X(64, 32, 2, 1) X(64, 32, 4, 1) X(128, 32, 2, 1) X(128, 32, 4, 1)
 
-int conv_halo_smem(int bn, int w, int r) { return halo_smem_bytes(bn, w, r); }
+int conv_halo_smem(int bn, int w, int r, int cblocks) { return halo_smem_bytes(bn, w, r, cblocks); }
 bool conv_halo_config_exists(int bn) { return bn == 64 || bn == 128 || bn == 256; }
 static int init_conv_halo_kernels() {
     int e;
@@ -1277,8 +1269,8 @@ static int init_conv_halo_kernels() {
 }
 static int launch_conv_halo(const ConvLaunch& L, cudaStream_t stream) {
     const int R = L.args.halo_rows;
-    const size_t smem = size_t(halo_smem_bytes(L.bn, L.args.Wo, R));
-    if (smem > 227 * 1024 || R < 1 || R * (L.args.Wo + 2) > 128) return static_cast<int>(cudaErrorInvalidValue);
+    const size_t smem = size_t(halo_smem_bytes(L.bn, L.args.Wo, R, L.args.cblocks));
+    if (smem > 227 * 1024 || R < 1 || R * (L.args.Wo + 2) > 128 || L.args.cblocks > kHaloMaxCBlocks) return static_cast<int>(cudaErrorInvalidValue);
     dim3 grid(L.grid_n, L.grid_m, 1);
     switch (L.bn) {
         case 64: return launch_kernel(conv3x3_halo_tcgen05<64>, grid, dim3(128), smem, stream, true, L.mapA, L.mapOut, L.args);

@@ -69,7 +69,7 @@ int init_conv_kernels();
 bool conv_config_exists(int bn, int kb, int stages, int sps = 1);  // is this configuration instantiated?
 int conv_smem_bytes(int bn, int stages, bool residual, int sps = 1);  // dynamic shared memory of one CTA
 bool conv_halo_config_exists(int bn);                                // 3x3 halo variant
-int conv_halo_smem(int bn, int w, int r);
+int conv_halo_smem(int bn, int w, int r, int cblocks);
 bool conv_ws_config_exists(int bn, int stages, int sps);             // persistent warp-specialised variant
 int conv_ws_smem(int bn, int stages, int sps, bool residual);
 // programmatic dependent launch on/off for every kernel of this library (default on)

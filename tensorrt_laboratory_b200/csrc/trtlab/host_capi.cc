@@ -5,6 +5,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
 #include <exception>
 
 #include "../b2_internal.h"
@@ -238,6 +241,29 @@ int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int bat
         issue(std::max(warmup, contexts * ring_batches <= 256 ? contexts * ring_batches : warmup), 0);  // also builds every cached graph
         cuda_ok(cudaDeviceSynchronize(), "warmup sync");
     }
+    // B2_PROBE_BG_H2D=1: keep the copy engine busy with pinned 'input' uploads nobody consumes while the forward passes
+    // run -- isolates how much PCIe traffic alone slows the kernels down (diagnostic, off by default)
+    std::atomic<bool> bg_stop{false};
+    std::thread bg;
+    if (status == B2_OK && getenv("B2_PROBE_BG_H2D") && atoi(getenv("B2_PROBE_BG_H2D")) > 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        bg = std::thread([&, dev] {
+            cudaSetDevice(dev);
+            void *h = nullptr, *d = nullptr;
+            cudaStream_t s = nullptr;
+            if (cudaMallocHost(&h, in_bytes) == cudaSuccess && cudaMalloc(&d, in_bytes) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) {
+                while (!bg_stop.load()) {
+                    cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s);
+                    cudaStreamSynchronize(s);
+                }
+            }
+            if (s) cudaStreamDestroy(s);
+            if (d) cudaFree(d);
+            if (h) cudaFreeHost(h);
+        });
+    }
     if (status == B2_OK) {
         cuda_ok(cudaEventRecord(start, ctrl), "record start");
         for (auto& x : ctx) cuda_ok(cudaStreamWaitEvent(x.s, start, 0), "wait start");
@@ -252,6 +278,8 @@ int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int bat
         if (status == B2_OK && cuda_ok(cudaEventElapsedTime(&ms, start, stop), "elapsed")) *elapsed_ms = ms;
         if (launches_per_step) *launches_per_step = b2_context_nb_launches(ctx[0].c, batch);
     }
+    bg_stop = true;
+    if (bg.joinable()) bg.join();
     cudaDeviceSynchronize();
     for (auto& x : ctx) {
         if (x.c) b2_context_destroy(x.c);

@@ -267,28 +267,42 @@ size_t Bindings::BindingSize(uint32_t binding_id) const {  // bindings.cc:171-17
 }
 
 // ---- ExecutionContext ----------------------------------------------------------------------------------
-ExecutionContext::ExecutionContext(size_t workspace_bytes) : m_Workspace(nullptr), m_WorkspaceBytes(workspace_bytes) {
-    m_Workspace = CudaDeviceMemory::Allocate(std::max<size_t>(workspace_bytes, 1024));
+ExecutionContext::Lane::Lane(size_t workspace_bytes)
+    : workspace(CudaDeviceMemory::Allocate(std::max<size_t>(workspace_bytes, 1024))), bytes(std::max<size_t>(workspace_bytes, 1024)),
+      last_done(nullptr) {}
+ExecutionContext::Lane::~Lane() { CudaDeviceMemory::Free(workspace); }
+
+ExecutionContext::ExecutionContext(size_t workspace_bytes) : ExecutionContext(std::make_shared<Lane>(workspace_bytes)) {}
+ExecutionContext::ExecutionContext(std::shared_ptr<Lane> lane) : m_Lane(std::move(lane)) {
     TRT_CHECK_CUDA(cudaEventCreate(&m_Start));
     TRT_CHECK_CUDA(cudaEventCreate(&m_Done));
 }
 ExecutionContext::~ExecutionContext() {
+    {
+        std::lock_guard<std::mutex> lock(m_Lane->mutex);
+        if (m_Lane->last_done == m_Done) {  // nobody may wait on an event that is about to disappear
+            cudaEventSynchronize(m_Done);
+            m_Lane->last_done = nullptr;
+        }
+    }
     cudaEventDestroy(m_Start);
     cudaEventDestroy(m_Done);
-    CudaDeviceMemory::Free(m_Workspace);
 }
 void ExecutionContext::SetContext(std::shared_ptr<IExecutionContext> context) {
     m_Context = std::move(context);
-    if (m_Context) TRT_CHECK_B2(b2_context_set_device_memory(m_Context->handle, m_Workspace));
+    if (m_Context) TRT_CHECK_B2(b2_context_set_device_memory(m_Context->handle, m_Lane->workspace));
 }
 void ExecutionContext::Infer(const std::shared_ptr<Bindings>& bindings) {
     TRTLAB_CHECK(m_Context) << "ExecutionContext::Infer without a model context (SetContext)";
-    TRTLAB_CHECK_OP(bindings->GetModel()->GetActivationsMemorySize(), <=, std::max<size_t>(m_WorkspaceBytes, 1024));
+    TRTLAB_CHECK_OP(bindings->GetModel()->GetActivationsMemorySize(), <=, m_Lane->bytes);
     cudaStream_t s = bindings->Stream();
-    TRT_CHECK_CUDA(cudaEventRecord(m_Start, s));
     const int batch = int(bindings->BatchSize() ? bindings->BatchSize() : bindings->GetModel()->GetMaxBatchSize());
+    std::lock_guard<std::mutex> lock(m_Lane->mutex);  // enqueue order on the lane == execution order on the device
+    if (m_Lane->last_done && m_Lane->last_done != m_Done) TRT_CHECK_CUDA(cudaStreamWaitEvent(s, m_Lane->last_done, 0));
+    TRT_CHECK_CUDA(cudaEventRecord(m_Start, s));
     TRT_CHECK_B2(b2_context_enqueue(m_Context->handle, batch, bindings->DeviceAddresses(), s, nullptr));
     TRT_CHECK_CUDA(cudaEventRecord(m_Done, s));
+    m_Lane->last_done = m_Done;
 }
 double ExecutionContext::Synchronize() {
     TRT_CHECK_CUDA(cudaEventSynchronize(m_Done));
@@ -322,6 +336,15 @@ InferenceManager::~InferenceManager() { JoinAllThreads(); }
 
 void InferenceManager::ActivateDevice() const { TRT_CHECK_CUDA(cudaSetDevice(m_Device)); }
 
+void InferenceManager::RecordComputeTime(double seconds) {
+    m_ComputeNs.fetch_add(uint64_t(seconds * 1e9), std::memory_order_relaxed);
+    m_ComputeCount.fetch_add(1, std::memory_order_relaxed);
+}
+double InferenceManager::MeanComputeTime(bool reset) {
+    const uint64_t n = reset ? m_ComputeCount.exchange(0) : m_ComputeCount.load();
+    const uint64_t ns = reset ? m_ComputeNs.exchange(0) : m_ComputeNs.load();
+    return n ? double(ns) * 1e-9 / double(n) : 0.0;
+}
 int InferenceManager::MaxExecConcurrency() const { return m_MaxExecutions; }
 int InferenceManager::MaxCopyConcurrency() const { return m_MaxBuffers; }
 
@@ -363,7 +386,7 @@ void InferenceManager::RegisterModel(const std::string& name, std::shared_ptr<Mo
     model->SetName(name);
     m_Models[name] = model;
     auto pool = Pool<IExecutionContext>::Create();
-    for (uint32_t i = 0; i < max_concurrency; i++) pool->Push(model->CreateExecutionContext());
+    for (uint32_t i = 0; i < max_concurrency * uint32_t(EnqueueDepth()); i++) pool->Push(model->CreateExecutionContext());
     m_ModelExecutionContexts[model.get()] = pool;
 }
 
@@ -393,8 +416,20 @@ void InferenceManager::AllocateResources() {  // inference_manager.cc:181-205
     for (int i = 0; i < m_MaxBuffers; i++)
         m_Buffers->Push(std::make_shared<FixedBuffers<CudaPinnedHostMemory, CudaDeviceMemory>>(m_HostStackSize, m_DeviceStackSize));
 
+    // m_MaxExecutions lanes (activation arenas == forward passes that can run at once), EnqueueDepth() tokens queued on each
     m_ExecutionContexts = Pool<ExecutionContext>::Create();
-    for (int i = 0; i < m_MaxExecutions; i++) m_ExecutionContexts->EmplacePush(new ExecutionContext(m_ActivationsSize));
+    std::vector<std::shared_ptr<ExecutionContext::Lane>> lanes;
+    for (int i = 0; i < m_MaxExecutions; i++) lanes.push_back(std::make_shared<ExecutionContext::Lane>(m_ActivationsSize));
+    for (int d = 0; d < EnqueueDepth(); d++)
+        for (int i = 0; i < m_MaxExecutions; i++) m_ExecutionContexts->EmplacePush(new ExecutionContext(lanes[size_t(i)]));
+}
+
+// Tokens per lane.  1 = the reference's behaviour (a lane is idle from the end of a forward pass until the host has
+// noticed, released the token and enqueued the next request); 2 (default) keeps the next request queued on the device.
+int InferenceManager::EnqueueDepth() {
+    const char* v = getenv("TRTLAB_ENQUEUE_DEPTH");
+    const int d = v ? atoi(v) : 2;
+    return d < 1 ? 1 : (d > 4 ? 4 : d);
 }
 
 auto InferenceManager::GetModel(std::string model_name) -> std::shared_ptr<Model> {
@@ -475,6 +510,7 @@ std::unique_ptr<InferBench::Results> InferBench::Run(const ModelsList& models, u
     auto lat_mutex = std::make_shared<std::mutex>();
     if (latencies_s) lat->reserve(max_batches ? max_batches : 1 << 16);
 
+    m_Resources->MeanComputeTime(true);
     auto start = clock::now();
     auto last = start + std::chrono::microseconds(static_cast<long long>(seconds * 1e6));
     while ((max_batches ? batch_count < max_batches : true) && clock::now() < last) {
@@ -510,6 +546,7 @@ std::unique_ptr<InferBench::Results> InferBench::Run(const ModelsList& models, u
     results[kBatchesPerSecond] = batch_count / total_time;
     results[kInferencesPerSecond] = inferences / total_time;
     results[kSecondsPerBatch] = batch_count ? total_time / batch_count : 0.0;
+    results[kGpuComputeTimePerBatch] = m_Resources->MeanComputeTime(true);
     results[kExecutionTimePerBatch] = batch_count ? total_time / (double(batch_count) / m_Resources->MaxExecConcurrency()) : 0.0;
     if (latencies_s && !lat->empty()) {
         std::vector<double> sorted(*lat);

@@ -97,11 +97,14 @@ def test_persistent_warp_specialised_tactic(gpu, bn, stages, sps):
                                             (512, 7, 512, 128), (64, 20, 128, 64), (64, 126, 64, 64)])
 def test_halo_3x3_tactic(gpu, cin, h, cout, bn):
     """conv3x3_halo_tcgen05: the input block of a tile is loaded once and the nine taps are shifted views of it.  Covers
-    every ResNet 3x3 geometry (R = 2, 4, 8, 7 rows per tile), ragged last row-tiles (14 = 8 + 6, 20 = 5*4), the widest
+    every ResNet 3x3 geometry (R = 2, 4, 8, 7 rows per tile; 1, 2, 4, 8 resident channel blocks), ragged last row-tiles (14 = 8 + 6, 20 = 5*4), the widest
     row the tile holds (W + 2 = 128) and every N tile."""
     batch = 1 if h > 100 else 3
-    _check(cin, h, cout, 3, 1, batch=batch, options={"bn": bn, "halo": 1})
+    a = _check(cin, h, cout, 3, 1, batch=batch, options={"bn": bn, "halo": 1})
     assert any(" halo" in n for n in helpers.LAST_LAUNCH_NAMES), helpers.LAST_LAUNCH_NAMES
+    b = _check(cin, h, cout, 3, 1, batch=batch, options={"bn": bn, "halo": -1})
+    assert not any(" halo" in n for n in helpers.LAST_LAUNCH_NAMES)
+    np.testing.assert_array_equal(a, b)  # same K order as the im2col kernel: bit-identical
     _check(cin, h, cout, 3, 1, batch=batch, relu=False, options={"bn": bn, "halo": 1}, seed=3)
 
 

@@ -26,8 +26,9 @@ def main():
     for var in variants:
       for t in tunes:
         for k in list(os.environ):
-            if k.startswith("B2_FORCE_"):
+            if k.startswith("B2_FORCE_") or k.startswith("B2_PDL"):
                 del os.environ[k]
+        os.environ["B2_PDL"] = "1"  # process-wide switch: always restate it
         os.environ.update(var)
         tag = "".join(f"_{k[3:].lower()}{v}" for k, v in var.items())
         cache = os.path.join(out_dir, f"tactics_autotune{t}{tag}.txt")

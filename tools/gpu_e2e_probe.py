@@ -18,10 +18,11 @@ def main():
         mgr.register_model("rn50", blob)
         mgr.update_resources()
         mgr.prefill_inputs("rn50", ring[:buf])
-        mgr.bench("rn50", 8, 600.0, 80, False)
+        mgr.bench("rn50", 8, 600.0, int(os.environ.get("PROBE_WARMUP", "80")), False)
         res, lats = mgr.bench("rn50", 8, 600.0, 1500, True)
         print(json.dumps(dict(contexts=ctx, buffers=buf, cuda_threads=cuda_t, post_threads=post_t,
-                              img_s=res["kInferencesPerSecond"], p50_ms=float(np.percentile(lats, 50) * 1e3),
+                              img_s=res["kInferencesPerSecond"], gpu_ms_per_batch=res["kGpuComputeTimePerBatch"] * 1e3,
+                              depth=os.environ.get("TRTLAB_ENQUEUE_DEPTH", "2"), p50_ms=float(np.percentile(lats, 50) * 1e3),
                               p99_ms=float(np.percentile(lats, 99) * 1e3))), flush=True)
         mgr.close()
 
