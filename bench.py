@@ -190,6 +190,11 @@ def run_b200(args):
     if capi.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device visible and there is no CPU fallback for the product path")
     capi.check(lib.b2_device_set(local))
+    # Each replica keeps ~6 host threads (bench loop, pre/cuda pools, 3 post threads).  When the replicas of this box
+    # outnumber its usable cores, spin-waiting on CUDA events starves the threads that feed the GPUs: block instead.
+    sync_mode = os.environ.get("B2_BENCH_SYNC", "auto")
+    blocking = sync_mode == "block" or (sync_mode == "auto" and usable_cores() < 6 * world)
+    capi.check(lib.b2_device_set_blocking_sync(1 if blocking else 0))
     dist = None
     if world > 1:
         import torch
@@ -302,7 +307,9 @@ def run_b200(args):
         "config": {"workload": "ResNet-50 fp16 batch=8, 1xB200 per replica, 4 concurrent ExecutionContexts/streams, synthetic 3x224x224 (BASELINE.json configs[1])",
                    "global_batch": BATCH * world, "contexts": CONTEXTS, "buffers": BUFFERS,
                    "l2_policy": f"inputs larger than L2: ring of {RING} distinct batches = {RING * in_bytes / 1e6:.0f} MB",
-                   "parallelism": f"replicas x{world} (no collective)"},
+                   "parallelism": f"replicas x{world} (no collective)",
+                   "host_sync": "blocking" if blocking else "spin", "host_cores": usable_cores(),
+                   "enqueue_depth": int(os.environ.get("TRTLAB_ENQUEUE_DEPTH", "2"))},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                 "p50_ms": p50, "p99_ms": p99, "api": "InferenceManager+InferRunner+InferBench (pinned host Buffers, H2D/D2H per request)"},

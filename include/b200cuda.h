@@ -22,6 +22,9 @@ extern "C" {
 int b2_device_count(void);                   /* 0 when no driver / no device */
 int b2_device_set(int device);               /* cudaSetDevice */
 int b2_device_get(void);                     /* current device or -1 */
+/* how host threads wait for the current device: 0 = driver default (spin when cores allow), 1 = block on an interrupt
+ * (cudaDeviceScheduleBlockingSync) -- for boxes where replicas x pipeline threads outnumber the host cores */
+int b2_device_set_blocking_sync(int blocking);
 int b2_device_info(int device, char* name, int name_cap, int* cc_major, int* cc_minor, int* sm_count,
                    size_t* total_mem, size_t* l2_bytes);
 

@@ -55,6 +55,7 @@ SYMBOLS = [
     ("b2_device_count", _I, []),
     ("b2_device_set", _I, [_I]),
     ("b2_device_get", _I, []),
+    ("b2_device_set_blocking_sync", _I, [_I]),
     ("b2_device_info", _I, [_I, _S, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_SZ), C.POINTER(_SZ)]),
     ("b2_malloc_device", _I, [_PVP, _SZ]),
     ("b2_free_device", _I, [_VP]),

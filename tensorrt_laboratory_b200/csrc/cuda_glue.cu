@@ -46,6 +46,10 @@ int b2_device_get(void) {
     return d;
 }
 
+int b2_device_set_blocking_sync(int blocking) {
+    B2G_CUDA(cudaSetDeviceFlags(blocking ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto));
+    return B2_OK;
+}
 int b2_device_info(int device, char* name, int name_cap, int* cc_major, int* cc_minor, int* sm_count,
                    size_t* total_mem, size_t* l2_bytes) {
     cudaDeviceProp p;

@@ -683,7 +683,9 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, int 
                 continue;  // split-K only where the plain grid leaves SMs idle
             const bool cn_forced_here = c->force_cn > 1 && kbsz == 64 && (int(r.cout_phys) / bn) % c->force_cn == 0;
             if (!cn_forced_here) candidates.push_back(ConvConfig{bn, st, sp, 0.0, sps, 0, 1});
-            if (kbsz == 64 && c->force_cn >= 0)  // clusters along N that multicast the activation tile
+            // clusters along N that multicast the activation tile: never won a timing on B200 (the L2 read is shared but
+            // every SM still ingests the whole tile, and the cluster barriers cost latency) -> tried only on request
+            if (kbsz == 64 && c->force_cn > 0)
                 for (int cn = 2; cn <= 4; cn *= 2)
                     if ((int(r.cout_phys) / bn) % cn == 0 && (!c->force_cn || cn == c->force_cn))
                         candidates.push_back(ConvConfig{bn, st, sp, 0.0, sps, 0, cn});

@@ -694,6 +694,7 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
     }
     if (dbg && threadIdx.x == 64) dbg[6] = clock64();
+    if (p.pdl_trigger == 2) pdl_launch_dependents();  // latest useful point: only the output store is left
     fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
     tc_fence_before();
     __syncthreads();

@@ -230,7 +230,15 @@ int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int bat
         cuda_ok(cudaEventCreate(&start), "cudaEventCreate");
         cuda_ok(cudaEventCreate(&stop), "cudaEventCreate");
     }
+    // B2_PROBE_STAGGER=1: de-phase the streams (stream k first runs one forward pass of a smaller batch), the way
+    // independently arriving requests meet each other; without it all contexts march through the layers in lockstep.
+    const bool stagger = getenv("B2_PROBE_STAGGER") && atoi(getenv("B2_PROBE_STAGGER")) > 0;
     auto issue = [&](int n_steps, int offset) {
+        for (int k = 1; stagger && k < contexts && status == B2_OK; ++k) {
+            Ctx& x = ctx[size_t(k)];
+            x.bind[in_id] = ring[0];
+            status = b2_context_enqueue(x.c, std::max(1, batch * k / contexts), x.bind.data(), x.s, nullptr);
+        }
         for (int i = 0; i < n_steps && status == B2_OK; ++i) {
             Ctx& x = ctx[size_t(i % contexts)];
             x.bind[in_id] = ring[size_t((i + offset) % ring_batches)];

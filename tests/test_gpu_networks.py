@@ -185,7 +185,7 @@ def test_tactic_cache_roundtrip(gpu, tmp_path, monkeypatch):
     x = np.random.default_rng(0).standard_normal((2, 64, 28, 28), dtype=np.float32)
     a = helpers.run_engine(low, x, builder.PREC_FP16)
     lines = cache.read_text().strip().splitlines()
-    assert len(lines) == 1 and len(lines[0].split()) == 8
+    assert len(lines) == 1 and len(lines[0].split()) == 10
     b = helpers.run_engine(low, x, builder.PREC_FP16)
     assert cache.read_text().strip().splitlines() == lines  # nothing re-tuned
     np.testing.assert_array_equal(list(a.values())[0], list(b.values())[0])

@@ -10,7 +10,9 @@ from tensorrt_laboratory_b200 import builder, capi, weights  # noqa: E402
 
 blob = builder.build_resnet_plan(50, builder.PREC_FP16, 8)
 ring = weights.synthetic_input(8, ring=8)
-for bg in ("0", "1", "0", "1"):
+for bg, st in (("0", "0"), ("0", "1"), ("1", "1"), ("0", "0"), ("0", "1")):
     os.environ["B2_PROBE_BG_H2D"] = bg
-    ms, _ = capi.device_throughput(blob, 4, 8, 800, 20, ring)
-    print(json.dumps({"bg_h2d": bg, "img_s": round(800 * 8 / (ms * 1e-3))}), flush=True)
+    os.environ["B2_PROBE_STAGGER"] = st
+    for n in (2, 3, 4):
+        ms, _ = capi.device_throughput(blob, n, 8, 800, 20, ring)
+        print(json.dumps({"bg_h2d": bg, "stagger": st, "contexts": n, "img_s": round(800 * 8 / (ms * 1e-3))}), flush=True)
