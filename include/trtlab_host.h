@@ -24,10 +24,10 @@ void trt_manager_destroy(trt_manager* m);
 int trt_manager_register_model(trt_manager* m, const char* name, const void* blob, size_t nbytes, int max_concurrency);
 int trt_manager_allocate(trt_manager* m); /* InferenceManager::AllocateResources */
 /* one request through InferRunner::Infer(pre, post): pinned H2D -> forward -> D2H, blocking */
-int trt_manager_infer(trt_manager* m, const char* model, int batch, const float* input, size_t input_bytes,
+int trt_manager_infer(trt_manager* m, const char* model, int batch, const void* input, size_t input_bytes,
                       float* output, size_t output_bytes, double* compute_seconds);
 /* write a distinct batch from `ring` into the pinned input region of every pooled Buffers */
-int trt_manager_prefill_inputs(trt_manager* m, const char* model, const float* ring, size_t ring_batches);
+int trt_manager_prefill_inputs(trt_manager* m, const char* model, const void* ring, size_t ring_batches);
 /* InferBench::Run closed loop; results16[InferBenchKey]; optional per-request latencies (seconds) */
 int trt_manager_bench(trt_manager* m, const char* model, int batch, double seconds, size_t max_batches,
                       double* results16, double* latencies, size_t lat_cap, size_t* lat_count);
@@ -35,7 +35,7 @@ int trt_manager_bench(trt_manager* m, const char* model, int batch, double secon
 int trt_timed_pipeline(const void* blob, size_t nbytes, int iters, float* h2d_ms, float* compute_ms, float* d2h_ms);
 /* device-resident throughput of `contexts` concurrent execution contexts (inputs cycled through a device ring) */
 int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int batch, int steps, int warmup,
-                          const float* host_ring, int ring_batches, double* elapsed_ms, int* launches_per_step);
+                          const void* host_ring, int ring_batches, double* elapsed_ms, int* launches_per_step);
 
 #ifdef __cplusplus
 }

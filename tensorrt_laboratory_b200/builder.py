@@ -90,8 +90,11 @@ def _name(s: str) -> bytes:
 
 def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
                outputs: Optional[Sequence[str]] = None, name: Optional[str] = None, stem_s2d: bool = True,
-               pack_weights: bool = True) -> bytes:
+               pack_weights: bool = True, input_dtype: str = "f32") -> bytes:
     """Serialize ``lowered`` (from :func:`graph.lower` with weights) into a plan blob.
+
+    ``input_dtype``: "f32" = the reference's binding contract (pybind casts inputs to float, infer.cc:435-441);
+    "f16" (fp16 engines only) = the secondary mode of SURVEY.md §8(d): half the H2D bytes per request.
 
     ``outputs``: tensor names to expose as output bindings (default: the graph output).  4-D activation
     outputs get an ``OUTPUT_CAST`` to fp32 NCHW; vector outputs (fc / softmax) are written in place.
@@ -133,7 +136,10 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
     # input binding + cast
     cin, hin, win = lowered["input_shape"]
     t_in = add_tensor(lowered["input"])
-    bindings.append(dict(name=lowered["input"], is_input=1, dtype=0, tensor=t_in, dims=[cin, hin, win]))
+    if input_dtype not in ("f32", "f16") or (input_dtype == "f16" and precision != PREC_FP16):
+        raise ValueError("input_dtype is 'f32' (the reference's binding contract) or, for fp16 engines, 'f16'")
+    bindings.append(dict(name=lowered["input"], is_input=1, dtype=1 if input_dtype == "f16" else 0, tensor=t_in,
+                         dims=[cin, hin, win]))
     ops.append(dict(name="cast:" + lowered["input"], type=OP_INPUT_CAST, inp=-1, res=-1, out=t_in, binding=0))
     # fp16 stem: a stride-2 conv that is the only reader of a thin (<= 4 channel) even-width input runs on a
     # horizontally space-to-depth packed copy of the input (see stem_s2d_transform)
@@ -239,11 +245,12 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
     return bytes(blob)
 
 
-def build_resnet_plan(depth: int = 50, precision: int = PREC_FP16, max_batch: int = 8, seed: int = 0) -> bytes:
+def build_resnet_plan(depth: int = 50, precision: int = PREC_FP16, max_batch: int = 8, seed: int = 0,
+                      input_dtype: str = "f32") -> bytes:
     """Convenience: generated Caffe-v1 ResNet + deterministic weights -> plan."""
     from . import weights as Wt
     net = G.resnet_caffe(depth)
-    return build_plan(G.lower(net, Wt.random_weights(net, seed)), precision, max_batch)
+    return build_plan(G.lower(net, Wt.random_weights(net, seed)), precision, max_batch, input_dtype=input_dtype)
 
 
 def single_conv_net(cin: int, h: int, w: int, cout: int, k: int, stride: int, pad: int, relu: bool = True,

@@ -91,6 +91,7 @@ SYMBOLS = [
     ("trt_device_throughput", _I, [_VP, _SZ, _I, _I, _I, _I, _VP, _I, C.POINTER(_D), C.POINTER(_I)]),
 ]
 
+NP_DTYPES = {0: np.float32, 1: np.float16, 2: np.int8, 3: np.int32}  # B2_DT_* (same order as utils.cc:40-46)
 BENCH_KEYS = ["kMaxExecConcurrency", "kMaxCopyConcurrency", "kBatchSize", "kWalltime", "kBatchesComputed",
               "kBatchesPerSecond", "kInferencesPerSecond", "kSecondsPerBatch", "kExecutionTimePerBatch",
               "kLatencyP50", "kLatencyP90", "kLatencyP99", "kLatencyMax", "kGpuComputeTimePerBatch"]
@@ -262,8 +263,9 @@ class Engine:
                 is_input=bool(lib.b2_engine_binding_is_input(self.handle, i)),
                 dtype=lib.b2_engine_binding_dtype(self.handle, i),
                 shape=shape,
-                item_bytes=int(np.prod(shape)) * 4,
+                item_bytes=int(np.prod(shape)) * NP_DTYPES[lib.b2_engine_binding_dtype(self.handle, i)]().itemsize,
             ))
+            self.bindings[-1]["np_dtype"] = NP_DTYPES[self.bindings[-1]["dtype"]]
 
     @property
     def device_memory_size(self) -> int:
@@ -291,6 +293,15 @@ class Engine:
             pass
 
 
+def input_np_dtype(blob: bytes):
+    """numpy dtype of a plan's (single) input binding: float32, or float16 for plans built with input_dtype="f16"."""
+    meta = Engine(blob, inspect_only=True)
+    try:
+        return [b["np_dtype"] for b in meta.bindings if b["is_input"]][0]
+    finally:
+        meta.destroy()
+
+
 class Session:
     """One ExecutionContext + its activation arena + device/pinned binding buffers + a stream:
     the Python-side analogue of the reference's BenchmarkWorkspace (workspace.cc:90-124)."""
@@ -316,7 +327,7 @@ class Session:
     def host_array(self, i: int, batch: Optional[int] = None) -> np.ndarray:
         b = self.engine.bindings[i]
         n = batch or self.engine.max_batch
-        return self.host[i].array(np.float32, (n,) + b["shape"])
+        return self.host[i].array(b["np_dtype"], (n,) + b["shape"])
 
     def h2d(self, batch: int):
         for i, b in enumerate(self.engine.bindings):
@@ -332,8 +343,8 @@ class Session:
         check(self._lib.b2_context_enqueue(self.ctx, batch, self._ptrs, self.stream.handle, None))
 
     def infer(self, x: np.ndarray) -> Dict[str, np.ndarray]:
-        """Synchronous convenience: pinned H2D -> forward -> D2H.  ``x``: [batch, C, H, W] fp32."""
-        x = np.ascontiguousarray(x, dtype=np.float32)
+        """Synchronous convenience: pinned H2D -> forward -> D2H.  ``x``: [batch, C, H, W] (cast to the binding dtype)."""
+        x = np.ascontiguousarray(x)
         batch = x.shape[0]
         inputs = [i for i, b in enumerate(self.engine.bindings) if b["is_input"]]
         if len(inputs) != 1:
@@ -410,7 +421,7 @@ class InferenceManager:
 
     def infer(self, name: str, x: np.ndarray) -> np.ndarray:
         meta = self.models[name]
-        x = np.ascontiguousarray(x, dtype=np.float32)
+        x = np.ascontiguousarray(x, dtype=[b["np_dtype"] for b in meta.bindings if b["is_input"]][0])
         batch = x.shape[0]
         ob = [b for b in meta.bindings if not b["is_input"]][0]
         out = np.empty((batch,) + ob["shape"], dtype=np.float32)
@@ -419,7 +430,7 @@ class InferenceManager:
         return out
 
     def prefill_inputs(self, name: str, ring: np.ndarray):
-        ring = np.ascontiguousarray(ring, dtype=np.float32)
+        ring = np.ascontiguousarray(ring, dtype=[b["np_dtype"] for b in self.models[name].bindings if b["is_input"]][0])
         check(self._lib.trt_manager_prefill_inputs(self.handle, name.encode(), ring.ctypes.data, ring.shape[0]))
 
     def bench(self, name: str, batch: int, seconds: float = 5.0, max_batches: int = 0, want_latencies: bool = True):
@@ -454,8 +465,8 @@ def timed_pipeline(blob: bytes, iters: int = 20):
 
 
 def device_throughput(blob: bytes, contexts: int, batch: int, steps: int, warmup: int, ring: np.ndarray):
-    """-> (elapsed_ms, kernel launches per step).  ``ring``: [R, batch, C, H, W] fp32 host array."""
-    ring = np.ascontiguousarray(ring, dtype=np.float32)
+    """-> (elapsed_ms, kernel launches per step).  ``ring``: [R, batch, C, H, W] host array (cast to the input dtype)."""
+    ring = np.ascontiguousarray(ring, dtype=input_np_dtype(blob))
     ms = _D()
     nl = _I()
     check(load().trt_device_throughput(blob, len(blob), contexts, batch, steps, warmup, ring.ctypes.data,

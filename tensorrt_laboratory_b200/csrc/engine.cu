@@ -137,6 +137,7 @@ struct Launch {
     const void* w = nullptr;
     const float* bias = nullptr;
     int in_binding = -1, out_binding = -1;
+    bool src_half = false;  // input cast: the binding is fp16
     int N = 0, C = 0, H = 0, W = 0, C_phys = 0, Ho = 0, Wo = 0, k = 0, stride = 0, pad = 0, K = 0, Cout = 0;
 };
 
@@ -330,13 +331,15 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
         b.tensor = r.tensor;
         b.nd = r.nd;
         if (r.nd == 0 || r.nd > 8) return fail(B2_EINVAL, "plan: binding %s has bad rank", b.name.c_str());
-        if (r.dtype != B2_DT_FLOAT) return fail(B2_EINVAL, "plan: binding %s: only fp32 bindings are supported", b.name.c_str());
+        // fp32 is the reference's binding contract; fp16 INPUT bindings are the secondary mode of fp16 engines
+        if (r.dtype != B2_DT_FLOAT && !(r.dtype == B2_DT_HALF && b.is_input && h.precision == B2_PREC_FP16))
+            return fail(B2_EINVAL, "plan: binding %s: bindings are fp32 (inputs of fp16 engines may be fp16)", b.name.c_str());
         size_t n = 1;
         for (uint32_t d = 0; d < 8; ++d) {
             b.dims[d] = d < r.nd ? r.dims[d] : 0;
             if (d < r.nd) n *= size_t(r.dims[d]);
         }
-        b.item_bytes = n * 4;
+        b.item_bytes = n * (r.dtype == B2_DT_HALF ? 2 : 4);
         e->bindings.push_back(b);
     }
     *payload = base + h.payload_offset;
@@ -820,6 +823,7 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                 const Tensor& t = e->tensors[r.out];
                 L.kind = L_INPUT_CAST;
                 L.in_binding = r.binding;
+                L.src_half = e->bindings[r.binding].dtype == B2_DT_HALF;
                 L.out = tptr(r.out);
                 L.C = t.c, L.H = t.h, L.W = t.w, L.C_phys = t.c_phys;
                 L.k = int(r.k);  // 2: horizontal space-to-depth (tensor is [H, W/2, 8]; binding is [C, H, W])
@@ -998,8 +1002,8 @@ int run_launch(const b2_engine* e, const Launch& L, void* const* bindings, cudaS
     void* out = L.out_binding >= 0 ? bindings[L.out_binding] : L.out;
     switch (L.kind) {
         case L_INPUT_CAST:
-            if (L.k == 2) return b2k::launch_input_cast_s2d(static_cast<const float*>(in), out, L.N, L.C, L.H, L.W, L.pad, L.stride, s);
-            return b2k::launch_input_cast(static_cast<const float*>(in), out, L.N, L.C, L.H, L.W, L.C_phys, half, s);
+            if (L.k == 2) return b2k::launch_input_cast_s2d(in, L.src_half, out, L.N, L.C, L.H, L.W, L.pad, L.stride, s);
+            return b2k::launch_input_cast(in, L.src_half, out, L.N, L.C, L.H, L.W, L.C_phys, half, s);
         case L_OUTPUT_CAST:
             return b2k::launch_output_cast(in, static_cast<float*>(out), L.N, L.C, L.H, L.W, L.C_phys, half, s);
         case L_CONV_TC:

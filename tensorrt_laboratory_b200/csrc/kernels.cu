@@ -1448,8 +1448,14 @@ int launch_conv_simt(const SimtConvArgs& a, bool half_storage, cudaStream_t stre
 
 // fp32 NCHW -> NHWC (channel-padded).  One thread per pixel: reads are coalesced per channel plane,
 // the write is one contiguous C_phys-element row.
-template <typename T>
-__global__ void input_cast_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int HW,
+__device__ __forceinline__ float ld_in(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_in(const __half* p) { return __half2float(__ldg(p)); }
+__device__ __forceinline__ float2 ld_in2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 ld_in2(const __half* p) { return __half22float2(__ldg(reinterpret_cast<const __half2*>(p))); }
+
+// S = element type of the input BINDING (fp32, or fp16 for plans built with input_dtype="f16")
+template <typename T, typename S>
+__global__ void input_cast_kernel(const S* __restrict__ src, T* __restrict__ dst, int N, int C, int HW,
                                   int C_phys) {
     pdl_launch_dependents();
     pdl_wait();
@@ -1457,23 +1463,24 @@ __global__ void input_cast_kernel(const float* __restrict__ src, T* __restrict__
     if (idx >= static_cast<long long>(N) * HW) return;
     const int n = static_cast<int>(idx / HW);
     const int px = static_cast<int>(idx - static_cast<long long>(n) * HW);
-    const float* s = src + static_cast<size_t>(n) * C * HW + px;
+    const S* s = src + static_cast<size_t>(n) * C * HW + px;
     T* d = dst + static_cast<size_t>(idx) * C_phys;
-    for (int c = 0; c < C_phys; ++c) d[c] = from_f<T>(c < C ? __ldg(s + static_cast<size_t>(c) * HW) : 0.0f);
+    for (int c = 0; c < C_phys; ++c) d[c] = from_f<T>(c < C ? ld_in(s + static_cast<size_t>(c) * HW) : 0.0f);
 }
 
 // specialisation used by the fp16 path when C_phys == 8: one 16-byte store per pixel
-__global__ void input_cast_c8_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int N, int C, int HW) {
+template <typename S>
+__global__ void input_cast_c8_kernel(const S* __restrict__ src, uint4* __restrict__ dst, int N, int C, int HW) {
     pdl_launch_dependents();
     pdl_wait();
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= static_cast<long long>(N) * HW) return;
     const int n = static_cast<int>(idx / HW);
     const int px = static_cast<int>(idx - static_cast<long long>(n) * HW);
-    const float* s = src + static_cast<size_t>(n) * C * HW + px;
+    const S* s = src + static_cast<size_t>(n) * C * HW + px;
     float f[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) f[c] = c < C ? __ldg(s + static_cast<size_t>(c) * HW) : 0.0f;
+    for (int c = 0; c < 8; ++c) f[c] = c < C ? ld_in(s + static_cast<size_t>(c) * HW) : 0.0f;
     uint4 o;
     __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
@@ -1481,23 +1488,30 @@ __global__ void input_cast_c8_kernel(const float* __restrict__ src, uint4* __res
     dst[idx] = o;
 }
 
-int launch_input_cast(const float* src, void* dst, int N, int C, int H, int W, int C_phys, bool half_storage,
-                      cudaStream_t stream) {
+template <typename S>
+static int launch_input_cast_t(const S* src, void* dst, int N, int C, int H, int W, int C_phys, bool half_storage,
+                               cudaStream_t stream) {
     const long long total = static_cast<long long>(N) * H * W;
     const int threads = 256;
     const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
     if (half_storage && C_phys == 8 && C <= 8)
-        B2_LAUNCH_RC = launch_kernel(input_cast_c8_kernel, dim3(blocks), dim3(threads), 0, stream, false, src, reinterpret_cast<uint4*>(dst), N, C, H * W);
+        B2_LAUNCH_RC = launch_kernel(input_cast_c8_kernel<S>, dim3(blocks), dim3(threads), 0, stream, false, src, reinterpret_cast<uint4*>(dst), N, C, H * W);
     else if (half_storage)
-        B2_LAUNCH_RC = launch_kernel(input_cast_kernel<__half>, dim3(blocks), dim3(threads), 0, stream, false, src, reinterpret_cast<__half*>(dst), N, C, H * W, C_phys);
+        B2_LAUNCH_RC = launch_kernel(input_cast_kernel<__half, S>, dim3(blocks), dim3(threads), 0, stream, false, src, reinterpret_cast<__half*>(dst), N, C, H * W, C_phys);
     else
-        B2_LAUNCH_RC = launch_kernel(input_cast_kernel<float>, dim3(blocks), dim3(threads), 0, stream, false, src, reinterpret_cast<float*>(dst), N, C, H * W, C_phys);
+        B2_LAUNCH_RC = launch_kernel(input_cast_kernel<float, S>, dim3(blocks), dim3(threads), 0, stream, false, src, reinterpret_cast<float*>(dst), N, C, H * W, C_phys);
     return B2_LAUNCH_RC;
+}
+int launch_input_cast(const void* src, bool src_half, void* dst, int N, int C, int H, int W, int C_phys, bool half_storage,
+                      cudaStream_t stream) {
+    if (src_half) return launch_input_cast_t(static_cast<const __half*>(src), dst, N, C, H, W, C_phys, half_storage, stream);
+    return launch_input_cast_t(static_cast<const float*>(src), dst, N, C, H, W, C_phys, half_storage, stream);
 }
 
 // fp32 NCHW -> fp16 [N, H, pad_l + W/2 + pad_r, 8], channel = dw*4 + c: one 16-byte store per PAIR of input pixels;
 // the pad_l / pad_r border pixels are written as zeros (the stem's horizontal padding made physical)
-__global__ void input_cast_s2d_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int N, int C, int H, int W,
+template <typename S>
+__global__ void input_cast_s2d_kernel(const S* __restrict__ src, uint4* __restrict__ dst, int N, int C, int H, int W,
                                       int pad_l, int pad_r) {
     pdl_launch_dependents();
     pdl_wait();
@@ -1512,12 +1526,12 @@ __global__ void input_cast_s2d_kernel(const float* __restrict__ src, uint4* __re
     const int w2 = wp - pad_l;
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
     if (w2 >= 0 && w2 < W2) {
-        const float* s = src + (static_cast<size_t>(n) * C * H + h) * W + 2 * w2;
+        const S* s = src + (static_cast<size_t>(n) * C * H + h) * W + 2 * w2;
         float f[8];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             float2 v = make_float2(0.f, 0.f);
-            if (c < C) v = __ldg(reinterpret_cast<const float2*>(s + static_cast<size_t>(c) * H * W));
+            if (c < C) v = ld_in2(s + static_cast<size_t>(c) * H * W);
             f[c] = v.x;
             f[4 + c] = v.y;
         }
@@ -1528,12 +1542,17 @@ __global__ void input_cast_s2d_kernel(const float* __restrict__ src, uint4* __re
     dst[idx] = o;
 }
 
-int launch_input_cast_s2d(const float* src, void* dst, int N, int C, int H, int W, int pad_l, int pad_r, cudaStream_t stream) {
+int launch_input_cast_s2d(const void* src, bool src_half, void* dst, int N, int C, int H, int W, int pad_l, int pad_r,
+                          cudaStream_t stream) {
     const long long total = static_cast<long long>(N) * H * (W / 2 + pad_l + pad_r);
     const int threads = 256;
     const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
-    B2_LAUNCH_RC = launch_kernel(input_cast_s2d_kernel, dim3(blocks), dim3(threads), 0, stream, false, src,
-                                 reinterpret_cast<uint4*>(dst), N, C, H, W, pad_l, pad_r);
+    if (src_half)
+        B2_LAUNCH_RC = launch_kernel(input_cast_s2d_kernel<__half>, dim3(blocks), dim3(threads), 0, stream, false,
+                                     static_cast<const __half*>(src), reinterpret_cast<uint4*>(dst), N, C, H, W, pad_l, pad_r);
+    else
+        B2_LAUNCH_RC = launch_kernel(input_cast_s2d_kernel<float>, dim3(blocks), dim3(threads), 0, stream, false,
+                                     static_cast<const float*>(src), reinterpret_cast<uint4*>(dst), N, C, H, W, pad_l, pad_r);
     return B2_LAUNCH_RC;
 }
 

@@ -92,11 +92,13 @@ struct SimtConvArgs {
 int launch_conv_simt(const SimtConvArgs& a, bool half_storage, cudaStream_t stream);
 
 // fp32 NCHW binding -> NHWC activations (zero-filled channel padding)
-int launch_input_cast(const float* src, void* dst, int N, int C, int H, int W, int C_phys,
+// (`src_half`: the binding holds fp16 instead of fp32 -- plans built with input_dtype="f16")
+int launch_input_cast(const void* src, bool src_half, void* dst, int N, int C, int H, int W, int C_phys,
                       bool half_storage, cudaStream_t stream);
 // fp32 NCHW binding -> fp16 [N, H, pad_l + W/2 + pad_r, 8] with channel = dw*4 + c (horizontal space-to-depth, C <= 4;
 // border pixels zero)
-int launch_input_cast_s2d(const float* src, void* dst, int N, int C, int H, int W, int pad_l, int pad_r, cudaStream_t stream);
+int launch_input_cast_s2d(const void* src, bool src_half, void* dst, int N, int C, int H, int W, int pad_l, int pad_r,
+                          cudaStream_t stream);
 // NHWC activations -> fp32 NCHW binding
 int launch_output_cast(const void* src, float* dst, int N, int C, int H, int W, int C_phys,
                        bool half_storage, cudaStream_t stream);

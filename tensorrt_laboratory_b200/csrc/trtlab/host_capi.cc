@@ -75,7 +75,7 @@ int trt_manager_allocate(trt_manager* m) {
     TRT_CATCH
 }
 
-int trt_manager_infer(trt_manager* m, const char* model_name, int batch, const float* input, size_t input_bytes,
+int trt_manager_infer(trt_manager* m, const char* model_name, int batch, const void* input, size_t input_bytes,
                       float* output, size_t output_bytes, double* compute_seconds) {
     if (!m || !model_name || !input || !output) return fail(B2_EINVAL, "bad arguments");
     TRT_TRY
@@ -105,7 +105,7 @@ int trt_manager_infer(trt_manager* m, const char* model_name, int batch, const f
 
 // Give every pooled Buffers a distinct input batch in its pinned host stack.  Bindings are bump-allocated
 // from a stack that is Reset() on return, so the addresses (and contents) persist across requests.
-int trt_manager_prefill_inputs(trt_manager* m, const char* model_name, const float* ring, size_t ring_batches) {
+int trt_manager_prefill_inputs(trt_manager* m, const char* model_name, const void* ring, size_t ring_batches) {
     if (!m || !model_name || !ring || ring_batches == 0) return fail(B2_EINVAL, "bad arguments");
     TRT_TRY
     auto model = m->mgr->GetModel(model_name);
@@ -170,7 +170,7 @@ int trt_timed_pipeline(const void* blob, size_t nbytes, int iters, float* h2d_ms
 // a device ring (sized by the caller to exceed L2), `steps` forward passes issued round-robin, timed with
 // CUDA events from the first launch to the completion of the last stream.
 int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int batch, int steps, int warmup,
-                          const float* host_ring, int ring_batches, double* elapsed_ms, int* launches_per_step) {
+                          const void* host_ring, int ring_batches, double* elapsed_ms, int* launches_per_step) {
     if (!blob || contexts < 1 || steps < 1 || !host_ring || ring_batches < 1 || !elapsed_ms) return fail(B2_EINVAL, "bad arguments");
     b2_runtime* rt = nullptr;
     b2_engine* eng = nullptr;
@@ -188,7 +188,7 @@ int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int bat
         int32_t dims[8];
         int nd = 0;
         b2_engine_binding_dims(eng, i, dims, &nd);
-        size_t n = 4;
+        size_t n = b2_engine_binding_dtype(eng, i) == B2_DT_HALF ? 2 : 4;
         for (int d = 0; d < nd; ++d) n *= size_t(dims[d]);
         bytes[i] = n * size_t(b2_engine_max_batch(eng));
         if (b2_engine_binding_is_input(eng, i)) in_id = i;
@@ -232,6 +232,12 @@ int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int bat
     }
     // B2_PROBE_STAGGER=1: de-phase the streams (stream k first runs one forward pass of a smaller batch), the way
     // independently arriving requests meet each other; without it all contexts march through the layers in lockstep.
+    const int tiny_h2d = getenv("B2_PROBE_TINY_H2D") ? atoi(getenv("B2_PROBE_TINY_H2D")) : 0;
+    void *tiny_dev = nullptr, *tiny_host = nullptr;
+    if (tiny_h2d > 0) {
+        cuda_ok(cudaMalloc(&tiny_dev, size_t(tiny_h2d)), "cudaMalloc probe");
+        cuda_ok(cudaMallocHost(&tiny_host, size_t(tiny_h2d)), "cudaMallocHost probe");
+    }
     const bool stagger = getenv("B2_PROBE_STAGGER") && atoi(getenv("B2_PROBE_STAGGER")) > 0;
     auto issue = [&](int n_steps, int offset) {
         for (int k = 1; stagger && k < contexts && status == B2_OK; ++k) {
@@ -242,6 +248,9 @@ int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int bat
         for (int i = 0; i < n_steps && status == B2_OK; ++i) {
             Ctx& x = ctx[size_t(i % contexts)];
             x.bind[in_id] = ring[size_t((i + offset) % ring_batches)];
+            // B2_PROBE_TINY_H2D=n: a n-byte pinned->device copy ahead of every forward pass (diagnostic: the cost of a
+            // copy-engine -> compute dependency in front of the graph launch, without the PCIe traffic of a real input)
+            if (tiny_h2d > 0) cudaMemcpyAsync(tiny_dev, tiny_host, size_t(tiny_h2d), cudaMemcpyHostToDevice, x.s);
             status = b2_context_enqueue(x.c, batch, x.bind.data(), x.s, nullptr);
         }
     };
@@ -262,8 +271,9 @@ int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int bat
             cudaStream_t s = nullptr;
             if (cudaMallocHost(&h, in_bytes) == cudaSuccess && cudaMalloc(&d, in_bytes) == cudaSuccess &&
                 cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) {
+                const int burst = atoi(getenv("B2_PROBE_BG_H2D"));  // copies queued per host synchronisation
                 while (!bg_stop.load()) {
-                    cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s);
+                    for (int k = 0; k < burst; ++k) cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s);
                     cudaStreamSynchronize(s);
                 }
             }
@@ -289,6 +299,8 @@ int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int bat
     bg_stop = true;
     if (bg.joinable()) bg.join();
     cudaDeviceSynchronize();
+    if (tiny_dev) cudaFree(tiny_dev);
+    if (tiny_host) cudaFreeHost(tiny_host);
     for (auto& x : ctx) {
         if (x.c) b2_context_destroy(x.c);
         if (x.scratch) cudaFree(x.scratch);

@@ -150,3 +150,21 @@ def test_cpp_core_unit_tests(tmp_path):
                     os.path.join(ROOT, "tests", "cpp", "test_core.cc"), "-o", str(exe), "-lpthread"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stderr
+
+
+def test_fp16_input_binding_is_recorded_in_the_plan():
+    """Secondary mode of SURVEY.md 8(d): the input binding of an fp16 engine may be declared fp16."""
+    import struct
+    net = builder.single_conv_net(64, 8, 8, 64, 1, 1, 0)
+    from tensorrt_laboratory_b200 import graph, weights
+    low = graph.lower(net, weights.random_weights(net, 0))
+    blob32 = builder.build_plan(low, builder.PREC_FP16, 2)
+    blob16 = builder.build_plan(low, builder.PREC_FP16, 2, input_dtype="f16")
+    assert len(blob32) == len(blob16)
+    diff = [i for i in range(len(blob32)) if blob32[i] != blob16[i]]
+    assert len(diff) == 1  # exactly the dtype field of the input binding record
+    assert blob32[diff[0]] == 0 and blob16[diff[0]] == 1
+    with pytest.raises(ValueError):
+        builder.build_plan(low, builder.PREC_FP32, 2, input_dtype="f16")
+    with pytest.raises(ValueError):
+        builder.build_plan(low, builder.PREC_FP16, 2, input_dtype="int8")

@@ -131,6 +131,31 @@ def test_inference_manager_pipeline_matches_direct_path(rn50, rn50_session):
         mgr.close()
 
 
+def test_fp16_input_binding_matches_fp32_binding(rn50, rn50_session):
+    """Secondary mode: the input binding declared fp16.  The engine rounds fp32 inputs to fp16 in its first kernel anyway,
+    so feeding the pre-rounded values through an fp16 binding gives bit-identical results -- via the bare C ABI and via
+    the InferenceManager pipeline (pinned Buffers sized by the binding dtype)."""
+    direct = rn50_session["sess"].infer(rn50["x"])["prob"]
+    blob = builder.build_resnet_plan(50, builder.PREC_FP16, 8, input_dtype="f16")
+    eng = capi.Engine(blob)
+    assert [b["dtype"] for b in eng.bindings if b["is_input"]] == [1]
+    assert [b["item_bytes"] for b in eng.bindings if b["is_input"]] == [3 * 224 * 224 * 2]
+    sess = capi.Session(eng)
+    try:
+        np.testing.assert_array_equal(sess.infer(rn50["x"])["prob"], direct)
+        np.testing.assert_array_equal(sess.infer(rn50["x"][:3])["prob"], direct[:3])
+    finally:
+        sess.close()
+        eng.destroy()
+    mgr = capi.InferenceManager(max_exec_concurrency=2, max_copy_concurrency=4)
+    try:
+        mgr.register_model("rn50h", blob)
+        mgr.update_resources()
+        np.testing.assert_array_equal(mgr.infer("rn50h", rn50["x"]), direct)
+    finally:
+        mgr.close()
+
+
 def test_timed_benchmark_workspace(rn50_session):
     t = capi.timed_pipeline(rn50_session["blob"], iters=5)
     assert t["h2d_ms"] > 0 and t["compute_ms"] > 0 and t["d2h_ms"] > 0

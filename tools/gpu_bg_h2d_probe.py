@@ -10,9 +10,8 @@ from tensorrt_laboratory_b200 import builder, capi, weights  # noqa: E402
 
 blob = builder.build_resnet_plan(50, builder.PREC_FP16, 8)
 ring = weights.synthetic_input(8, ring=8)
-for bg, st in (("0", "0"), ("0", "1"), ("1", "1"), ("0", "0"), ("0", "1")):
+os.environ["B2_PROBE_TINY_H2D"] = "0"
+for bg in ("0", "1", "64", "0", "64"):
     os.environ["B2_PROBE_BG_H2D"] = bg
-    os.environ["B2_PROBE_STAGGER"] = st
-    for n in (2, 3, 4):
-        ms, _ = capi.device_throughput(blob, n, 8, 800, 20, ring)
-        print(json.dumps({"bg_h2d": bg, "stagger": st, "contexts": n, "img_s": round(800 * 8 / (ms * 1e-3))}), flush=True)
+    ms, _ = capi.device_throughput(blob, 4, 8, 1600, 20, ring)
+    print(json.dumps({"background_h2d_burst": bg, "contexts": 4, "img_s": round(1600 * 8 / (ms * 1e-3))}), flush=True)
