@@ -13,6 +13,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <cstring>
 #include <functional>
 #include <future>
 #include <map>
@@ -22,6 +23,7 @@
 
 #include "b200cuda.h"
 #include "b200infer.h"
+#include "trtlab/core/batcher.h"
 #include "trtlab/core/hotpath_core.h"
 
 // CUDA handle aliases: when the CUDA runtime header is present use its types, otherwise opaque pointers
@@ -517,6 +519,74 @@ enum InferBenchKey {
     kLatencyP99,
     kLatencyMax,
     kGpuComputeTimePerBatch  // mean device time of one forward pass (start/done events of its ExecutionContext)
+};
+
+// ------------------------------------------------------------------------------------------------
+// BatchedInferRunner -- dynamic batching in front of the hot path (host part): single requests of
+// 1..k images are merged by a Dispatcher<StandardBatcher> until the model's max batch is reached or the batching
+// window expires, then travel as ONE request through InferRunner (pinned H2D -> forward -> D2H) and are scattered back.
+// Same roles as the reference's batching service (examples/03_Batching/inference-batcher.cc:298-366: window 2000 us,
+// max batch from the model), with the engine instead of a TRTIS round trip behind it.  Single-input single-output models.
+// ------------------------------------------------------------------------------------------------
+class BatchedInferRunner {
+  public:
+    struct Request {
+        const void* input;  // `items` batch items in the input binding's dtype/layout; valid until the future is ready
+        void* output;       // room for `items` output items
+        uint32_t items;
+    };
+    using future_type = std::shared_future<void>;
+
+    BatchedInferRunner(std::shared_ptr<Model> model, std::shared_ptr<InferenceManager> resources,
+                       std::chrono::nanoseconds window = std::chrono::microseconds(2000), size_t workers = 2)
+        : m_Model(std::move(model)), m_Resources(std::move(resources)), m_Batches(std::make_shared<std::atomic<size_t>>(0)) {
+        TRTLAB_CHECK(m_Model->GetInputBindingIds().size() == 1 && m_Model->GetOutputBindingIds().size() == 1)
+            << "BatchedInferRunner handles single-input single-output models";
+        auto model_ = m_Model;
+        auto res = m_Resources;
+        auto batches = m_Batches;
+        auto execute = [model_, res, batches](const std::vector<Request>& reqs, std::function<void()> release) {
+            res->ActivateDevice();
+            const uint32_t in_id = model_->GetInputBindingIds()[0], out_id = model_->GetOutputBindingIds()[0];
+            const size_t in_item = model_->GetBinding(in_id).bytesPerBatchItem, out_item = model_->GetBinding(out_id).bytesPerBatchItem;
+            auto buffers = res->GetBuffers();
+            auto bindings = buffers->CreateBindings(model_);
+            buffers.reset();
+            uint32_t total = 0;
+            for (const auto& r : reqs) {
+                memcpy(static_cast<char*>(bindings->HostAddress(in_id)) + size_t(total) * in_item, r.input, size_t(r.items) * in_item);
+                total += r.items;
+            }
+            bindings->SetBatchSize(total);
+            InferRunner runner(model_, res);
+            auto done = runner.Infer(bindings, [&reqs, out_id, out_item](std::shared_ptr<Bindings>& b) {
+                uint32_t at = 0;
+                for (const auto& r : reqs) {
+                    memcpy(r.output, static_cast<const char*>(b->HostAddress(out_id)) + size_t(at) * out_item, size_t(r.items) * out_item);
+                    at += r.items;
+                }
+                b.reset();
+            });
+            done.wait();  // `reqs` lives in the batch, which the dispatcher keeps alive until this function returns
+            batches->fetch_add(1);
+            release();
+        };
+        // every request carries one batch item, so "max requests per batch" == the model's max batch size
+        m_Dispatcher = std::make_unique<DispatcherType>(StandardBatcher<Request, standard_threads>(size_t(m_Model->GetMaxBatchSize())),
+                                                        window, std::make_shared<ThreadPool>(workers),
+                                                        std::make_shared<DeferredShortTaskPool>(), execute);
+    }
+    // one single-item request (the common case: one image per RPC)
+    future_type Infer(const void* input, void* output) { return m_Dispatcher->enqueue(Request{input, output, 1}); }
+    size_t BatchesExecuted() const { return m_Batches->load(); }
+    void Shutdown() { m_Dispatcher->shutdown(); }
+
+  private:
+    using DispatcherType = Dispatcher<StandardBatcher<Request, standard_threads>>;
+    std::shared_ptr<Model> m_Model;
+    std::shared_ptr<InferenceManager> m_Resources;
+    std::shared_ptr<std::atomic<size_t>> m_Batches;
+    std::unique_ptr<DispatcherType> m_Dispatcher;
 };
 
 class InferBench {

@@ -26,6 +26,10 @@ int trt_manager_allocate(trt_manager* m); /* InferenceManager::AllocateResources
 /* one request through InferRunner::Infer(pre, post): pinned H2D -> forward -> D2H, blocking */
 int trt_manager_infer(trt_manager* m, const char* model, int batch, const void* input, size_t input_bytes,
                       float* output, size_t output_bytes, double* compute_seconds);
+/* `n` single-image requests through BatchedInferRunner (Dispatcher<StandardBatcher>, window_us): inputs/outputs are
+ * contiguous [n][item]; *batches_executed = number of merged forward passes it took */
+int trt_manager_infer_batched(trt_manager* m, const char* model, int n, const void* inputs, void* outputs, int window_us,
+                              int* batches_executed);
 /* write a distinct batch from `ring` into the pinned input region of every pooled Buffers */
 int trt_manager_prefill_inputs(trt_manager* m, const char* model, const void* ring, size_t ring_batches);
 /* InferBench::Run closed loop; results16[InferBenchKey]; optional per-request latencies (seconds) */

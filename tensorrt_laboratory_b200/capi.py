@@ -85,6 +85,7 @@ SYMBOLS = [
     ("trt_manager_register_model", _I, [_VP, _S, _VP, _SZ, _I]),
     ("trt_manager_allocate", _I, [_VP]),
     ("trt_manager_infer", _I, [_VP, _S, _I, _VP, _SZ, _VP, _SZ, C.POINTER(_D)]),
+    ("trt_manager_infer_batched", _I, [_VP, _S, _I, _VP, _VP, _I, C.POINTER(_I)]),
     ("trt_manager_prefill_inputs", _I, [_VP, _S, _VP, _SZ]),
     ("trt_manager_bench", _I, [_VP, _S, _I, _D, _SZ, C.POINTER(_D), C.POINTER(_D), _SZ, C.POINTER(_SZ)]),
     ("trt_timed_pipeline", _I, [_VP, _SZ, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -428,6 +429,17 @@ class InferenceManager:
         check(self._lib.trt_manager_infer(self.handle, name.encode(), batch, x.ctypes.data, x.nbytes,
                                           out.ctypes.data, out.nbytes, None))
         return out
+
+    def infer_batched(self, name: str, x: np.ndarray, window_us: int = 2000):
+        """Every image of ``x`` as its own request through BatchedInferRunner -> (outputs [n, ...], merged forward passes)."""
+        meta = self.models[name]
+        x = np.ascontiguousarray(x, dtype=[b["np_dtype"] for b in meta.bindings if b["is_input"]][0])
+        ob = [b for b in meta.bindings if not b["is_input"]][0]
+        out = np.empty((x.shape[0],) + ob["shape"], dtype=np.float32)
+        nb = _I(0)
+        check(self._lib.trt_manager_infer_batched(self.handle, name.encode(), x.shape[0], x.ctypes.data, out.ctypes.data,
+                                                  window_us, C.byref(nb)))
+        return out, nb.value
 
     def prefill_inputs(self, name: str, ring: np.ndarray):
         ring = np.ascontiguousarray(ring, dtype=[b["np_dtype"] for b in self.models[name].bindings if b["is_input"]][0])

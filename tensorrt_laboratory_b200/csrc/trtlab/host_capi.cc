@@ -103,6 +103,24 @@ int trt_manager_infer(trt_manager* m, const char* model_name, int batch, const v
     TRT_CATCH
 }
 
+int trt_manager_infer_batched(trt_manager* m, const char* model_name, int n, const void* inputs, void* outputs, int window_us,
+                              int* batches_executed) {
+    if (!m || !model_name || n < 1 || !inputs || !outputs) return fail(B2_EINVAL, "bad arguments");
+    TRT_TRY
+    auto model = m->mgr->GetModel(model_name);
+    const size_t in_item = model->GetBinding(model->GetInputBindingIds()[0]).bytesPerBatchItem;
+    const size_t out_item = model->GetBinding(model->GetOutputBindingIds()[0]).bytesPerBatchItem;
+    BatchedInferRunner runner(model, m->mgr, std::chrono::microseconds(window_us > 0 ? window_us : 2000));
+    std::vector<BatchedInferRunner::future_type> futures;
+    for (int i = 0; i < n; ++i)
+        futures.push_back(runner.Infer(static_cast<const char*>(inputs) + size_t(i) * in_item, static_cast<char*>(outputs) + size_t(i) * out_item));
+    for (auto& f : futures) f.get();
+    runner.Shutdown();
+    if (batches_executed) *batches_executed = int(runner.BatchesExecuted());
+    return B2_OK;
+    TRT_CATCH
+}
+
 // Give every pooled Buffers a distinct input batch in its pinned host stack.  Bindings are bump-allocated
 // from a stack that is Reset() on return, so the addresses (and contents) persist across requests.
 int trt_manager_prefill_inputs(trt_manager* m, const char* model_name, const void* ring, size_t ring_batches) {

@@ -8,7 +8,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <vector>
 
+#include "trtlab/core/batcher.h"
 #include "trtlab/core/hotpath_core.h"
 
 using namespace trtlab;
@@ -167,6 +169,117 @@ static void test_cyclic_allocator() {
     std::memset(survivor.get(), 0xab, 128);
 }
 
+// StandardBatcher / Dispatcher / DeferredShortTaskPool (cases of trtlab/core/tests/test_batcher.cc)
+static void test_standard_batcher() {
+    StandardBatcher<int, standard_threads> batcher(5);
+    for (int i = 0; i < 9; i++) {
+        auto f = batcher.enqueue(i);
+        auto batch = batcher.update();
+        if (i == 4) {
+            EXPECT(batch.has_value());
+            EXPECT(batch->items.size() == 5 && batch->batch_id == 0);
+            EXPECT(f.wait_for(std::chrono::seconds(0)) == std::future_status::timeout);
+            batch->promise.set_value();
+            EXPECT(f.wait_for(std::chrono::seconds(0)) == std::future_status::ready);
+        } else {
+            EXPECT(!batch.has_value());
+        }
+    }
+    EXPECT(!batcher.update().has_value());
+    auto rest = batcher.close_batch();
+    EXPECT(rest.has_value() && rest->items.size() == 4 && rest->batch_id == 1);
+    EXPECT(batcher.empty() && !batcher.close_batch().has_value());
+}
+
+static void test_deferred_task_pool() {
+    using namespace std::chrono_literals;
+    using clock = std::chrono::high_resolution_clock;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int> order;
+    DeferredShortTaskPool pool;
+    auto start = clock::now();
+    auto push = [&](int ms) {
+        pool.enqueue_deferred(start + std::chrono::milliseconds(ms), [&, ms] {
+            {
+                std::lock_guard<std::mutex> l(mu);
+                order.push_back(ms);
+            }
+            cv.notify_one();
+        });
+    };
+    push(25), push(5), push(10);
+    {
+        std::unique_lock<std::mutex> l(mu);
+        EXPECT(order.empty());
+        cv.wait(l, [&] { return order.size() == 3; });
+    }
+    EXPECT(order[0] == 5 && order[1] == 10 && order[2] == 25);  // by deadline, not by submission
+    const auto wall = std::chrono::duration_cast<std::chrono::milliseconds>(clock::now() - start).count();
+    EXPECT(wall >= 25 && wall < 60);
+    pool.shutdown();
+    bool threw = false;
+    try {
+        pool.enqueue_deferred(clock::now() + 3ms, [] {});
+    } catch (const std::runtime_error&) {
+        threw = true;
+    }
+    EXPECT(threw);
+}
+
+static void test_dispatcher_full_batch_and_window() {
+    using namespace std::chrono_literals;
+    std::mutex mu;
+    std::vector<size_t> sizes;
+    auto execute = [&](const std::vector<int>& batch, std::function<void()> release) {
+        {
+            std::lock_guard<std::mutex> l(mu);
+            sizes.push_back(batch.size());
+        }
+        std::this_thread::sleep_for(2ms);
+        release();
+    };
+    auto workers = std::make_shared<ThreadPool>(1);
+    auto timers = std::make_shared<DeferredShortTaskPool>();
+    StandardBatcher<int, standard_threads> batcher(5);
+    Dispatcher<decltype(batcher)> dispatcher(std::move(batcher), 15ms, workers, timers, execute);
+    std::vector<std::shared_future<void>> futures;
+    for (int i = 0; i < 9; i++) futures.push_back(dispatcher.enqueue(i));
+    for (int i = 0; i < 5; i++) futures[i].wait();                                        // the full batch ran at once
+    EXPECT(futures[5].wait_for(0s) == std::future_status::timeout);                       // the rest waits for the window
+    EXPECT(futures[5].wait_for(200ms) == std::future_status::ready);                      // ... which closes it
+    for (auto& f : futures) f.wait();
+    {
+        std::lock_guard<std::mutex> l(mu);
+        EXPECT(sizes.size() == 2 && sizes[0] == 5 && sizes[1] == 4);
+    }
+    // shutdown flushes an open batch without waiting for its window and refuses new items
+    auto late = dispatcher.enqueue(42);
+    dispatcher.shutdown();
+    EXPECT(late.wait_for(0s) == std::future_status::ready);
+    bool threw = false;
+    try {
+        dispatcher.enqueue(43);
+    } catch (const std::runtime_error&) {
+        threw = true;
+    }
+    EXPECT(threw);
+    // an exception in the user function reaches the callers of that batch
+    StandardBatcher<int, standard_threads> b2(2);
+    Dispatcher<decltype(b2)> failing(std::move(b2), 5ms, workers, timers,
+                                      [](const std::vector<int>&, std::function<void()>) { throw std::runtime_error("boom"); });
+    auto f0 = failing.enqueue(1);
+    auto f1 = failing.enqueue(2);
+    bool got = false;
+    try {
+        f1.get();
+    } catch (const std::runtime_error&) {
+        got = true;
+    }
+    EXPECT(got);
+    (void)f0;
+}
+
 static void test_bytes() {
     EXPECT(BytesToString(512) == "512 B");
     EXPECT(BytesToString(1536) == "1.5 KiB");
@@ -190,6 +303,9 @@ int main() {
     test_async_compute();
     test_bytes();
     test_cyclic_allocator();
+    test_standard_batcher();
+    test_deferred_task_pool();
+    test_dispatcher_full_batch_and_window();
     std::printf("ALL OK\n");
     return 0;
 }

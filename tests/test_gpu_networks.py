@@ -156,6 +156,23 @@ def test_fp16_input_binding_matches_fp32_binding(rn50, rn50_session):
         mgr.close()
 
 
+def test_dynamic_batching_runner(rn50, rn50_session):
+    """BatchedInferRunner: 13 single-image requests -> one full batch of 8 + one window-closed batch of 5; every image's
+    result is bit-identical to the direct batch-8 path (results do not depend on the batch an image travels in)."""
+    x = np.concatenate([rn50["x"], rn50["x"][:5]], axis=0)
+    direct = rn50_session["sess"].infer(rn50["x"])["prob"]
+    want = np.concatenate([direct, direct[:5]], axis=0)
+    mgr = capi.InferenceManager(max_exec_concurrency=2, max_copy_concurrency=4)
+    try:
+        mgr.register_model("rn50", rn50_session["blob"])
+        mgr.update_resources()
+        got, batches = mgr.infer_batched("rn50", x, window_us=20000)
+        assert batches == 2
+        np.testing.assert_array_equal(got, want)
+    finally:
+        mgr.close()
+
+
 def test_timed_benchmark_workspace(rn50_session):
     t = capi.timed_pipeline(rn50_session["blob"], iters=5)
     assert t["h2d_ms"] > 0 and t["compute_ms"] > 0 and t["d2h_ms"] > 0
