@@ -103,6 +103,9 @@ struct Tensor {
 struct Op {
     b2plan::OpRec r;
     std::string name;
+    // >= 0: this op's only consumer is the residual input of op `side_join`, and nothing in between depends on it (the
+    // shortcut convolution of a ResNet "a" block): it may run on a forked stream, concurrently with the ops up to there
+    int side_join = -1;
     // conv geometry with the "0 = square" defaults resolved
     int kh() const { return int(r.k); }
     int kw() const { return int(r.kw ? r.kw : r.k); }
@@ -138,6 +141,7 @@ struct Launch {
     const float* bias = nullptr;
     int in_binding = -1, out_binding = -1;
     bool src_half = false;  // input cast: the binding is fp16
+    int side_join = -1;     // see Op::side_join (launch index == op index)
     int N = 0, C = 0, H = 0, W = 0, C_phys = 0, Ho = 0, Wo = 0, k = 0, stride = 0, pad = 0, K = 0, Cout = 0;
 };
 
@@ -234,6 +238,11 @@ struct b2_context {
     int no_pack = 0;    // reserved (packed plans cannot fall back to the tensor-map weight path)
     int no_fold = 0;    // 1: run the stem through the generic 8-channel tap path instead of the row-folded one
     int autotune = 4;  // 0 off (cost model), 1 latency mode, N>=2 throughput mode over N streams
+    int fork = 0;      // 1: run side branches (Op::side_join) on a forked stream / a parallel graph branch.  Off by default:
+                       // measured neutral on B200 (0.476 ms either way, 4-context throughput within noise) -- the fork and
+                       // join turn the programmatic (PDL) edges around them into full dependencies, which eats the overlap
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
 };
 
 namespace {
@@ -348,11 +357,32 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
 
 // ---- activation arena: first-fit over live intervals ------------------------------------------
 void plan_arena(b2_engine* e) {
+    // side branches: a conv whose output is consumed exactly once, as the residual of a later op, with at least one
+    // independent op in between.  Regions do not nest or overlap.
+    int busy_until = -1;
+    for (size_t i = 0; i < e->ops.size(); ++i) {
+        Op& op = e->ops[i];
+        op.side_join = -1;
+        if (int(i) <= busy_until || op.r.type != b2plan::OP_CONV || op.r.out < 0 || e->tensors[op.r.out].binding >= 0) continue;
+        int consumers = 0, join = -1;
+        bool as_residual_only = true;
+        for (size_t k = i + 1; k < e->ops.size(); ++k) {
+            const auto& rk = e->ops[k].r;
+            if (rk.in == op.r.out) ++consumers, as_residual_only = false;
+            if (rk.res == op.r.out) ++consumers, join = int(k);
+        }
+        if (consumers == 1 && as_residual_only && join > int(i) + 1) {
+            op.side_join = join;
+            busy_until = join;
+        }
+    }
     for (size_t i = 0; i < e->ops.size(); ++i) {
         const auto& r = e->ops[i].r;
         if (r.out >= 0 && e->tensors[r.out].def < 0) e->tensors[r.out].def = int(i);
         for (int t : {r.in, r.res})
             if (t >= 0) e->tensors[t].last_use = std::max(e->tensors[t].last_use, int(i));
+        // a side op may still be READING its input while the ops before the join run: keep that buffer until the join
+        if (e->ops[i].side_join >= 0 && r.in >= 0) e->tensors[r.in].last_use = std::max(e->tensors[r.in].last_use, e->ops[i].side_join);
     }
     struct Live {
         size_t off, size;
@@ -818,6 +848,7 @@ int build_plan(b2_context* c, int batch, Plan** out) {
         Launch L;
         L.name = op.name;
         L.N = batch;
+        L.side_join = op.side_join;
         switch (r.type) {
             case b2plan::OP_INPUT_CAST: {
                 const Tensor& t = e->tensors[r.out];
@@ -898,8 +929,11 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                         if (!have) {
                             // The split-K factor fixes the fp32 summation order, so it is chosen ONCE, at max batch,
                             // and reused for every batch size: an image's result does not depend on its batch.
-                            int splits = 0, halo = -1;
-                            if (batch != e->max_batch) {
+                            // (a side-branch op runs concurrently with its neighbours and must not share the split-K
+                            // workspace / arrival counters with them: it never splits)
+                            const bool side = op.side_join >= 0;
+                            int splits = side ? 1 : 0, halo = -1;
+                            if (batch != e->max_batch && !side) {
                                 ConvConfig top = cfg;
                                 bool have_top = false;
                                 {
@@ -923,6 +957,7 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                             tune_cache_append(e, op_index, batch, cfg);
                         }
                     }
+                    if (op.side_join >= 0 && cfg.splits > 1) cfg.splits = 1;  // forced / cached tactic on a side-branch op
                     int rc = make_conv_launch(c, op, batch, cfg, &L.conv);
                     if (rc) return rc;
                 } else {
@@ -1022,12 +1057,42 @@ int run_launch(const b2_engine* e, const Launch& L, void* const* bindings, cudaS
     return int(cudaErrorInvalidValue);
 }
 
-int run_all(const b2_engine* e, const Plan& plan, void* const* bindings, cudaStream_t s) {
-    for (const Launch& L : plan.launches) {
-        const int rc = run_launch(e, L, bindings, s);
+// Launches the plan on `s`.  Side branches go to the context's second stream between a fork and a join event: inside
+// a stream capture that becomes a parallel branch of the graph, outside it is plain two-stream concurrency.
+int run_all(b2_context* c, const Plan& plan, void* const* bindings, cudaStream_t s) {
+    const b2_engine* e = c->e;
+    bool fork = c->fork != 0;
+    if (fork && !c->side) {
+        if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            fork = false;
+        }
+    }
+    int pending_join = -1;
+    for (size_t i = 0; i < plan.launches.size(); ++i) {
+        const Launch& L = plan.launches[i];
+        if (pending_join == int(i)) {
+            B2_CUDA(cudaStreamWaitEvent(s, c->join_ev, 0));
+            pending_join = -1;
+        }
+        int rc;
+        if (fork && pending_join < 0 && L.side_join > int(i)) {
+            B2_CUDA(cudaEventRecord(c->fork_ev, s));
+            B2_CUDA(cudaStreamWaitEvent(c->side, c->fork_ev, 0));
+            rc = run_launch(e, L, bindings, c->side);
+            if (rc == 0) {
+                B2_CUDA(cudaEventRecord(c->join_ev, c->side));
+                pending_join = L.side_join;
+            }
+        } else {
+            rc = run_launch(e, L, bindings, s);
+        }
         if (rc != 0)
             return fail(B2_ECUDA, "launch of %s failed: %s", L.name.c_str(), cudaGetErrorString(cudaError_t(rc)));
     }
+    if (pending_join >= 0) B2_CUDA(cudaStreamWaitEvent(s, c->join_ev, 0));  // never leave the branch dangling
     return B2_OK;
 }
 
@@ -1172,6 +1237,7 @@ int b2_context_create(b2_engine* e, b2_context** out) {
     c->force_halo = env_int("B2_FORCE_HALO", 0);
     c->pdl_trigger = env_int("B2_PDL_TRIGGER", 1);
     c->autotune = env_int("B2_AUTOTUNE", 4);
+    c->fork = env_int("B2_FORK", 0);
     if (getenv("B2_PDL")) b2k::set_pdl(env_int("B2_PDL", 1) != 0);
     void* p = nullptr;
     if (cudaMalloc(&p, kMaxSplitTiles * sizeof(int)) != cudaSuccess || cudaMemset(p, 0, kMaxSplitTiles * sizeof(int)) != cudaSuccess) {
@@ -1195,6 +1261,9 @@ void b2_context_destroy(b2_context* c) {
     if (!c) return;
     drop_cached(c);
     if (c->d_counters) cudaFree(c->d_counters);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+    if (c->join_ev) cudaEventDestroy(c->join_ev);
     delete c;
 }
 
@@ -1226,6 +1295,7 @@ int b2_context_set_option(b2_context* c, const char* key, int value) {
     else if (k == "ws") c->force_ws = value;
     else if (k == "cn") c->force_cn = value;
     else if (k == "halo") c->force_halo = value;
+    else if (k == "fork") c->fork = value;
     else if (k == "pdl_trigger") c->pdl_trigger = value;
     else if (k == "autotune") c->autotune = value;
     else if (k == "no_fold") c->no_fold = value;
@@ -1250,7 +1320,7 @@ int b2_context_enqueue(b2_context* c, int batch, void* const* bindings, b2_strea
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     B2_CUDA(cudaStreamIsCapturing(stream, &cap));
     if (cap != cudaStreamCaptureStatusNone || !c->use_graph) {
-        if ((rc = run_all(c->e, *plan, bindings, stream))) return rc;
+        if ((rc = run_all(c, *plan, bindings, stream))) return rc;
     } else {
         b2_context::GraphKey key;
         key.batch = batch;
@@ -1264,7 +1334,7 @@ int b2_context_enqueue(b2_context* c, int batch, void* const* bindings, b2_strea
             }
             cudaGraph_t graph = nullptr;
             B2_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-            rc = run_all(c->e, *plan, bindings, stream);
+            rc = run_all(c, *plan, bindings, stream);
             cudaError_t ce = cudaStreamEndCapture(stream, &graph);
             if (rc) {
                 if (graph) cudaGraphDestroy(graph);
@@ -1356,6 +1426,7 @@ const char* b2_context_launch_name(b2_context* c, int batch, int i) {
              (L->conv.args.a_mode == b2k::A_TILED ? " tiled" : " im2col") +
              " grid=" + std::to_string(L->conv.grid_n) + "x" + std::to_string(L->conv.grid_m) + "x" +
              std::to_string(L->conv.args.splits) + " kblk=" + std::to_string(L->conv.args.num_kblocks);
+    if (L->side_join >= 0) s += " side";
     return s.c_str();
 }
 double b2_context_launch_flops(b2_context* c, int batch, int i) {

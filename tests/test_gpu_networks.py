@@ -156,6 +156,30 @@ def test_fp16_input_binding_matches_fp32_binding(rn50, rn50_session):
         mgr.close()
 
 
+def test_side_branches_run_forked_and_change_nothing(rn50, rn50_session):
+    """The shortcut convolutions of the four "a" blocks run on a forked stream (a parallel branch of the captured graph)
+    while branch2a/2b execute; results are bit-identical to the linear schedule, with and without graph replay."""
+    eng = capi.Engine(rn50_session["blob"])
+    outs = {}
+    try:
+        for fork, graph_ in ((1, 1), (0, 1), (1, 0)):
+            sess = capi.Session(eng, {"fork": fork, "graph": graph_})
+            try:
+                outs[(fork, graph_)] = sess.infer(rn50["x"])["prob"]
+                for _ in range(3):
+                    np.testing.assert_array_equal(sess.infer(rn50["x"])["prob"], outs[(fork, graph_)])
+                n = sess.nb_launches(8)
+                names = [capi.load().b2_context_launch_name(sess.ctx, 8, i).decode() for i in range(n)]
+                assert sum(1 for s_ in names if s_.endswith(" side")) == 4
+            finally:
+                sess.close()
+    finally:
+        eng.destroy()
+    np.testing.assert_array_equal(outs[(1, 1)], outs[(0, 1)])
+    np.testing.assert_array_equal(outs[(1, 0)], outs[(0, 1)])
+    np.testing.assert_array_equal(outs[(1, 1)], rn50_session["sess"].infer(rn50["x"])["prob"])
+
+
 def test_dynamic_batching_runner(rn50, rn50_session):
     """BatchedInferRunner: 13 single-image requests -> one full batch of 8 + one window-closed batch of 5; every image's
     result is bit-identical to the direct batch-8 path (results do not depend on the batch an image travels in)."""
