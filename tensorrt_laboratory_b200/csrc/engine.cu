@@ -680,7 +680,8 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, int 
     const int bns[4] = {256, 128, 64, 32};
     const int stgs[4] = {1, 2, 4, 8};
     int status = B2_OK;
-    const int iters = 12;
+    const int iters = std::max(4, env_int("B2_TUNE_ITERS", 12));   // launches per stream and measurement
+    const int reps = std::max(1, env_int("B2_TUNE_REPS", 2));      // measurements per candidate (the quietest counts)
     const int m_tiles = (M + 127) / 128;
     const int split_cands[4] = {1, 2, 4, 8};
     std::vector<ConvConfig> candidates;
@@ -764,7 +765,7 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, int 
             for (int k = 0; k < ns; ++k) cudaStreamSynchronize(ss[k]);
             float ms = 1e30f;
             cudaError_t se = cudaSuccess;
-            for (int rep = 0; rep < 2 && !rc && se == cudaSuccess; ++rep) {  // two measurements, keep the quieter one
+            for (int rep = 0; rep < reps && !rc && se == cudaSuccess; ++rep) {  // keep the quietest measurement
                 cudaEventRecord(e0, ss[0]);
                 for (int k = 1; k < ns; ++k) cudaStreamWaitEvent(ss[k], e0, 0);
                 for (int i = 0; i < iters && !rc; ++i)
