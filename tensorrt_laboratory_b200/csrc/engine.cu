@@ -568,7 +568,8 @@ int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& c
     cl.sps = cfg.sps > 0 ? cfg.sps : 1;
     cl.grid_n = int(r.cout_phys) / cl.bn;
     cl.ws_ctas = cfg.ws;
-    cl.cn = (cfg.cn > 1 && cfg.ws == 0 && cl.kb == 64 && cl.grid_n % cfg.cn == 0) ? cfg.cn : 1;
+    cl.cn = (cfg.cn > 1 && cfg.ws == 0 && cl.kb == 64 && cl.grid_n % cfg.cn == 0 &&
+             b2k::conv_cluster_config_exists(cl.bn, cl.stages, cl.sps, cfg.cn)) ? cfg.cn : 1;
     cl.args.cn = cl.cn;
     cl.args.tiles_m = cl.grid_m;
     cl.args.tiles_n = cl.grid_n;
@@ -715,13 +716,15 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, int 
                            (sp - 1) * kpc >= nkb ||
                            size_t(tiles) * sp * 128 * bn * 4 > kSplitWorkspaceBytes))
                 continue;  // split-K only where the plain grid leaves SMs idle
-            const bool cn_forced_here = c->force_cn > 1 && kbsz == 64 && (int(r.cout_phys) / bn) % c->force_cn == 0;
+            const bool cn_forced_here = c->force_cn > 1 && kbsz == 64 && (int(r.cout_phys) / bn) % c->force_cn == 0 &&
+                                        b2k::conv_cluster_config_exists(bn, st, sps, c->force_cn);
             if (!cn_forced_here) candidates.push_back(ConvConfig{bn, st, sp, 0.0, sps, 0, 1});
             // clusters along N that multicast the activation tile: never won a timing on B200 (the L2 read is shared but
             // every SM still ingests the whole tile, and the cluster barriers cost latency) -> tried only on request
             if (kbsz == 64 && c->force_cn > 0)
                 for (int cn = 2; cn <= 4; cn *= 2)
-                    if ((int(r.cout_phys) / bn) % cn == 0 && (!c->force_cn || cn == c->force_cn))
+                    if ((int(r.cout_phys) / bn) % cn == 0 && (!c->force_cn || cn == c->force_cn) &&
+                        b2k::conv_cluster_config_exists(bn, st, sps, cn))
                         candidates.push_back(ConvConfig{bn, st, sp, 0.0, sps, 0, cn});
         }
     }

@@ -268,7 +268,7 @@ __device__ __forceinline__ uint32_t swz_off(int row, int chunk) {
     return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
 
-template <int BN, int KB, int STAGES, int SPS>
+template <int BN, int KB, int STAGES, int SPS, int CN = 1>
 __global__ void __launch_bounds__(128)
 conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
@@ -328,9 +328,11 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     // each activation sub-block and multicasts it to all of them, so L2 serves the tile once per cluster instead of once
     // per CTA.  A stage may be refilled only when EVERY CTA has consumed it -> the MMA warps multicast their stage
     // release and the empty barriers count cn arrivals.
-    const int cn = (KB == 64) ? p.cn : 1;
+    // (compile-time: the one-CTA instantiations carry none of the cluster code in their loops)
+    static_assert(CN == 1 || KB == 64, "clusters exist for the 64-wide K path only");
+    constexpr int cn = CN;
     const uint32_t crank = cn > 1 ? cluster_ctarank() : 0u;
-    const uint16_t cmask = static_cast<uint16_t>((1u << cn) - 1u);
+    constexpr uint16_t cmask = static_cast<uint16_t>((1u << cn) - 1u);
 
     // ---------------- prologue: nothing here depends on the previous kernel's output ----------------
     if (threadIdx.x == 0) {
@@ -1232,19 +1234,19 @@ static int launch_kernel(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStre
     return launch_kernel_cluster(kern, grid, block, smem, stream, pdl, 1u, args...);
 }
 
-template <int BN, int KB, int STAGES, int SPS>
+template <int BN, int KB, int STAGES, int SPS, int CN = 1>
 static int launch_one(const ConvLaunch& L, cudaStream_t stream) {
     dim3 grid(L.grid_n, L.grid_m, L.args.splits);
     const size_t smem = size_t(conv_smem_layout_bytes(BN, STAGES, L.args.residual != nullptr, SPS));
-    if (L.cn > 1 && (KB != 64 || L.grid_n % L.cn != 0 || L.args.cn != L.cn)) return static_cast<int>(cudaErrorInvalidValue);
-    return launch_kernel_cluster(conv_f16_tcgen05<BN, KB, STAGES, SPS>, grid, dim3(128), smem, stream, true,
-                                 static_cast<unsigned>(L.cn > 1 ? L.cn : 1), L.mapA, L.mapB, L.mapOut, L.mapRes, L.args);
+    if (CN > 1 && (KB != 64 || L.grid_n % CN != 0 || L.args.cn != CN)) return static_cast<int>(cudaErrorInvalidValue);
+    return launch_kernel_cluster(conv_f16_tcgen05<BN, KB, STAGES, SPS, CN>, grid, dim3(128), smem, stream, true,
+                                 static_cast<unsigned>(CN), L.mapA, L.mapB, L.mapOut, L.mapRes, L.args);
 }
 
-template <int BN, int KB, int STAGES, int SPS>
+template <int BN, int KB, int STAGES, int SPS, int CN = 1>
 static int init_one() {
     const int want = conv_smem_layout_bytes(BN, STAGES, true, SPS);
-    return static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES, SPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES, SPS, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  want > 227 * 1024 ? conv_smem_layout_bytes(BN, STAGES, false, SPS) : want));
 }
 
@@ -1281,6 +1283,11 @@ static int launch_conv_halo(const ConvLaunch& L, cudaStream_t stream) {
     return static_cast<int>(cudaErrorInvalidValue);
 }
 
+// cluster-multicast instantiations (BN, STAGES, SPS, CN): an experiment-only tactic (never won a timing), kept small
+#define B2_FOR_EACH_CONV_CLUSTER(X) \
+    X(32, 4, 1, 2) X(32, 4, 1, 4) X(64, 1, 1, 2) X(64, 2, 1, 2) X(64, 2, 1, 4) X(64, 2, 2, 2) X(64, 4, 2, 2) X(64, 4, 2, 4) \
+    X(128, 2, 1, 2) X(128, 2, 1, 4) X(128, 2, 2, 2)
+
 int init_conv_ws_kernels();
 int launch_conv_f16_tcgen05_ws(const ConvLaunch& L, cudaStream_t stream);
 
@@ -1292,12 +1299,23 @@ int init_conv_kernels() {
     if ((e = init_one<BN_, KB_, ST_, SPS_>())) return e;
     B2_FOR_EACH_CONV(B2_INIT)
 #undef B2_INIT
+#define B2_INIT_CL(BN_, ST_, SPS_, CN_) \
+    if ((e = init_one<BN_, 64, ST_, SPS_, CN_>())) return e;
+    B2_FOR_EACH_CONV_CLUSTER(B2_INIT_CL)
+#undef B2_INIT_CL
     return 0;
 }
 
 int launch_conv_f16_tcgen05(const ConvLaunch& L, cudaStream_t stream) {
     if (L.halo) return launch_conv_halo(L, stream);
     if (L.ws_ctas > 0) return launch_conv_f16_tcgen05_ws(L, stream);
+    if (L.cn > 1) {
+#define B2_CASE_CL(BN_, ST_, SPS_, CN_) \
+    if (L.bn == BN_ && L.kb == 64 && L.stages == ST_ && L.sps == SPS_ && L.cn == CN_) return launch_one<BN_, 64, ST_, SPS_, CN_>(L, stream);
+        B2_FOR_EACH_CONV_CLUSTER(B2_CASE_CL)
+#undef B2_CASE_CL
+        return static_cast<int>(cudaErrorInvalidValue);
+    }
 #define B2_CASE(BN_, KB_, ST_, SPS_) \
     if (L.bn == BN_ && L.kb == KB_ && L.stages == ST_ && L.sps == SPS_) return launch_one<BN_, KB_, ST_, SPS_>(L, stream);
     B2_FOR_EACH_CONV(B2_CASE)
@@ -1348,6 +1366,14 @@ bool conv_ws_config_exists(int bn, int stages, int sps) {
 }
 
 int conv_ws_smem(int bn, int stages, int sps, bool residual) { return conv_ws_smem_bytes(bn, stages, sps, residual); }
+
+bool conv_cluster_config_exists(int bn, int stages, int sps, int cn) {
+#define B2_HAS_CL(BN_, ST_, SPS_, CN_) \
+    if (bn == BN_ && stages == ST_ && sps == SPS_ && cn == CN_) return true;
+    B2_FOR_EACH_CONV_CLUSTER(B2_HAS_CL)
+#undef B2_HAS_CL
+    return false;
+}
 
 bool conv_config_exists(int bn, int kb, int stages, int sps) {
 #define B2_HAS(BN_, KB_, ST_, SPS_) \
@@ -1675,7 +1701,62 @@ __global__ void avgpool_kernel(const T* __restrict__ src, T* __restrict__ dst, i
     dst[idx] = from_f<T>(static_cast<float>(acc / static_cast<acc_t>(HW)));
 }
 
+// fp16 global average pool, 16 bytes per load: block = 32 channel groups (8 channels each) x 8 pixel slices; every slice
+// sums its pixels (stride 8), the slices are added in fixed order through smem -> deterministic, ~7 loads per thread for
+// the 7x7 plane instead of 49 dependent 2-byte loads
+__global__ void __launch_bounds__(256) avgpool_h8_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int HW, int C8) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ float part[8][32][8];
+    const int lane_cg = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int groups_per_img = (C8 + 31) / 32;
+    const int n = blockIdx.x / groups_per_img;
+    const int cg = (blockIdx.x - n * groups_per_img) * 32 + lane_cg;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (cg < C8) {
+        const uint4* base = src + static_cast<size_t>(n) * HW * C8 + cg;
+        for (int px = slice; px < HW; px += 8) {
+            const uint4 v = __ldg(base + static_cast<size_t>(px) * C8);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h2[i]);
+                acc[2 * i] += f.x;
+                acc[2 * i + 1] += f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[slice][lane_cg][i] = acc[i];
+    __syncthreads();
+    if (slice == 0 && cg < C8) {
+        const float inv = 1.0f / static_cast<float>(HW);
+        float tot[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float t = part[0][lane_cg][i];
+#pragma unroll
+            for (int sl = 1; sl < 8; ++sl) t += part[sl][lane_cg][i];
+            tot[i] = t * inv;
+        }
+        uint4 o;
+        __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(tot[2 * i], tot[2 * i + 1]);
+        dst[static_cast<size_t>(n) * C8 + cg] = o;
+    }
+}
+
 int launch_avgpool(const void* src, void* dst, int N, int HW, int C_phys, bool half_storage, cudaStream_t stream) {
+    if (half_storage && C_phys % 8 == 0) {
+        const int c8 = C_phys / 8;
+        const unsigned blocks = static_cast<unsigned>(N * ((c8 + 31) / 32));
+        B2_LAUNCH_RC = launch_kernel(avgpool_h8_kernel, dim3(blocks), dim3(256), 0, stream, true, reinterpret_cast<const uint4*>(src),
+                                     reinterpret_cast<uint4*>(dst), N, HW, c8);
+        return B2_LAUNCH_RC;
+    }
     const int threads = 128;
     const unsigned blocks = static_cast<unsigned>((N * C_phys + threads - 1) / threads);
     if (half_storage)

@@ -68,6 +68,7 @@ int launch_conv_f16_tcgen05(const ConvLaunch& L, cudaStream_t stream);
 int init_conv_kernels();
 bool conv_config_exists(int bn, int kb, int stages, int sps = 1);  // is this configuration instantiated?
 int conv_smem_bytes(int bn, int stages, bool residual, int sps = 1);  // dynamic shared memory of one CTA
+bool conv_cluster_config_exists(int bn, int stages, int sps, int cn);  // cluster-multicast instantiations
 bool conv_halo_config_exists(int bn);                                // 3x3 halo variant
 int conv_halo_smem(int bn, int w, int r, int cblocks);
 bool conv_ws_config_exists(int bn, int stages, int sps);             // persistent warp-specialised variant
