@@ -268,7 +268,7 @@ __device__ __forceinline__ uint32_t swz_off(int row, int chunk) {
     return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
 
-template <int BN, int KB, int STAGES, int SPS, int CN = 1>
+template <int BN, int KB, int STAGES, int SPS, int CN = 1, bool DBG = false>
 __global__ void __launch_bounds__(128)
 conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
@@ -306,7 +306,9 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN;
     const int m0 = blockIdx.y * 128;
-    long long* dbg = p.dbg ? p.dbg + 16ll * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+    // phase timestamps / bottleneck-isolation switches exist only in the DBG instantiations: even never-taken uniform
+    // branches inside the single-thread producer and MMA loops are measurable (see profiles/README.md, A/B runs)
+    long long* dbg = (DBG && p.dbg) ? p.dbg + 16ll * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
     if (dbg && threadIdx.x == 0) {
         dbg[0] = clock64();
         unsigned long long gt;
@@ -367,7 +369,8 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int n = p.taps_phys - kb * TPS;
         return n > TPS ? TPS : n;
     };
-    const bool skip_mma = p.dbg_mode & 1, skip_a = KB == 64 && (p.dbg_mode & 2), skip_b = KB == 64 && (p.dbg_mode & 4);
+    const bool skip_mma = DBG && (p.dbg_mode & 1), skip_a = DBG && KB == 64 && (p.dbg_mode & 2),
+               skip_b = DBG && KB == 64 && (p.dbg_mode & 4);
     // step i of the pipeline covers K-blocks kb_begin + i*SPS ... ; `kb` below is always the FIRST K-block of a step
     auto stage_bytes = [&](int kb) -> uint32_t {
         if (KB == 64) {
@@ -1239,6 +1242,9 @@ static int launch_one(const ConvLaunch& L, cudaStream_t stream) {
     dim3 grid(L.grid_n, L.grid_m, L.args.splits);
     const size_t smem = size_t(conv_smem_layout_bytes(BN, STAGES, L.args.residual != nullptr, SPS));
     if (CN > 1 && (KB != 64 || L.grid_n % CN != 0 || L.args.cn != CN)) return static_cast<int>(cudaErrorInvalidValue);
+    if (CN == 1 && (L.args.dbg != nullptr || L.args.dbg_mode != 0))
+        return launch_kernel_cluster(conv_f16_tcgen05<BN, KB, STAGES, SPS, 1, true>, grid, dim3(128), smem, stream, true, 1u, L.mapA,
+                                     L.mapB, L.mapOut, L.mapRes, L.args);
     return launch_kernel_cluster(conv_f16_tcgen05<BN, KB, STAGES, SPS, CN>, grid, dim3(128), smem, stream, true,
                                  static_cast<unsigned>(CN), L.mapA, L.mapB, L.mapOut, L.mapRes, L.args);
 }
@@ -1246,8 +1252,13 @@ static int launch_one(const ConvLaunch& L, cudaStream_t stream) {
 template <int BN, int KB, int STAGES, int SPS, int CN = 1>
 static int init_one() {
     const int want = conv_smem_layout_bytes(BN, STAGES, true, SPS);
-    return static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES, SPS, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 want > 227 * 1024 ? conv_smem_layout_bytes(BN, STAGES, false, SPS) : want));
+    const int bytes = want > 227 * 1024 ? conv_smem_layout_bytes(BN, STAGES, false, SPS) : want;
+    if (CN == 1) {
+        const int e = static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES, SPS, 1, true>,
+                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if (e) return e;
+    }
+    return static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES, SPS, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 }
 
 int conv_smem_bytes(int bn, int stages, bool residual, int sps) { return conv_smem_layout_bytes(bn, stages, residual, sps); }
