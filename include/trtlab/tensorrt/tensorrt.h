@@ -24,6 +24,7 @@
 #include "b200cuda.h"
 #include "b200infer.h"
 #include "trtlab/core/batcher.h"
+#include "trtlab/tensorrt/metrics.h"
 #include "trtlab/core/hotpath_core.h"
 
 // CUDA handle aliases: when the CUDA runtime header is present use its types, otherwise opaque pointers
@@ -306,6 +307,10 @@ class Bindings {
 
     inline cudaStream_t Stream() const { return m_Buffers->Stream(); }
     void Synchronize() const { m_Buffers->Synchronize(); }
+    // device time of this request's forward pass, filled in by InferRunner's post stage before the user's function runs
+    // (what the reference's service reads from ctx->Synchronize(), server.cc:169)
+    double ComputeTime() const { return m_ComputeSeconds; }
+    void SetComputeTime(double seconds) { m_ComputeSeconds = seconds; }
     size_t BindingSize(uint32_t binding_id) const;
 
   private:
@@ -316,6 +321,7 @@ class Bindings {
     std::vector<void*> m_HostAddresses;
     std::vector<void*> m_DeviceAddresses;
     void* m_ActivationsAddress;
+    double m_ComputeSeconds = 0.0;
     friend class Buffers;
 };
 
@@ -389,6 +395,8 @@ class InferenceManager : public ::trtlab::Resources {
     int MaxExecConcurrency() const;
     static int EnqueueDepth();
     // device time of finished forward passes (fed by InferRunner's post stage)
+    // request / compute summaries, load-ratio histogram, power gauge (metrics.h); fed by InferBench and by services
+    Metrics& GetMetrics() { return m_Metrics; }
     void RecordComputeTime(double seconds);
     double MeanComputeTime(bool reset);  // tokens queued per execution lane (TRTLAB_ENQUEUE_DEPTH, default 2)
     int MaxCopyConcurrency() const;
@@ -400,6 +408,7 @@ class InferenceManager : public ::trtlab::Resources {
 
   private:
     int m_Device;
+    Metrics m_Metrics;
     std::atomic<uint64_t> m_ComputeNs{0};
     std::atomic<uint64_t> m_ComputeCount{0};
     int m_MaxExecutions;
@@ -478,7 +487,9 @@ struct InferRunner : public AsyncComputeWrapper<void(std::shared_ptr<Bindings>&)
             bindings->CopyFromDevice(bindings->OutputBindings());                  // D2H
             resources->AcquireThreadPool("post").enqueue([resources, bindings, trt_ctx, Post]() mutable {
                 resources->ActivateDevice();
-                resources->RecordComputeTime(trt_ctx->Synchronize());
+                const double compute_seconds = trt_ctx->Synchronize();
+                resources->RecordComputeTime(compute_seconds);
+                bindings->SetComputeTime(compute_seconds);
                 trt_ctx.reset();  // returns both pool tokens
                 bindings->Synchronize();
                 (*Post)(bindings);

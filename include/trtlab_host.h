@@ -30,6 +30,10 @@ int trt_manager_infer(trt_manager* m, const char* model, int batch, const void* 
  * contiguous [n][item]; *batches_executed = number of merged forward passes it took */
 int trt_manager_infer_batched(trt_manager* m, const char* model, int n, const void* inputs, void* outputs, int window_us,
                               int* batches_executed);
+/* Prometheus text exposition of the manager's metrics (request/compute summaries per model, load-ratio histogram,
+ * GPU power gauge sampled now through NVML); returns the text length (excluding the NUL) or a negative B2_E* code;
+ * at most cap-1 bytes are written */
+int trt_manager_metrics_text(trt_manager* m, char* buf, size_t cap);
 /* write a distinct batch from `ring` into the pinned input region of every pooled Buffers */
 int trt_manager_prefill_inputs(trt_manager* m, const char* model, const void* ring, size_t ring_batches);
 /* InferBench::Run closed loop; results16[InferBenchKey]; optional per-request latencies (seconds) */

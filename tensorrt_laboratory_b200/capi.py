@@ -86,6 +86,7 @@ SYMBOLS = [
     ("trt_manager_allocate", _I, [_VP]),
     ("trt_manager_infer", _I, [_VP, _S, _I, _VP, _SZ, _VP, _SZ, C.POINTER(_D)]),
     ("trt_manager_infer_batched", _I, [_VP, _S, _I, _VP, _VP, _I, C.POINTER(_I)]),
+    ("trt_manager_metrics_text", _I, [_VP, C.c_char_p, _SZ]),
     ("trt_manager_prefill_inputs", _I, [_VP, _S, _VP, _SZ]),
     ("trt_manager_bench", _I, [_VP, _S, _I, _D, _SZ, C.POINTER(_D), C.POINTER(_D), _SZ, C.POINTER(_SZ)]),
     ("trt_timed_pipeline", _I, [_VP, _SZ, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -440,6 +441,14 @@ class InferenceManager:
         check(self._lib.trt_manager_infer_batched(self.handle, name.encode(), x.shape[0], x.ctypes.data, out.ctypes.data,
                                                   window_us, C.byref(nb)))
         return out, nb.value
+
+    def metrics_text(self) -> str:
+        """Prometheus text exposition (request/compute summaries, load-ratio histogram, GPU power gauge)."""
+        buf = C.create_string_buffer(1 << 16)
+        n = self._lib.trt_manager_metrics_text(self.handle, buf, len(buf))
+        if n < 0:
+            raise RuntimeError(self._lib.b2_last_error().decode())
+        return buf.value.decode()
 
     def prefill_inputs(self, name: str, ring: np.ndarray):
         ring = np.ascontiguousarray(ring, dtype=[b["np_dtype"] for b in self.models[name].bindings if b["is_input"]][0])

@@ -121,6 +121,20 @@ int trt_manager_infer_batched(trt_manager* m, const char* model_name, int n, con
     TRT_CATCH
 }
 
+int trt_manager_metrics_text(trt_manager* m, char* buf, size_t cap) {
+    if (!m || !buf || cap == 0) return -fail(B2_EINVAL, "bad arguments");
+    try {
+        m->mgr->GetMetrics().SamplePower(m->mgr->Device());
+        const std::string text = m->mgr->GetMetrics().Expose();
+        const size_t n = std::min(text.size(), cap - 1);
+        memcpy(buf, text.data(), n);
+        buf[n] = 0;
+        return int(text.size());
+    } catch (const std::exception& e) {
+        return -fail(B2_ESTATE, "%s", e.what());
+    }
+}
+
 // Give every pooled Buffers a distinct input batch in its pinned host stack.  Bindings are bump-allocated
 // from a stack that is Reset() on return, so the addresses (and contents) persist across requests.
 int trt_manager_prefill_inputs(trt_manager* m, const char* model_name, const void* ring, size_t ring_batches) {

@@ -523,9 +523,11 @@ std::unique_ptr<InferBench::Results> InferBench::Run(const ModelsList& models, u
         const auto t0 = clock::now();
         InferRunner runner(model, m_Resources);
         const bool want_lat = latencies_s != nullptr;
-        futures.push_back(runner.Infer(bindings, [t0, lat, lat_mutex, want_lat](std::shared_ptr<Bindings>& b) mutable {
+        auto resources = m_Resources;
+        futures.push_back(runner.Infer(bindings, [t0, lat, lat_mutex, want_lat, resources](std::shared_ptr<Bindings>& b) mutable {
+            const double dt = std::chrono::duration<double>(clock::now() - t0).count();
+            resources->GetMetrics().ObserveRequest(b->GetModel()->Name(), b->ComputeTime(), dt);
             if (want_lat) {
-                const double dt = std::chrono::duration<double>(clock::now() - t0).count();
                 std::lock_guard<std::mutex> l(*lat_mutex);
                 lat->push_back(dt);
             }

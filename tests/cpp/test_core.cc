@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "trtlab/core/batcher.h"
+#include "trtlab/tensorrt/metrics.h"
 #include "trtlab/core/hotpath_core.h"
 
 using namespace trtlab;
@@ -280,6 +281,25 @@ static void test_dispatcher_full_batch_and_window() {
     (void)f0;
 }
 
+// Metrics: the reference service's series in Prometheus text format (examples/02_TensorRT_GRPC/src/server.cc:82-107)
+static void test_metrics_exposition() {
+    Metrics m;
+    for (int i = 1; i <= 100; i++) m.ObserveRequest("rn50", i * 1e-3, i * 1.3e-3);  // load ratio 1.3 each
+    m.ObserveRequest("mnist", 1e-3, 0.2);                                          // load ratio 200
+    m.SetPower(0, 512.5);
+    const std::string t = m.Expose();
+    auto has = [&](const char* s) { return t.find(s) != std::string::npos; };
+    EXPECT(has("# TYPE yais_inference_compute_duration_ms summary"));
+    EXPECT(has("yais_inference_compute_duration_ms{model=\"rn50\",quantile=\"0.5\"} 51"));
+    EXPECT(has("yais_inference_compute_duration_ms_count{model=\"rn50\"} 100"));
+    EXPECT(has("yais_inference_request_duration_ms_sum{model=\"mnist\"} 200"));
+    EXPECT(has("yais_inference_load_ratio_bucket{le=\"1.25\"} 0"));
+    EXPECT(has("yais_inference_load_ratio_bucket{le=\"1.5\"} 100"));
+    EXPECT(has("yais_inference_load_ratio_bucket{le=\"100\"} 100"));
+    EXPECT(has("yais_inference_load_ratio_bucket{le=\"+Inf\"} 101"));
+    EXPECT(has("yais_gpus_power_usage{gpu=\"0\"} 512.5"));
+}
+
 static void test_bytes() {
     EXPECT(BytesToString(512) == "512 B");
     EXPECT(BytesToString(1536) == "1.5 KiB");
@@ -303,6 +323,7 @@ int main() {
     test_async_compute();
     test_bytes();
     test_cyclic_allocator();
+    test_metrics_exposition();
     test_standard_batcher();
     test_deferred_task_pool();
     test_dispatcher_full_batch_and_window();

@@ -147,7 +147,7 @@ def test_stem_space_to_depth_is_exact():
 def test_cpp_core_unit_tests(tmp_path):
     exe = tmp_path / "test_core"
     subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
-                    os.path.join(ROOT, "tests", "cpp", "test_core.cc"), "-o", str(exe), "-lpthread"], check=True)
+                    os.path.join(ROOT, "tests", "cpp", "test_core.cc"), "-o", str(exe), "-lpthread", "-ldl"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stderr
 

@@ -127,6 +127,12 @@ def test_inference_manager_pipeline_matches_direct_path(rn50, rn50_session):
         assert res["kBatchesComputed"] == 64 and res["kInferencesPerSecond"] > 0
         assert res["kMaxExecConcurrency"] == 2 and res["kMaxCopyConcurrency"] == 4
         assert len(lats) == 64 and (lats > 0).all()
+        # observability: the reference service's four series, Prometheus text format
+        text = mgr.metrics_text()
+        assert 'yais_inference_compute_duration_ms_count{model="rn50"} 64' in text
+        assert 'yais_inference_request_duration_ms{model="rn50",quantile="0.99"}' in text
+        assert 'yais_inference_load_ratio_bucket{le="+Inf"} 64' in text
+        assert 0 < res["kGpuComputeTimePerBatch"] < 0.05
     finally:
         mgr.close()
 
