@@ -268,7 +268,10 @@ __device__ __forceinline__ uint32_t swz_off(int row, int chunk) {
     return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
 
-template <int BN, int KB, int STAGES, int SPS, int CN = 1, bool DBG = false>
+// AV resolves the operand paths at compile time for the production instantiations: 1 = im2col-mode activations + packed
+// weights, 2 = tiled activations + packed weights, 0 = decided at run time from ConvArgs (thin-K paths, unpacked plans,
+// clusters, debug).
+template <int BN, int KB, int STAGES, int SPS, int CN = 1, bool DBG = false, int AV = 0>
 __global__ void __launch_bounds__(128)
 conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapRes,
@@ -326,6 +329,9 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         return rem < SPS ? rem : SPS;
     };
     const bool split = p.splits > 1;
+    static_assert(AV == 0 || (KB == 64 && CN == 1 && !DBG), "resolved operand paths exist for the plain 64-wide K kernels");
+    const bool a_tiled = AV == 2 ? true : (AV == 1 ? false : p.a_mode == A_TILED);
+    const bool w_packed = AV != 0 ? true : p.wpacked != nullptr;
     // Cluster of `cn` CTAs along N (same 128 output pixels, different output-channel tiles): every CTA fetches 1/cn of
     // each activation sub-block and multicasts it to all of them, so L2 serves the tile once per cluster instead of once
     // per CTA.  A stage may be refilled only when EVERY CTA has consumed it -> the MMA warps multicast their stage
@@ -385,7 +391,7 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (KB == 64) {
             const int ns = subs_in_step((kb - kb_begin) / SPS);
             for (int u = 0; u < ns; ++u) {
-                if (p.wpacked != nullptr) {  // one contiguous run of BN/32 pre-swizzled 4 KiB blocks
+                if (w_packed) {  // one contiguous run of BN/32 pre-swizzled 4 KiB blocks
                     bulk_load_1d(&full_bar[s], b_dst + u * Cfg::B_SUBBLK,
                                  p.wpacked + (static_cast<size_t>(kb + u) * (p.Cout >> 5) + (n0 >> 5)) * 4096, BN * 128);
                 } else {
@@ -410,7 +416,7 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int slice_rows = 128 / cn;                 // rows of the A tile this CTA fetches (all of them: cn == 1)
             int ms = m0 + static_cast<int>(crank) * slice_rows;  // first output pixel of the slice
             const uint32_t slice_off = crank * static_cast<uint32_t>(slice_rows) * 128u;  // 128-byte swizzled rows
-            if (p.a_mode == A_IM2COL) {
+            if (!a_tiled) {
                 if (ms >= p.M) ms = 0;  // slice entirely past the last pixel: its rows are never stored, fetch valid ones
                 img0 = ms / p.HoWo;
                 const int rem = ms - img0 * p.HoWo;
@@ -435,13 +441,13 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     const int ns = subs_in_step((kb - kb_begin) / SPS);
                     for (int u = 0; u < ns; ++u) {
                         if (cn > 1) {
-                            if (p.a_mode == A_TILED) {
+                            if (a_tiled) {
                                 tma_load_2d_mc(&mapA, &full_bar[s], a_dst + u * Cfg::A_SUBBLK + slice_off, cur_cb * 64, ms, cmask);
                             } else {
                                 tma_load_im2col_4d_mc(&mapA, &full_bar[s], a_dst + u * Cfg::A_SUBBLK + slice_off, cur_cb * 64, base_w,
                                                       base_h, img0, static_cast<uint16_t>(cur_sx), static_cast<uint16_t>(cur_r), cmask);
                             }
-                        } else if (p.a_mode == A_TILED) {
+                        } else if (a_tiled) {
                             tma_load_2d(&mapA, &full_bar[s], a_dst + u * Cfg::A_SUBBLK, cur_cb * 64, m0);
                         } else {
                             tma_load_im2col_4d(&mapA, &full_bar[s], a_dst + u * Cfg::A_SUBBLK, cur_cb * 64, base_w, base_h, img0,
@@ -1245,6 +1251,15 @@ static int launch_one(const ConvLaunch& L, cudaStream_t stream) {
     if (CN == 1 && (L.args.dbg != nullptr || L.args.dbg_mode != 0))
         return launch_kernel_cluster(conv_f16_tcgen05<BN, KB, STAGES, SPS, 1, true>, grid, dim3(128), smem, stream, true, 1u, L.mapA,
                                      L.mapB, L.mapOut, L.mapRes, L.args);
+    if constexpr (CN == 1 && KB == 64) {
+        if (L.args.wpacked != nullptr) {
+            if (L.args.a_mode == A_TILED)
+                return launch_kernel_cluster(conv_f16_tcgen05<BN, KB, STAGES, SPS, 1, false, 2>, grid, dim3(128), smem, stream, true, 1u,
+                                             L.mapA, L.mapB, L.mapOut, L.mapRes, L.args);
+            return launch_kernel_cluster(conv_f16_tcgen05<BN, KB, STAGES, SPS, 1, false, 1>, grid, dim3(128), smem, stream, true, 1u,
+                                         L.mapA, L.mapB, L.mapOut, L.mapRes, L.args);
+        }
+    }
     return launch_kernel_cluster(conv_f16_tcgen05<BN, KB, STAGES, SPS, CN>, grid, dim3(128), smem, stream, true,
                                  static_cast<unsigned>(CN), L.mapA, L.mapB, L.mapOut, L.mapRes, L.args);
 }
@@ -1254,9 +1269,15 @@ static int init_one() {
     const int want = conv_smem_layout_bytes(BN, STAGES, true, SPS);
     const int bytes = want > 227 * 1024 ? conv_smem_layout_bytes(BN, STAGES, false, SPS) : want;
     if (CN == 1) {
-        const int e = static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES, SPS, 1, true>,
-                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        int e = static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES, SPS, 1, true>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         if (e) return e;
+        if constexpr (KB == 64) {
+            if ((e = static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES, SPS, 1, false, 1>,
+                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)))) return e;
+            if ((e = static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES, SPS, 1, false, 2>,
+                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)))) return e;
+        }
     }
     return static_cast<int>(cudaFuncSetAttribute(conv_f16_tcgen05<BN, KB, STAGES, SPS, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
 }
