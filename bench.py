@@ -291,8 +291,8 @@ def run_b200(args):
         "bound": "tensor", "kernel": "conv_f16_tcgen05 (all %d conv launches of one forward pass)" % n_conv,
         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
         # DRAM bytes (read+write) of the 53 conv launches of ONE forward pass = one step, from the committed ncu pass
-        # profiles/ncu_metrics_r1h.csv (cold L2; outputs stay L2-resident inside each kernel)
-        "traffic": 267.8e6, "traffic_source": "profiles/ncu_metrics_r1h.csv",
+        # profiles/ncu_metrics_r1i.csv (cold L2; outputs stay L2-resident inside each kernel)
+        "traffic": 267.2e6, "traffic_source": "profiles/ncu_metrics_r1i.csv",
         "peak_source": peak_src,
         "flops_per_step": conv_flops, "conv_share_of_step": conv_share,
         "hbm_view": {"algorithmic_bytes_per_step": ALGO_BYTES_PER_STEP,
