@@ -495,7 +495,7 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             for (int i = npre; i < nk; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
-                long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                long long c0 = 0, c1 = 0, c3 = 0;
                 if (dbg) c0 = clock64();
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (dbg) c1 = clock64();
@@ -1461,7 +1461,6 @@ __global__ void conv_simt_kernel(SimtConvArgs a) {
     }
     const T* in = reinterpret_cast<const T*>(a.in);
     const T* w = reinterpret_cast<const T*>(a.w) + static_cast<size_t>(co) * a.taps_phys * a.Cin_phys;
-    const int kblocks = a.taps_phys * a.Cin_phys / 64;
     acc_t acc = 0;
     for (int r = 0; r < a.kh; ++r) {
         const int hi = ho * a.stride_h - a.pad_h + r;
