@@ -1,0 +1,60 @@
+"""Python module `trtlab` (pybind11): the reference's trtlab/pybind surface (infer.cc:683-720) on this runtime.
+The GPU case replays the reference's results-pinning script examples/30_PyTensorRT/server.py:19-31 on the golden vectors."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tensorrt_laboratory_b200")
+
+
+def _module():
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    import trtlab  # built in-tree by __graft_entry__.build()
+    return trtlab
+
+
+def test_module_surface_matches_the_reference():
+    trtlab = _module()
+    assert {"InferenceManager", "InferRunner", "InferFuture"} <= set(dir(trtlab))
+    mgr = trtlab.InferenceManager(max_exec_concurrency=2)  # keywords of infer.cc:686-688
+    for name in ("register_tensorrt_engine", "update_resources", "infer_runner", "get_models", "serve"):
+        assert hasattr(mgr, name)
+    for name in ("infer", "input_bindings", "output_bindings", "max_batch_size"):
+        assert hasattr(trtlab.InferRunner, name)
+    assert hasattr(trtlab.InferFuture, "get") and hasattr(trtlab.InferFuture, "wait")
+    assert mgr.get_models() == {}
+    with pytest.raises(RuntimeError):  # missing engine file: std::runtime_error, as runtime.cc:83-86
+        mgr.register_tensorrt_engine("nope", "/nonexistent/engine.plan")
+    with pytest.raises(RuntimeError):
+        mgr.serve()
+
+
+@pytest.mark.gpu
+def test_mnist_known_answer_through_the_python_surface(gpu, tmp_path):
+    from tensorrt_laboratory_b200 import builder, graph
+    trtlab = _module()
+    net, w, xs, ys = helpers.load_mnist_golden()
+    plan = tmp_path / "mnist-v1.3.plan"
+    plan.write_bytes(builder.build_plan(graph.lower(net, w), builder.PREC_FP32, 1))
+    models = trtlab.InferenceManager(max_exec_concurrency=2)
+    mnist = models.register_tensorrt_engine("mnist", str(plan))
+    models.update_resources()
+    ins, outs = mnist.input_bindings(), mnist.output_bindings()
+    assert list(ins) == ["Input3"] and ins["Input3"]["shape"] == [1, 28, 28] and ins["Input3"]["dtype"] == np.float32
+    assert len(outs) == 1 and mnist.max_batch_size() == 1
+    results = [mnist.infer(Input3=x) for x in xs]          # futures, all in flight
+    results = [r.get() for r in results]
+    for r, e, want in zip(results, ys, (2, 0, 9)):
+        for key, val in r.items():
+            np.testing.assert_almost_equal(val.reshape((1, 10)), e.reshape((1, 10)), decimal=3)  # server.py:31
+            assert int(val.argmax()) == want
+    assert "mnist" in models.get_models() and 'model="mnist"' not in models.metrics_text()  # InferBench feeds metrics, infer() does not
+    with pytest.raises(ValueError):
+        mnist.infer(Input3=np.zeros((2, 1, 28, 28), np.float32))  # batch > max_batch_size
+    with pytest.raises(Exception):
+        mnist.infer(Nope=np.zeros((1, 1, 28, 28), np.float32))
