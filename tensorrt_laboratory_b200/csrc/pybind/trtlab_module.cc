@@ -60,7 +60,11 @@ struct PyInferRunner : public InferRunner {
         size_t seen = 0;
         for (auto item : kwargs) {
             const std::string key = py::cast<std::string>(item.first);
-            const uint32_t id = model.BindingId(key);  // throws for an unknown name
+            // (Model::BindingId aborts on an unknown name, like the reference's CHECK; a Python caller gets an exception)
+            bool known = false;
+            for (uint32_t i = 0; i < uint32_t(model.GetBindingsCount()); ++i) known = known || model.GetBinding(i).name == key;
+            if (!known) throw py::key_error(key + " is not a binding of model " + model.Name());
+            const uint32_t id = model.BindingId(key);
             const auto& b = model.GetBinding(id);
             if (!b.isInput) throw py::value_error(key + " is not an input binding");
             py::array arr = py::array::ensure(item.second, py::array::c_style | py::array::forcecast);

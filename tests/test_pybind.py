@@ -56,5 +56,6 @@ def test_mnist_known_answer_through_the_python_surface(gpu, tmp_path):
     assert "mnist" in models.get_models() and 'model="mnist"' not in models.metrics_text()  # InferBench feeds metrics, infer() does not
     with pytest.raises(ValueError):
         mnist.infer(Input3=np.zeros((2, 1, 28, 28), np.float32))  # batch > max_batch_size
-    with pytest.raises(Exception):
+    with pytest.raises(KeyError):
         mnist.infer(Nope=np.zeros((1, 1, 28, 28), np.float32))
+    np.testing.assert_almost_equal(mnist.infer(Input3=xs[0]).get()[list(outs)[0]].reshape(1, 10), ys[0], decimal=3)  # still serving
