@@ -393,12 +393,12 @@ class InferenceManager : public ::trtlab::Resources {
     void ForEachModel(std::function<void(const Model&)>);
 
     int MaxExecConcurrency() const;
-    static int EnqueueDepth();
-    // device time of finished forward passes (fed by InferRunner's post stage)
+    static int EnqueueDepth();  // tokens queued per execution lane (TRTLAB_ENQUEUE_DEPTH, default 2)
     // request / compute summaries, load-ratio histogram, power gauge (metrics.h); fed by InferBench and by services
     Metrics& GetMetrics() { return m_Metrics; }
+    // device time of finished forward passes (fed by InferRunner's post stage)
     void RecordComputeTime(double seconds);
-    double MeanComputeTime(bool reset);  // tokens queued per execution lane (TRTLAB_ENQUEUE_DEPTH, default 2)
+    double MeanComputeTime(bool reset);
     int MaxCopyConcurrency() const;
 
     // CUDA's current device is per thread and defaults to 0: pipeline stages running on pool threads adopt the
