@@ -151,8 +151,31 @@ def _value_info_name(buf: bytes) -> str:
     return ""
 
 
+def _value_info_shape(buf: bytes) -> List[int]:
+    """Static dims of a ValueInfoProto (type.tensor_type.shape.dim[*].dim_value); symbolic dims read as 0."""
+    dims: List[int] = []
+    for fno, _, v in _fields(buf):
+        if fno != 2:
+            continue
+        for f2, _, tt in _fields(v):           # TypeProto: tensor_type = 1
+            if f2 != 1:
+                continue
+            for f3, _, shp in _fields(tt):     # Tensor: elem_type = 1, shape = 2
+                if f3 != 2:
+                    continue
+                for f4, _, dim in _fields(shp):  # TensorShapeProto: dim = 1
+                    if f4 != 1:
+                        continue
+                    val = 0
+                    for f5, _, dv in _fields(dim):
+                        if f5 == 1:
+                            val = _signed(dv)
+                    dims.append(val)
+    return dims
+
+
 def parse_model(buf: bytes) -> dict:
-    """-> {nodes: [...], initializers: {name: ndarray}, inputs: [names], outputs: [names]}"""
+    """-> {nodes: [...], initializers: {name: ndarray}, inputs: [names], outputs: [names], input_shapes: {name: dims}}"""
     graph = None
     for fno, _, v in _fields(buf):
         if fno == 7:
@@ -160,6 +183,7 @@ def parse_model(buf: bytes) -> dict:
     if graph is None:
         raise ValueError("onnx: no graph in model")
     nodes, inits, inputs, outputs = [], {}, [], []
+    in_shapes: Dict[str, List[int]] = {}
     for fno, _, v in _fields(graph):
         if fno == 1:
             nodes.append(_parse_node(v))
@@ -168,10 +192,12 @@ def parse_model(buf: bytes) -> dict:
             inits[n] = a
         elif fno == 11:
             inputs.append(_value_info_name(v))
+            in_shapes[inputs[-1]] = _value_info_shape(v)
         elif fno == 12:
             outputs.append(_value_info_name(v))
     return {"nodes": nodes, "initializers": inits,
-            "inputs": [i for i in inputs if i not in inits], "outputs": outputs}
+            "inputs": [i for i in inputs if i not in inits], "outputs": outputs,
+            "input_shapes": {k: d for k, d in in_shapes.items() if k not in inits}}
 
 
 def load_model(path: str) -> dict:

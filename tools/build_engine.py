@@ -20,7 +20,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", choices=["resnet50", "resnet152", "mnist"])
     ap.add_argument("--prototxt")
-    ap.add_argument("--onnx", help="MNIST-style ONNX file (Conv/Add/Relu/MaxPool/Reshape/MatMul)")
+    ap.add_argument("--onnx", help="ONNX CNN classifier (Conv / BatchNormalization / Relu / Add / MaxPool / AveragePool / "
+                                   "GlobalAveragePool / Flatten / Reshape / Gemm / MatMul / Softmax), e.g. an ONNX-zoo ResNet")
     ap.add_argument("--precision", choices=["fp16", "fp32"], default="fp16")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--seed", type=int, default=0)
@@ -32,8 +33,8 @@ def main():
             net = graph.parse_prototxt(f.read())
         wts = weights.random_weights(net, a.seed)
     elif a.onnx:
-        from tensorrt_laboratory_b200 import onnx_lite
-        net, wts = onnx_lite.mnist_to_caffe_like(onnx_lite.load_model(a.onnx))
+        from tensorrt_laboratory_b200 import onnx_import, onnx_lite
+        net, wts = onnx_import.import_onnx(onnx_lite.load_model(a.onnx), name=os.path.splitext(os.path.basename(a.onnx))[0])
     elif a.model == "mnist":
         sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         from tests import helpers
