@@ -108,8 +108,11 @@ int b2_context_nb_launches(b2_context* c, int batch);
  * SIMT reference kernels instead of the tcgen05 path (debug); "bn"/"stages"/"splits" force the conv tile,
  * pipeline depth and split-K factor (0 = cost model); "pdl"=0/1 programmatic dependent launch (process-wide);
  * "pdl_trigger"=0/1 release point of the dependent kernel; "autotune"=0 (cost model) / 1 (latency) / N>=2 (N-stream
- * throughput, default 4) on-device tactic selection; "sps"=2 double-width pipeline stages; returns B2_EINVAL for
- * unknown keys.  Environment: B2_TUNE_CACHE=<file> persists tuned tactics across processes (timing cache). */
+ * throughput, default 4) on-device tactic selection; "sps"=2 double-width pipeline stages; tactic switches
+ * "halo"=1/-1 (3x3 halo kernel everywhere it applies / never; 0 = tuner decides), "ws"=1/N/-1 (persistent
+ * warp-specialised kernel), "cn"=2/4/-1 (cluster multicast of the activation tile), "fork"=0/1 (shortcut convolutions
+ * on a parallel graph branch); returns B2_EINVAL for unknown keys.  Every tactic computes bit-identical results.
+ * Environment: B2_TUNE_CACHE=<file> persists tuned tactics across processes (timing cache). */
 int b2_context_set_option(b2_context* c, const char* key, int value);
 
 /* per-layer device timing of one forward (serialised launches, CUDA events): fills up to `cap`
