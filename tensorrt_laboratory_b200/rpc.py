@@ -342,3 +342,108 @@ def build_inference_server(manager, model_name: str, address: str = "127.0.0.1:0
     executor = server.register_executor(Executor(executor_threads))
     executor.register_contexts(rpc, InferenceResources(manager, model_name), contexts)
     return server
+
+
+# ------------------------------------------------------------------------------------------------
+# replica router: one front port, N replica servers behind it
+# ------------------------------------------------------------------------------------------------
+class _PassThrough(grpc.GenericRpcHandler):
+    """Method-agnostic unary proxy: request and response travel as raw bytes, so any service can sit behind it."""
+
+    def __init__(self, router: "Router"):
+        self._router = router
+
+    def service(self, handler_call_details):
+        method = handler_call_details.method
+
+        def forward(request_bytes, grpc_ctx):
+            meta = tuple(grpc_ctx.invocation_metadata())
+            backend = self._router._pick(dict(meta))
+            try:
+                call = backend.channel.unary_unary(method)  # no (de)serializers: bytes in, bytes out
+                return call(request_bytes, metadata=tuple((k, v) for k, v in meta if not k.startswith(":") and k != "user-agent"))
+            except grpc.RpcError as e:
+                grpc_ctx.abort(e.code(), e.details())
+            finally:
+                backend.done()
+
+        return grpc.unary_unary_rpc_method_handler(forward)
+
+
+class _Backend:
+    def __init__(self, target: str):
+        self.target = target
+        self.channel = grpc.insecure_channel(target, options=[("grpc.max_receive_message_length", 64 << 20),
+                                                              ("grpc.max_send_message_length", 64 << 20)])
+        self.outstanding = 0
+        self.served = 0
+        self._lock = threading.Lock()
+
+    def take(self):
+        with self._lock:
+            self.outstanding += 1
+            self.served += 1
+
+    def done(self):
+        with self._lock:
+            self.outstanding -= 1
+
+
+class Router:
+    """Front end of a replica set: the role Envoy plays in the reference (examples/99_LoadBalancer/lb-envoy.j2
+    ``lb_policy: round_robin``; model-aware routing by the ``custom-metadata-model-name`` header,
+    examples/Deployment/RouteRequests).  One replica = one process per GPU serving on its own port; requests are
+    independent, so the router never touches payloads (no collective, no NCCL).
+
+    ``policy``: "round_robin" or "least_outstanding".  ``routes``: optional {model name: [backend targets]} consulted
+    when the request carries the routing header; unknown models fall back to the whole set."""
+
+    HEADER = "custom-metadata-model-name"
+
+    def __init__(self, backends, address: str = "127.0.0.1:0", policy: str = "round_robin", routes=None, threads: int = 16):
+        if policy not in ("round_robin", "least_outstanding"):
+            raise ValueError("policy must be round_robin or least_outstanding")
+        if not backends:
+            raise ValueError("a router needs at least one backend")
+        self.backends = [_Backend(t) for t in backends]
+        self._by_target = {b.target: b for b in self.backends}
+        self.policy = policy
+        self.routes = {m: [self._by_target[t] for t in ts] for m, ts in (routes or {}).items()}
+        self.address, self.threads = address, threads
+        self._next: Dict[int, int] = {}
+        self._lock = threading.Lock()
+        self._server = None
+        self.port = None
+
+    def _pick(self, metadata: Dict[str, str]) -> _Backend:
+        pool = self.routes.get(metadata.get(self.HEADER, ""), self.backends)
+        with self._lock:
+            if self.policy == "round_robin":
+                i = self._next.get(id(pool), 0)
+                self._next[id(pool)] = (i + 1) % len(pool)
+                b = pool[i]
+            else:
+                b = min(pool, key=lambda x: x.outstanding)
+            b.take()
+        return b
+
+    def async_start(self):
+        self._server = grpc.server(futures.ThreadPoolExecutor(max_workers=self.threads),
+                                   options=[("grpc.max_receive_message_length", 64 << 20), ("grpc.max_send_message_length", 64 << 20)])
+        self._server.add_generic_rpc_handlers((_PassThrough(self),))
+        self.port = self._server.add_insecure_port(self.address)
+        self._server.start()
+        return self
+
+    def served(self) -> Dict[str, int]:
+        return {b.target: b.served for b in self.backends}
+
+    def running(self) -> bool:
+        return self._server is not None
+
+    def shutdown(self):
+        if self._server is not None:
+            self._server.stop(grace=1.0).wait()
+            self._server = None
+        for b in self.backends:
+            b.channel.close()

@@ -84,6 +84,38 @@ def test_unknown_method_and_unregistered_contexts():
     server.shutdown()
 
 
+def test_router_spreads_requests_over_replicas_and_routes_by_model_header():
+    """Replica front end: round-robin over N backends like the reference's Envoy cluster, model-aware
+    routing by the `custom-metadata-model-name` header, least-outstanding as the alternative policy."""
+    servers = [rpc.build_echo_server(contexts=4).async_start() for _ in range(3)]
+    targets = [f"127.0.0.1:{s.port}" for s in servers]
+    router = rpc.Router(targets, routes={"flowers-152": targets[2:]}).async_start()
+    Input, Output = rpc.message("simple.Input"), rpc.message("simple.Output")
+    client = rpc.ClientUnary(f"127.0.0.1:{router.port}", "/simple.Inference/Compute", Input, Output)
+    outs = [client.enqueue(Input(batch_id=i)).result(timeout=30) for i in range(1, 91)]   # sequential: exact round robin
+    assert [o.batch_id for o in outs] == list(range(1, 91))
+    assert list(router.served().values()) == [30, 30, 30]
+    futs = [client.enqueue(Input(batch_id=i), headers={rpc.Router.HEADER: "flowers-152"}) for i in range(100, 120)]
+    assert sorted(f.result(timeout=30).batch_id for f in futs) == list(range(100, 120))
+    assert list(router.served().values()) == [30, 30, 50]                                  # the routed model has one replica
+    # errors of the backend travel through (unknown method), the router stays up
+    bad = rpc.ClientUnary(f"127.0.0.1:{router.port}", "/simple.Inference/Nope", Input, Output)
+    assert bad.enqueue(Input(batch_id=1), lambda i, o, s: s).result(timeout=30) == grpc.StatusCode.UNIMPLEMENTED
+    assert router.running()
+    lo = rpc.Router(targets, policy="least_outstanding").async_start()
+    c2 = rpc.ClientUnary(f"127.0.0.1:{lo.port}", "/simple.Inference/Compute", Input, Output)
+    futs = [c2.enqueue(Input(batch_id=i)) for i in range(60)]
+    assert sorted(f.result(timeout=30).batch_id for f in futs) == list(range(60))
+    assert sum(lo.served().values()) == 60 and min(lo.served().values()) > 0
+    for c in (client, bad, c2):
+        c.close()
+    router.shutdown(), lo.shutdown()
+    for s in servers:
+        s.shutdown()
+    with pytest.raises(ValueError):
+        rpc.Router([])
+
+
 @pytest.mark.gpu
 def test_inference_service_matches_direct_path(gpu):
     from tensorrt_laboratory_b200 import builder, capi, weights
