@@ -360,7 +360,7 @@ class _PassThrough(grpc.GenericRpcHandler):
             meta = tuple(grpc_ctx.invocation_metadata())
             backend = self._router._pick(dict(meta))
             try:
-                call = backend.channel.unary_unary(method)  # no (de)serializers: bytes in, bytes out
+                call = backend.call_for(method)  # no (de)serializers: bytes in, bytes out
                 return call(request_bytes, metadata=tuple((k, v) for k, v in meta if not k.startswith(":") and k != "user-agent"))
             except grpc.RpcError as e:
                 grpc_ctx.abort(e.code(), e.details())
@@ -378,6 +378,13 @@ class _Backend:
         self.outstanding = 0
         self.served = 0
         self._lock = threading.Lock()
+        self._calls: Dict[str, Callable] = {}
+
+    def call_for(self, method: str):
+        call = self._calls.get(method)
+        if call is None:
+            call = self._calls.setdefault(method, self.channel.unary_unary(method))
+        return call
 
     def take(self):
         with self._lock:
