@@ -549,7 +549,7 @@ class BatchedInferRunner {
     using future_type = std::shared_future<void>;
 
     BatchedInferRunner(std::shared_ptr<Model> model, std::shared_ptr<InferenceManager> resources,
-                       std::chrono::nanoseconds window = std::chrono::microseconds(2000), size_t workers = 2)
+                       std::chrono::nanoseconds window = std::chrono::microseconds(2000), size_t workers = 0)
         : m_Model(std::move(model)), m_Resources(std::move(resources)), m_Batches(std::make_shared<std::atomic<size_t>>(0)) {
         TRTLAB_CHECK(m_Model->GetInputBindingIds().size() == 1 && m_Model->GetOutputBindingIds().size() == 1)
             << "BatchedInferRunner handles single-input single-output models";
@@ -583,6 +583,9 @@ class BatchedInferRunner {
             release();
         };
         // every request carries one batch item, so "max requests per batch" == the model's max batch size
+        // a worker stays with its merged batch until the results are scattered: one per execution lane (+1 to overlap
+        // the host copies of the next batch) keeps every lane fed
+        if (workers == 0) workers = size_t(m_Resources->MaxExecConcurrency()) + 1;
         m_Dispatcher = std::make_unique<DispatcherType>(StandardBatcher<Request, standard_threads>(size_t(m_Model->GetMaxBatchSize())),
                                                         window, std::make_shared<ThreadPool>(workers),
                                                         std::make_shared<DeferredShortTaskPool>(), execute);
