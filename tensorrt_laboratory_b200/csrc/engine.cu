@@ -127,7 +127,19 @@ struct Binding {
     size_t item_bytes;
 };
 
-enum LKind { L_INPUT_CAST, L_CONV_TC, L_CONV_SIMT, L_MAXPOOL, L_AVGPOOL, L_FC, L_SOFTMAX, L_OUTPUT_CAST };
+enum LKind { L_INPUT_CAST, L_CONV_TC, L_CONV_SIMT, L_MAXPOOL, L_AVGPOOL, L_FC, L_SOFTMAX, L_OUTPUT_CAST, L_NET };
+
+// A run of consecutive tcgen05 convolution layers executed by ONE persistent kernel (net_kernel.cu): device-side layer
+// table, dependency ranges and arrival counters live in one allocation owned by the plan.
+struct NetRun {
+    b2k::NetArgs args{};
+    int ctas = 0;
+    int first_op = 0, last_op = 0;
+    void* d_blob = nullptr;
+    ~NetRun() {
+        if (d_blob) cudaFree(d_blob);
+    }
+};
 
 struct Launch {
     LKind kind;
@@ -142,11 +154,14 @@ struct Launch {
     int in_binding = -1, out_binding = -1;
     bool src_half = false;  // input cast: the binding is fp16
     int side_join = -1;     // see Op::side_join (launch index == op index)
+    std::shared_ptr<NetRun> net;  // L_NET
+    bool net_member = false;      // L_CONV_TC that build_plan folds into an L_NET launch
     int N = 0, C = 0, H = 0, W = 0, C_phys = 0, Ho = 0, Wo = 0, k = 0, stride = 0, pad = 0, K = 0, Cout = 0;
 };
 
 struct Plan {
     int batch = 0;
+    bool has_net = false;  // contains a persistent network kernel: a handful of launches, replayed directly (no graph)
     std::vector<Launch> launches;
 };
 
@@ -241,6 +256,11 @@ struct b2_context {
     int fork = 0;      // 1: run side branches (Op::side_join) on a forked stream / a parallel graph branch.  Off by default:
                        // measured neutral on B200 (0.476 ms either way, 4-context throughput within noise) -- the fork and
                        // join turn the programmatic (PDL) edges around them into full dependencies, which eats the overlap
+    int net = 0;       // 1: runs of 64-channel-block tcgen05 convolutions execute as ONE persistent kernel (net_kernel.cu).
+                       // Opt-in: bit-identical, but measured slower than the per-layer kernels at batch 8 (profiles/README.md, r2a-c)
+    int net_ctas = 0;  // CTAs of that kernel (0 = one per SM); a server running N contexts gives each about 148 / N
+    int net_bn = 0;    // force its N tile (64 / 128); 0 = 128 wherever the channel count allows
+    int net_stages = 0;  // force its shared-memory ring depth (2..4); 0 = the deepest that lets two CTAs share an SM
     cudaStream_t side = nullptr;
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
 };
@@ -398,8 +418,12 @@ void plan_arena(b2_engine* e) {
         Tensor& t = e->tensors[ti];
         if (t.last_use < t.def) t.last_use = t.def;
         const size_t size = align_up(t.item_bytes * e->max_batch, 1024);
-        // a buffer may be reused once its last reader has been launched BEFORE the new producer
-        live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.last < t.def; }), live.end());
+        // a buffer may be reused once its last reader has been launched BEFORE the new producer.  fp16 engines keep it
+        // two more ops: the persistent network kernel overlaps consecutive layers tile by tile, and a recycled buffer
+        // makes its new producer wait for the COMPLETION of every earlier layer that touched it -- with the slack those
+        // layers lie >= 3 ops back and are long finished when the producer's first tile is due.
+        const int slack = e->half() ? 2 : 0;
+        live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.last + slack < t.def; }), live.end());
         std::sort(live.begin(), live.end(), [](const Live& a, const Live& b) { return a.off < b.off; });
         size_t off = 0;
         for (const Live& l : live) {
@@ -829,6 +853,152 @@ void tune_cache_append(const b2_engine* e, int op, int batch, const ConvConfig& 
     fclose(f);
 }
 
+// ---- persistent-kernel runs ----------------------------------------------------------------------
+// Folds every maximal run of consecutive `net_member` convolution launches (launch index == op index here) into one
+// L_NET launch: layer table with the TMA maps already built by make_conv_launch, the input M-tile range every output
+// M tile depends on, and the layers whose completion a recycled output buffer has to wait for.
+int fuse_net_runs(b2_context* c, Plan* plan, int batch) {
+    b2_engine* e = c->e;
+    std::vector<Launch>& ls = plan->launches;
+    bool any = false;
+    for (const Launch& L : ls) any = any || L.net_member;
+    if (!any) return B2_OK;
+    std::vector<Launch> fused;
+    size_t i = 0;
+    while (i < ls.size()) {
+        if (!ls[i].net_member) {
+            fused.push_back(std::move(ls[i]));
+            ++i;
+            continue;
+        }
+        size_t j = i;
+        while (j + 1 < ls.size() && ls[j + 1].net_member && int(j + 1 - i) < b2k::kNetMaxLayers - 1) ++j;
+        const int n = int(j - i + 1);
+        std::vector<b2k::NetLayer> layers(n);
+        std::vector<short2> deps;
+        std::map<int, int> producer;  // tensor index -> local layer
+        int tile_cursor = 0, flag_cursor = 0;
+        double flops = 0, bytes = 0;
+        auto trange = [&](int ti, size_t* lo, size_t* hi) {
+            const Tensor& t = e->tensors[ti];
+            *lo = t.offset;
+            *hi = t.offset + t.item_bytes * size_t(batch);
+        };
+        for (int l = 0; l < n; ++l) {
+            const Op& op = e->ops[i + l];
+            const b2plan::OpRec& r = op.r;
+            const b2k::ConvLaunch& cl = ls[i + l].conv;
+            const b2k::ConvArgs& a = cl.args;
+            b2k::NetLayer& nl = layers[l];
+            memset(&nl, 0, sizeof nl);
+            nl.mapA = cl.mapA;
+            b2k::NetLayerInfo& f = nl.info;
+            f.wpacked = a.wpacked, f.bias = a.bias, f.out = a.out, f.residual = a.residual;
+            f.M = a.M, f.Cout = a.Cout, f.num_kblocks = a.num_kblocks, f.cblocks = a.cblocks;
+            f.kw = a.kw, f.HoWo = a.HoWo, f.Wo = a.Wo, f.stride_h = a.stride_h, f.stride_w = a.stride_w;
+            f.pad_h = a.pad_h, f.pad_w = a.pad_w, f.relu = a.relu, f.a_mode = a.a_mode;
+            f.bn = cl.bn, f.tiles_m = cl.grid_m, f.tiles_n = cl.grid_n;
+            f.tile_begin = tile_cursor, f.total_tiles = cl.grid_m * cl.grid_n;
+            tile_cursor += f.total_tiles;
+            f.out_flag_off = flag_cursor;
+            flag_cursor += f.tiles_m;
+            f.in_flag_off = f.res_flag_off = -1;
+            auto pin = producer.find(r.in);
+            if (pin != producer.end()) f.in_flag_off = layers[pin->second].info.out_flag_off, f.in_need = layers[pin->second].info.tiles_n;
+            if (r.res >= 0) {
+                auto pres = producer.find(r.res);
+                if (pres != producer.end())
+                    f.res_flag_off = layers[pres->second].info.out_flag_off, f.res_need = layers[pres->second].info.tiles_n;
+            }
+            // input M tiles read by each output M tile (a superset: whole rows once the window is clipped)
+            f.dep_off = int(deps.size());
+            const Tensor& ti = e->tensors[r.in];
+            const Tensor& to = e->tensors[r.out];
+            const int Hin = int(ti.h), Win = int(ti.w), Wo = int(to.w), HoWo = int(to.h * to.w);
+            const int in_tiles = (batch * Hin * Win + 127) / 128;
+            for (int mt = 0; mt < f.tiles_m; ++mt) {
+                const int m_lo = mt * 128, m_hi = std::min(m_lo + 127, f.M - 1);
+                const int n0 = m_lo / HoWo, p0 = (m_lo % HoWo) / Wo, q0 = m_lo % Wo;
+                const int n1 = m_hi / HoWo, p1 = (m_hi % HoWo) / Wo, q1 = m_hi % Wo;
+                int lr = p0 * op.sh() - op.ph(), lc = q0 * op.sw() - op.pw_lo();
+                if (lr < 0) lr = 0, lc = 0;
+                if (lc < 0) lc = 0;
+                int hr = p1 * op.sh() - op.ph() + op.kh() - 1, hc = q1 * op.sw() - op.pw_lo() + op.kw() - 1;
+                if (hr > Hin - 1) hr = Hin - 1, hc = Win - 1;
+                if (hc > Win - 1) hc = Win - 1;
+                const int lo = (n0 * Hin * Win + lr * Win + lc) / 128;
+                const int hi = std::min((n1 * Hin * Win + hr * Win + hc) / 128, in_tiles - 1);
+                deps.push_back(make_short2(short(lo), short(std::max(lo, hi))));
+            }
+            // recycled arena memory: every earlier layer of the run that read or wrote bytes this layer will overwrite
+            size_t olo, ohi;
+            trange(r.out, &olo, &ohi);
+            f.war_upto = -1;
+            for (int q = 0; q < l; ++q) {
+                const b2plan::OpRec& rq = e->ops[i + q].r;
+                for (int u : {rq.in, rq.res, rq.out}) {
+                    if (u < 0 || u == r.out || e->tensors[u].binding >= 0) continue;
+                    size_t ulo, uhi;
+                    trange(u, &ulo, &uhi);
+                    if (ulo < ohi && olo < uhi) f.war_upto = q;
+                }
+            }
+            producer[r.out] = l;
+            flops += ls[i + l].flops, bytes += ls[i + l].bytes;
+        }
+        for (int l = 0; l < n; ++l)
+            if (layers[l].info.tiles_m > 32767) return fail(B2_EINVAL, "layer too large for the persistent kernel (M tiles > 32767)");
+        auto run = std::make_shared<NetRun>();
+        const size_t off_layers = 0;
+        const size_t off_deps = align_up(off_layers + size_t(n) * sizeof(b2k::NetLayer), 256);
+        const size_t off_mt = align_up(off_deps + deps.size() * sizeof(short2), 256);
+        const size_t off_ld = off_mt + size_t(flag_cursor) * sizeof(int);
+        const size_t off_ctrl = off_ld + size_t(n) * sizeof(int);
+        const size_t total = off_ctrl + 2 * sizeof(int);
+        if (cudaMalloc(&run->d_blob, total) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B2_ENOMEM, "cudaMalloc(%zu) for the persistent-kernel tables failed", total);
+        }
+        uint8_t* d = static_cast<uint8_t*>(run->d_blob);
+        {   // on a private non-blocking stream: other threads may be capturing graphs, which forbids legacy-stream work
+            cudaStream_t up = nullptr;
+            B2_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+            cudaError_t ue = cudaMemsetAsync(d, 0, total, up);
+            if (ue == cudaSuccess) ue = cudaMemcpyAsync(d + off_layers, layers.data(), size_t(n) * sizeof(b2k::NetLayer), cudaMemcpyHostToDevice, up);
+            if (ue == cudaSuccess) ue = cudaMemcpyAsync(d + off_deps, deps.data(), deps.size() * sizeof(short2), cudaMemcpyHostToDevice, up);
+            if (ue == cudaSuccess) ue = cudaStreamSynchronize(up);
+            cudaStreamDestroy(up);
+            if (ue != cudaSuccess) return fail(B2_ECUDA, "upload of the persistent-kernel tables failed: %s", cudaGetErrorString(ue));
+        }
+        run->args.layers = reinterpret_cast<const b2k::NetLayer*>(d + off_layers);
+        run->args.deps = reinterpret_cast<const short2*>(d + off_deps);
+        run->args.mt_done = reinterpret_cast<int*>(d + off_mt);
+        run->args.layer_done = reinterpret_cast<int*>(d + off_ld);
+        run->args.ctrl = reinterpret_cast<int*>(d + off_ctrl);
+        run->args.n_layers = n, run->args.total_tiles = tile_cursor, run->args.n_flags = flag_cursor;
+        // ring depth: the deepest that still lets two CTAs share an SM (227 KiB less 1 KiB of system use per CTA)
+        int stages = c->net_stages > 0 ? c->net_stages : 4;
+        while (c->net_stages <= 0 && stages > 2 && 2 * (b2k::net_smem_bytes(n, stages) + 1024) > 227 * 1024) --stages;
+        run->args.stages = std::max(2, std::min(stages, 4));
+        const int per_sm = 2 * (b2k::net_smem_bytes(n, run->args.stages) + 1024) <= 227 * 1024 ? 2 : 1;
+        run->ctas = c->net_ctas > 0 ? c->net_ctas : 148 * per_sm;
+        run->ctas = std::max(1, std::min(run->ctas, std::min(148 * per_sm, tile_cursor)));
+        run->first_op = int(i), run->last_op = int(j);
+        Launch L;
+        L.kind = L_NET;
+        L.name = ls[i].name + ".." + ls[j].name;
+        L.flops = flops, L.bytes = bytes;
+        L.N = batch;
+        L.net = run;
+        fused.push_back(std::move(L));
+        i = j + 1;
+    }
+    for (Launch& L : fused) L.side_join = -1;  // launch indices no longer equal op indices: no forked side branches
+    ls = std::move(fused);
+    plan->has_net = true;
+    return B2_OK;
+}
+
 // ---- per-batch launch plan ---------------------------------------------------------------------
 int build_plan(b2_context* c, int batch, Plan** out) {
     b2_engine* e = c->e;
@@ -915,7 +1085,16 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                     if (c->force_cn > 1 && kbsz == 64 && cfg.ws == 0 && !cfg.halo && (int(r.cout_phys) / cfg.bn) % c->force_cn == 0) cfg.cn = c->force_cn;
                     const bool forced = c->force_bn || c->force_stages || c->force_splits || c->force_sps;
                     const int op_index = int(&op - &e->ops[0]);
-                    if (!forced && c->autotune) {
+                    // member of a persistent-kernel run: 64-channel K blocks, packed weights, 64 | Cout; no tactic to tune
+                    const bool net_ok = c->net && !forced && kbsz == 64 && (r.relu & 2) && !c->no_pack && r.cout_phys % 64 == 0 &&
+                                        c->force_ws <= 0 && c->force_cn <= 0 && c->force_halo <= 0 && !c->force_im2col;
+                    if (net_ok) {
+                        int bn = (r.cout_phys % 128 == 0) ? 128 : 64;
+                        if (c->net_bn == 64) bn = 64;
+                        cfg = ConvConfig{bn, 4, 1, 0.0, 1, 0, 1};
+                        cfg.halo = 0;
+                        L.net_member = true;
+                    } else if (!forced && c->autotune) {
                         bool have = false;
                         {
                             std::lock_guard<std::mutex> lock(e->tune_mutex);
@@ -1030,6 +1209,8 @@ int build_plan(b2_context* c, int batch, Plan** out) {
         }
         plan->launches.push_back(std::move(L));
     }
+    int rc = fuse_net_runs(c, plan.get(), batch);
+    if (rc) return rc;
     *out = plan.get();
     c->cur->plans[batch] = std::move(plan);
     return B2_OK;
@@ -1057,6 +1238,8 @@ int run_launch(const b2_engine* e, const Launch& L, void* const* bindings, cudaS
             return b2k::launch_fc(in, L.w, L.bias, static_cast<float*>(out), L.N, L.K, L.Cout, half, s);
         case L_SOFTMAX:
             return b2k::launch_softmax(static_cast<const float*>(in), static_cast<float*>(out), L.N, L.C, s);
+        case L_NET:
+            return b2k::launch_net_f16_tcgen05(L.net->args, L.net->ctas, s);
     }
     return int(cudaErrorInvalidValue);
 }
@@ -1154,6 +1337,7 @@ static int deserialize_impl(b2_runtime* rt, const void* blob, size_t nbytes, boo
             return fail(B2_ENODEVICE, "device %d is sm_%d%d; this library only carries sm_100a code", dev, prop.major, prop.minor);
         e->device = dev;
         rc = b2k::init_conv_kernels();
+        if (!rc) rc = b2k::init_net_kernel();
         if (rc) return fail(B2_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaError_t(rc)));
         const size_t bytes = std::max<size_t>(e->payload_bytes, 256);
         if (rt && rt->alloc) {
@@ -1242,6 +1426,10 @@ int b2_context_create(b2_engine* e, b2_context** out) {
     c->pdl_trigger = env_int("B2_PDL_TRIGGER", 1);
     c->autotune = env_int("B2_AUTOTUNE", 4);
     c->fork = env_int("B2_FORK", 0);
+    c->net = env_int("B2_NET", 0);
+    c->net_ctas = env_int("B2_NET_CTAS", 0);
+    c->net_bn = env_int("B2_NET_BN", 0);
+    c->net_stages = env_int("B2_NET_STAGES", 0);
     if (getenv("B2_PDL")) b2k::set_pdl(env_int("B2_PDL", 1) != 0);
     void* p = nullptr;
     if (cudaMalloc(&p, kMaxSplitTiles * sizeof(int)) != cudaSuccess || cudaMemset(p, 0, kMaxSplitTiles * sizeof(int)) != cudaSuccess) {
@@ -1300,6 +1488,10 @@ int b2_context_set_option(b2_context* c, const char* key, int value) {
     else if (k == "cn") c->force_cn = value;
     else if (k == "halo") c->force_halo = value;
     else if (k == "fork") c->fork = value;
+    else if (k == "net") c->net = value;
+    else if (k == "net_ctas") c->net_ctas = value;
+    else if (k == "net_bn") c->net_bn = value;
+    else if (k == "net_stages") c->net_stages = value;
     else if (k == "pdl_trigger") c->pdl_trigger = value;
     else if (k == "autotune") c->autotune = value;
     else if (k == "no_fold") c->no_fold = value;
@@ -1323,7 +1515,9 @@ int b2_context_enqueue(b2_context* c, int batch, void* const* bindings, b2_strea
     if ((rc = build_plan(c, batch, &plan))) return rc;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     B2_CUDA(cudaStreamIsCapturing(stream, &cap));
-    if (cap != cudaStreamCaptureStatusNone || !c->use_graph) {
+    // A plan with a persistent network kernel is a handful of launches: it is issued directly.  No captured graph means
+    // no per-(binding pointers) graph cache, no capture or instantiation on the request path.
+    if (cap != cudaStreamCaptureStatusNone || !c->use_graph || plan->has_net) {
         if ((rc = run_all(c, *plan, bindings, stream))) return rc;
     } else {
         b2_context::GraphKey key;
@@ -1416,11 +1610,39 @@ int b2_context_debug_conv_timing(b2_context* c, int batch, int i, int reps, b2_s
     return B2_OK;
 }
 
+// Debug aid (not part of the drop-in surface): one forward pass with the instrumented instantiation of the persistent
+// network kernel; `out` receives 8 roles x 8 int64 counters per CTA (see net_kernel.cu), `n_ctas` the CTA count.
+int b2_context_debug_net_timing(b2_context* c, int batch, void* const* bindings, b2_stream_t stream_, long long* out, int cap_ctas,
+                                int* n_ctas) {
+    Plan* plan = nullptr;
+    if (!c || build_plan(c, batch, &plan)) return fail(B2_EINVAL, "no plan");
+    NetRun* run = nullptr;
+    for (Launch& L : plan->launches)
+        if (L.kind == L_NET) run = L.net.get();
+    if (!run) return fail(B2_EINVAL, "the plan has no persistent network kernel");
+    if (n_ctas) *n_ctas = run->ctas;
+    if (run->ctas > cap_ctas) return fail(B2_EINVAL, "counter buffer too small (%d CTAs)", run->ctas);
+    long long* d = nullptr;
+    const size_t bytes = size_t(run->ctas) * 64 * sizeof(long long);
+    B2_CUDA(cudaMalloc(&d, bytes));
+    cudaMemset(d, 0, bytes);
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    run->args.dbg = d;
+    int rc = run_all(c, *plan, bindings, s);
+    cudaError_t se = cudaStreamSynchronize(s);
+    run->args.dbg = nullptr;
+    if (!rc && se == cudaSuccess) cudaMemcpy(out, d, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (rc) return rc;
+    if (se != cudaSuccess) return fail(B2_ECUDA, "debug launch failed: %s", cudaGetErrorString(se));
+    return B2_OK;
+}
+
 const char* b2_context_launch_name(b2_context* c, int batch, int i) {
     static thread_local std::string s;
     const Launch* L = get_launch(c, batch, i);
     if (!L) return nullptr;
-    static const char* kinds[] = {"input_cast", "conv_tcgen05", "conv_simt", "maxpool", "avgpool", "fc", "softmax", "output_cast"};
+    static const char* kinds[] = {"input_cast", "conv_tcgen05", "conv_simt", "maxpool", "avgpool", "fc", "softmax", "output_cast", "net_tcgen05"};
     s = std::string(kinds[L->kind]) + ":" + L->name;
     if (L->kind == L_CONV_TC)
         s += " bn=" + std::to_string(L->conv.bn) + " kb=" + std::to_string(L->conv.kb) +
@@ -1430,6 +1652,9 @@ const char* b2_context_launch_name(b2_context* c, int batch, int i) {
              (L->conv.args.a_mode == b2k::A_TILED ? " tiled" : " im2col") +
              " grid=" + std::to_string(L->conv.grid_n) + "x" + std::to_string(L->conv.grid_m) + "x" +
              std::to_string(L->conv.args.splits) + " kblk=" + std::to_string(L->conv.args.num_kblocks);
+    if (L->kind == L_NET)
+        s += " layers=" + std::to_string(L->net->args.n_layers) + " tiles=" + std::to_string(L->net->args.total_tiles) +
+             " ctas=" + std::to_string(L->net->ctas) + " stages=" + std::to_string(L->net->args.stages);
     if (L->side_join >= 0) s += " side";
     return s.c_str();
 }

@@ -386,7 +386,12 @@ void InferenceManager::RegisterModel(const std::string& name, std::shared_ptr<Mo
     model->SetName(name);
     m_Models[name] = model;
     auto pool = Pool<IExecutionContext>::Create();
-    for (uint32_t i = 0; i < max_concurrency * uint32_t(EnqueueDepth()); i++) pool->Push(model->CreateExecutionContext());
+    for (uint32_t i = 0; i < max_concurrency * uint32_t(EnqueueDepth()); i++) {
+        auto ctx = model->CreateExecutionContext();
+        // m_MaxExecutions forward passes share the GPU: each persistent network kernel gets its share of the 2 x 148 CTA slots
+        if (!getenv("B2_NET_CTAS")) b2_context_set_option(ctx->handle, "net_ctas", std::max(1, 296 / std::max(1, m_MaxExecutions)));
+        pool->Push(std::move(ctx));
+    }
     m_ModelExecutionContexts[model.get()] = pool;
 }
 

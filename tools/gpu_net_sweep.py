@@ -1,0 +1,30 @@
+"""Device-resident throughput of the persistent network kernel against the per-layer kernels (4 contexts, RN50 b=8)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tensorrt_laboratory_b200 import builder, capi, weights  # noqa: E402
+
+BATCH = int(os.environ.get("SWEEP_BATCH", "8"))
+steps = int(os.environ.get("SWEEP_STEPS", "400"))
+blob = builder.build_resnet_plan(int(os.environ.get("SWEEP_DEPTH", "50")), builder.PREC_FP16, BATCH, seed=0)
+ring = weights.synthetic_input(BATCH, seed=1234, ring=32)
+settings = sys.argv[1:] or ["net=0", "net=1,ctas=37", "net=1,ctas=48", "net=1,ctas=74", "net=1,ctas=148", "net=1,ctas=37,bn=64",
+                            "ctx=1,net=0", "ctx=1,net=1,ctas=148", "ctx=1,net=1,ctas=74", "ctx=2,net=1,ctas=74", "ctx=8,net=1,ctas=18",
+                            "ctx=8,net=1,ctas=37"]
+for st in settings:
+    kv = dict(x.split("=") for x in st.split(","))
+    os.environ["B2_NET"] = kv.get("net", "1")
+    os.environ.pop("B2_NET_CTAS", None)
+    os.environ.pop("B2_NET_BN", None)
+    if "ctas" in kv:
+        os.environ["B2_NET_CTAS"] = kv["ctas"]
+    if "bn" in kv:
+        os.environ["B2_NET_BN"] = kv["bn"]
+    ctx = int(kv.get("ctx", "4"))
+    try:
+        ms, nl = capi.device_throughput(blob, ctx, BATCH, steps, 40, ring)
+        print(json.dumps({"setting": st, "img_per_s": steps * BATCH / (ms * 1e-3), "ms_per_step": ms / steps, "launches": nl}), flush=True)
+    except Exception as ex:  # keep sweeping
+        print(json.dumps({"setting": st, "error": str(ex)}), flush=True)
