@@ -104,6 +104,20 @@ int b2_context_enqueue(b2_context* c, int batch, void* const* bindings, b2_strea
                        b2_event_t input_consumed);
 /* number of kernels one enqueue at `batch` launches (for reporting) */
 int b2_context_nb_launches(b2_context* c, int batch);
+
+/* ---- ahead-of-time work (the role of TensorRT's builder / trtexec, reference models/setup.py:53-55): tactic selection
+ * and graph instantiation happen at model-registration time, never inside b2_context_enqueue. ---- */
+/* Times the kernel tactics of every convolution on THIS device, on a private arena, at max batch (and at every batch
+ * size 1..max when `all_batches` != 0) with `streams` concurrent streams (0 = default 4); results are kept on the engine.
+ * No-op for fp32 engines and for plans that carry a tactic table.  Untuned engines run on a closed-form cost model. */
+int b2_engine_tune(b2_engine* e, int streams, int all_batches);
+int b2_engine_nb_tactics(const b2_engine* e);
+/* exports the tactic table, 10 x uint32 per record {op, batch, bn, stages, splits, sps, ws, cn, halo, 0} (the TacticRec
+ * layout of the plan format); builder.attach_tactics() appends it to a plan blob.  Returns the records written. */
+int b2_engine_get_tactics(const b2_engine* e, uint32_t* out, int cap_records);
+/* Builds the launch plan of `batch` for the context's current device memory and instantiates its CUDA-graph segments
+ * (one graph per context and batch, independent of the binding pointers).  `stream` may be NULL. */
+int b2_context_prepare(b2_context* c, int batch, b2_stream_t stream);
 /* knobs: "graph"=0/1 replay the forward as a cached CUDA graph (default 1); "simt"=0/1 force the
  * SIMT reference kernels instead of the tcgen05 path (debug); "bn"/"stages"/"splits" force the conv tile,
  * pipeline depth and split-K factor (0 = cost model); "pdl"=0/1 programmatic dependent launch (process-wide);

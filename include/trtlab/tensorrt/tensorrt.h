@@ -335,10 +335,11 @@ class ExecutionContext {
     // a lane: their forward passes are ordered ON THE DEVICE (cudaStreamWaitEvent), so the host can enqueue request
     // n+1 of a lane while request n still runs and the lane never waits for a host round trip between requests.
     struct Lane {
-        explicit Lane(size_t workspace_bytes);
+        explicit Lane(size_t workspace_bytes, int index = 0);
         ~Lane();
         void* workspace;
         size_t bytes;
+        int index;              // position among the manager's lanes (engine-side contexts are pinned to a lane)
         std::mutex mutex;
         cudaEvent_t last_done;  // nullptr until the lane has been used
     };
@@ -356,6 +357,8 @@ class ExecutionContext {
     // fiber-friendly variant: 0 when done, 1 while running (cuda_sync<userspace_threads>, sync.h:19-47)
     int Query();
     void Reset();
+    int LaneIndex() const { return m_Lane->index; }
+    void* Workspace() const { return m_Lane->workspace; }
 
   private:
     std::shared_ptr<IExecutionContext> m_Context;
@@ -422,7 +425,13 @@ class InferenceManager : public ::trtlab::Resources {
     Runtime* m_ActiveRuntime;
     std::map<std::string, std::unique_ptr<ThreadPool>> m_ThreadPools;
     std::map<std::string, std::shared_ptr<Model>> m_Models;
-    std::map<const Model*, std::shared_ptr<Pool<IExecutionContext>>> m_ModelExecutionContexts;
+    // Engine-side contexts per model.  When the model may use every lane (the default) there is ONE POOL PER LANE with
+    // EnqueueDepth() contexts each: a context then only ever meets its lane's activation arena, so its launch plans and
+    // CUDA graphs (one per batch size) can all be built in AllocateResources() -- nothing is captured, instantiated or
+    // tuned on the request path.  A model with capped concurrency keeps the reference's single shared pool.
+    std::map<const Model*, std::vector<std::shared_ptr<Pool<IExecutionContext>>>> m_ModelExecutionContexts;
+    std::vector<std::shared_ptr<ExecutionContext::Lane>> m_Lanes;
+    void PrepareModel(const Model* model);
 };
 
 // ------------------------------------------------------------------------------------------------

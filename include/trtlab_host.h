@@ -41,6 +41,15 @@ int trt_manager_bench(trt_manager* m, const char* model, int batch, double secon
                       double* results16, double* latencies, size_t lat_cap, size_t* lat_count);
 /* TimedBenchmarkWorkspace::enqueue_pipeline averaged over iters */
 int trt_timed_pipeline(const void* blob, size_t nbytes, int iters, float* h2d_ms, float* compute_ms, float* d2h_ms);
+/* v2 surface: BenchmarkWorkspace (caller-captured graph of the forward pass, reference workspace.cc:21-124) at max batch:
+ * pinned input -> async_h2d -> enqueue() -> async_d2h, `iters` times; returns the output of the last pass.
+ * managed_runtime != 0: weights through ManagedRuntime (cudaMallocManaged + ReadMostly, allocator.cc:72-77) */
+int trt_workspace_infer(const void* blob, size_t nbytes, const void* input, size_t input_bytes, void* output,
+                        size_t output_bytes, int managed_runtime, int iters);
+/* the v1 hot path by hand over CyclicBuffers<CudaPinnedHostMemory, CudaDeviceMemory> (buffers.h:122-154): `rounds`
+ * requests cut from a 3-segment ring (which therefore wraps); output and device time of the last request */
+int trt_cyclic_infer(const void* blob, size_t nbytes, int batch, const void* input, size_t input_bytes, void* output,
+                     size_t output_bytes, int managed_runtime, int rounds, double* compute_seconds);
 /* device-resident throughput of `contexts` concurrent execution contexts (inputs cycled through a device ring) */
 int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int batch, int steps, int warmup,
                           const void* host_ring, int ring_batches, double* elapsed_ms, int* launches_per_step);

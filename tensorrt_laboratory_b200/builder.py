@@ -271,3 +271,20 @@ def single_conv_net(cin: int, h: int, w: int, cout: int, k: int, stride: int, pa
         L.append(dict(name="relu", type="ReLU", bottoms=[top], tops=[top]))
     return {"name": f"conv{k}x{k}s{stride}_{cin}x{h}x{w}_{cout}", "input": "data", "input_dims": [1, cin, h, w],
             "layers": L}
+
+
+def attach_tactics(blob: bytes, tactics: np.ndarray) -> bytes:
+    """Append a tactic table (``capi.Engine.tactics()`` after ``Engine.tune()``: [n, 10] uint32 records
+    {op, batch, bn, stages, splits, sps, ws, cn, halo, 0}) to a plan blob -- the role of the tactics a TensorRT plan file
+    carries (reference models/setup.py:53-55: trtexec tunes offline).  An engine deserialized from the result never tunes."""
+    tactics = np.ascontiguousarray(tactics, dtype=np.uint32).reshape(-1, 10)
+    hdr = list(_HEADER.unpack_from(blob, 0))
+    base = blob
+    old_n, _, old_off = struct.unpack_from("<IIQ", blob, _HEADER.size - 16)
+    if old_n:  # replace an existing table
+        base = blob[:old_off]
+    off = (len(base) + 63) // 64 * 64
+    out = bytearray(base) + bytes(off - len(base)) + tactics.tobytes()
+    struct.pack_into("<IIQ", out, _HEADER.size - 16, tactics.shape[0], 0, off)
+    del hdr
+    return bytes(out)

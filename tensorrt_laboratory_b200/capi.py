@@ -47,6 +47,10 @@ SYMBOLS = [
     ("b2_context_enqueue", _I, [_VP, _I, _PVP, _VP, _VP]),
     ("b2_context_nb_launches", _I, [_VP, _I]),
     ("b2_context_set_option", _I, [_VP, _S, _I]),
+    ("b2_engine_tune", _I, [_VP, _I, _I]),
+    ("b2_engine_nb_tactics", _I, [_VP]),
+    ("b2_engine_get_tactics", _I, [_VP, C.POINTER(C.c_uint32), _I]),
+    ("b2_context_prepare", _I, [_VP, _I, _VP]),
     ("b2_context_profile", _I, [_VP, _I, _PVP, _VP, C.POINTER(C.c_float), _I]),
     ("b2_context_launch_name", _S, [_VP, _I, _I]),
     ("b2_context_launch_flops", _D, [_VP, _I, _I]),
@@ -91,6 +95,8 @@ SYMBOLS = [
     ("trt_manager_bench", _I, [_VP, _S, _I, _D, _SZ, C.POINTER(_D), C.POINTER(_D), _SZ, C.POINTER(_SZ)]),
     ("trt_timed_pipeline", _I, [_VP, _SZ, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("trt_device_throughput", _I, [_VP, _SZ, _I, _I, _I, _I, _VP, _I, C.POINTER(_D), C.POINTER(_I)]),
+    ("trt_workspace_infer", _I, [_VP, _SZ, _VP, _SZ, _VP, _SZ, _I, _I]),
+    ("trt_cyclic_infer", _I, [_VP, _SZ, _I, _VP, _SZ, _VP, _SZ, _I, _I, C.POINTER(_D)]),
 ]
 
 NP_DTYPES = {0: np.float32, 1: np.float16, 2: np.int8, 3: np.int32}  # B2_DT_* (same order as utils.cc:40-46)
@@ -277,6 +283,19 @@ class Engine:
     def weights_size(self) -> int:
         return self._lib.b2_engine_weights_size(self.handle)
 
+    def tune(self, streams: int = 0, all_batches: bool = False) -> int:
+        """Time the kernel tactics on this device now (model-registration time), never on the request path.
+        -> number of tactics the engine holds."""
+        check(self._lib.b2_engine_tune(self.handle, int(streams), 1 if all_batches else 0))
+        return self._lib.b2_engine_nb_tactics(self.handle)
+
+    def tactics(self) -> np.ndarray:
+        """[n, 10] uint32: {op, batch, bn, stages, splits, sps, ws, cn, halo, 0} -- builder.attach_tactics() input."""
+        n = self._lib.b2_engine_nb_tactics(self.handle)
+        out = np.zeros((max(n, 1), 10), np.uint32)
+        got = self._lib.b2_engine_get_tactics(self.handle, out.ctypes.data_as(C.POINTER(C.c_uint32)), n)
+        return out[:got]
+
     def flops(self, batch: int) -> float:
         return self._lib.b2_engine_flops(self.handle, batch)
 
@@ -374,6 +393,10 @@ class Session:
 
     def nb_launches(self, batch: int) -> int:
         return self._lib.b2_context_nb_launches(self.ctx, batch)
+
+    def prepare(self, batch: int):
+        """Build the launch plan and instantiate its graph segments ahead of the first request."""
+        check(self._lib.b2_context_prepare(self.ctx, batch, self.stream.handle))
 
     def close(self):
         if self.ctx and self.ctx.value:
@@ -493,3 +516,32 @@ def device_throughput(blob: bytes, contexts: int, batch: int, steps: int, warmup
     check(load().trt_device_throughput(blob, len(blob), contexts, batch, steps, warmup, ring.ctypes.data,
                                        ring.shape[0], C.byref(ms), C.byref(nl)))
     return ms.value, nl.value
+
+
+def _single_io(blob: bytes):
+    meta = Engine(blob, inspect_only=True)
+    ins = [b for b in meta.bindings if b["is_input"]]
+    outs = [b for b in meta.bindings if not b["is_input"]]
+    if len(ins) != 1 or len(outs) != 1:
+        raise ValueError("single-input single-output engines only")
+    return meta, ins[0], outs[0]
+
+
+def workspace_infer(blob: bytes, x: np.ndarray, managed_runtime: bool = False, iters: int = 2) -> np.ndarray:
+    """v2 surface: BenchmarkWorkspace at max batch (caller-captured graph); ``x``: [max_batch, C, H, W]."""
+    meta, i, o = _single_io(blob)
+    x = np.ascontiguousarray(x, dtype=i["np_dtype"])
+    out = np.zeros((meta.max_batch,) + o["shape"], o["np_dtype"])
+    check(load().trt_workspace_infer(blob, len(blob), x.ctypes.data, x.nbytes, out.ctypes.data, out.nbytes, int(managed_runtime), iters))
+    return out
+
+
+def cyclic_infer(blob: bytes, x: np.ndarray, managed_runtime: bool = False, rounds: int = 7):
+    """The v1 hot path by hand over CyclicBuffers<CudaPinnedHostMemory, CudaDeviceMemory>; -> (output, device seconds)."""
+    meta, i, o = _single_io(blob)
+    x = np.ascontiguousarray(x, dtype=i["np_dtype"])
+    out = np.zeros((x.shape[0],) + o["shape"], o["np_dtype"])
+    sec = _D()
+    check(load().trt_cyclic_infer(blob, len(blob), x.shape[0], x.ctypes.data, x.nbytes, out.ctypes.data, out.nbytes, int(managed_runtime),
+                                  rounds, C.byref(sec)))
+    return out, sec.value

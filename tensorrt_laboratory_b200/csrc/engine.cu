@@ -127,7 +127,7 @@ struct Binding {
     size_t item_bytes;
 };
 
-enum LKind { L_INPUT_CAST, L_CONV_TC, L_CONV_SIMT, L_MAXPOOL, L_AVGPOOL, L_FC, L_SOFTMAX, L_OUTPUT_CAST, L_NET };
+enum LKind { L_INPUT_CAST, L_CONV_TC, L_CONV_SIMT, L_MAXPOOL, L_AVGPOOL, L_FC, L_SOFTMAX, L_OUTPUT_CAST, L_NET, L_TAIL };
 
 // A run of consecutive tcgen05 convolution layers executed by ONE persistent kernel (net_kernel.cu): device-side layer
 // table, dependency ranges and arrival counters live in one allocation owned by the plan.
@@ -155,14 +155,28 @@ struct Launch {
     bool src_half = false;  // input cast: the binding is fp16
     int side_join = -1;     // see Op::side_join (launch index == op index)
     std::shared_ptr<NetRun> net;  // L_NET
+    b2k::TailArgs tail{};         // L_TAIL: pool + fc + softmax in one launch (out = the output binding)
     bool net_member = false;      // L_CONV_TC that build_plan folds into an L_NET launch
     int N = 0, C = 0, H = 0, W = 0, C_phys = 0, Ho = 0, Wo = 0, k = 0, stride = 0, pad = 0, K = 0, Cout = 0;
 };
 
+// A maximal run of launches that touch no binding: captured ONCE per plan (= per context, arena and batch) into a CUDA
+// graph that is valid for any binding pointers.  Launches that read or write a binding (the input cast, the classifier
+// tail, output casts) are issued directly around it, so the engine never captures or instantiates per Buffers object.
+struct Segment {
+    int begin = 0, end = 0;  // [begin, end) launch indices
+    bool graphable = false;
+    cudaGraphExec_t exec = nullptr;
+};
 struct Plan {
     int batch = 0;
     bool has_net = false;  // contains a persistent network kernel: a handful of launches, replayed directly (no graph)
     std::vector<Launch> launches;
+    std::vector<Segment> segments;
+    ~Plan() {
+        for (Segment& sg : segments)
+            if (sg.exec) cudaGraphExecDestroy(sg.exec);
+    }
 };
 
 }  // namespace
@@ -218,23 +232,19 @@ struct b2_engine {
     std::mutex tune_run_mutex;  // serialises on-device tactic timing across contexts of this engine
     std::map<std::pair<int, int>, ConvConfig> tuned;  // (op index, batch) -> measured-best configuration
     bool tune_cache_loaded = false;
+    bool tactics_from_plan = false;  // the blob carried a tactic table: nothing left to tune
+    bool tuned_at_load = false;      // b2_engine_tune has run
     bool half() const { return precision == B2_PREC_FP16; }
 };
 
 struct b2_context {
     b2_engine* e = nullptr;
     uint8_t* scratch = nullptr;
-    struct GraphKey {
-        int batch;
-        std::vector<void*> ptrs;
-        bool operator<(const GraphKey& o) const { return batch != o.batch ? batch < o.batch : ptrs < o.ptrs; }
-    };
-    // Launch plans (TMA maps embed arena addresses) and captured graphs are cached PER SCRATCH pointer: the
-    // reference pairs a pooled IExecutionContext with whichever pooled activation block the request drew
-    // (inference_manager.cc:254-273), so the same context sees several scratch pointers over its life.
+    // Launch plans (TMA maps embed arena addresses) and their captured graph segments are cached PER SCRATCH pointer:
+    // the reference pairs a pooled IExecutionContext with whichever pooled activation block the request drew
+    // (inference_manager.cc:254-273), so the same context may see several scratch pointers over its life.
     struct ScratchState {
         std::map<int, std::unique_ptr<Plan>> plans;
-        std::map<GraphKey, cudaGraphExec_t> graphs;
     };
     std::map<uint8_t*, ScratchState> states;
     ScratchState* cur = nullptr;
@@ -261,6 +271,8 @@ struct b2_context {
     int net_ctas = 0;  // CTAs of that kernel (0 = one per SM); a server running N contexts gives each about 148 / N
     int net_bn = 0;    // force its N tile (64 / 128); 0 = 128 wherever the channel count allows
     int net_stages = 0;  // force its shared-memory ring depth (2..4); 0 = the deepest that lets two CTAs share an SM
+    int fuse_tail = 1;   // global average pool + FC + softmax as one launch (tail_f16_kernel)
+    int* d_tail_ctrl = nullptr;  // its ticket / arrival counters (zero between launches)
     cudaStream_t side = nullptr;
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
 };
@@ -370,6 +382,19 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
         }
         b.item_bytes = n * (r.dtype == B2_DT_HALF ? 2 : 4);
         e->bindings.push_back(b);
+    }
+    if (h.n_tactics) {  // tactic table written by an offline tuning run (b2_engine_get_tactics -> builder.attach_tactics)
+        if (h.tactics_offset > nbytes || size_t(h.n_tactics) > (nbytes - h.tactics_offset) / sizeof(TacticRec))
+            return fail(B2_EINVAL, "plan: tactic table outside the blob");
+        for (uint32_t i = 0; i < h.n_tactics; ++i) {
+            TacticRec t;
+            memcpy(&t, base + h.tactics_offset + size_t(i) * sizeof(TacticRec), sizeof t);
+            if (t.op >= h.n_ops || t.batch == 0 || t.batch > h.max_batch) return fail(B2_EINVAL, "plan: tactic %u out of range", i);
+            ConvConfig cfg{int(t.bn), int(t.stages), int(t.splits), 0.0, int(t.sps), int(t.ws), int(t.cn)};
+            cfg.halo = int(t.halo);
+            e->tuned[{int(t.op), int(t.batch)}] = cfg;
+        }
+        e->tactics_from_plan = true;
     }
     *payload = base + h.payload_offset;
     return B2_OK;
@@ -853,6 +878,54 @@ void tune_cache_append(const b2_engine* e, int op, int batch, const ConvConfig& 
     fclose(f);
 }
 
+// Can `cfg` (possibly measured at another batch size) run `op` at `batch`?
+bool tactic_applies(const b2_context* c, const Op& op, int batch, const ConvConfig& cfg) {
+    const b2plan::OpRec& r = op.r;
+    if (cfg.bn <= 0 || int(r.cout_phys) % cfg.bn) return false;
+    const int kbsz = conv_kb(c, op);
+    if (cfg.halo) return conv_halo_rows(c, op) > 0 && b2k::conv_halo_config_exists(cfg.bn);
+    if (cfg.ws) return kbsz == 64 && b2k::conv_ws_config_exists(cfg.bn, cfg.stages, cfg.sps);
+    if (!b2k::conv_config_exists(cfg.bn, kbsz, cfg.stages, cfg.sps)) return false;
+    if (cfg.splits > 1) {
+        const int tiles = ((batch * int(c->e->tensors[r.out].h * c->e->tensors[r.out].w) + 127) / 128) * (int(r.cout_phys) / cfg.bn);
+        if (tiles > kMaxSplitTiles || size_t(tiles) * cfg.splits * 128 * cfg.bn * 4 > kSplitWorkspaceBytes) return false;
+    }
+    return true;
+}
+
+// Times the tactics of every tcgen05 convolution of the engine at `batch` (and, first, at max batch: the split-K factor
+// is chosen once there) on a context with a PRIVATE arena -- never on memory a request may be using.
+int tune_engine_batch(b2_context* c, int batch) {
+    b2_engine* e = c->e;
+    for (size_t i = 0; i < e->ops.size(); ++i) {
+        const Op& op = e->ops[i];
+        const b2plan::OpRec& r = op.r;
+        if (r.type != b2plan::OP_CONV || !e->half()) continue;
+        const bool kb64 = r.cin_phys % 64 == 0, kb8 = r.cin_phys == 8;
+        if (!((kb64 || kb8) && r.cout_phys % 32 == 0 && (kb64 || r.taps_phys % 2 == 0))) continue;
+        {
+            std::lock_guard<std::mutex> lock(e->tune_mutex);
+            if (e->tuned.count({int(i), batch})) continue;
+        }
+        const Tensor& to = e->tensors[r.out];
+        const int kbsz = conv_kb(c, op), nkb = conv_num_kblocks(c, op);
+        const bool side = op.side_join >= 0;
+        int splits = side ? 1 : 0;
+        if (batch != e->max_batch && !side) {
+            std::lock_guard<std::mutex> lock(e->tune_mutex);
+            auto it = e->tuned.find({int(i), e->max_batch});
+            if (it != e->tuned.end()) splits = it->second.splits;
+        }
+        ConvConfig cfg = pick_conv_config(batch * int(to.h) * int(to.w), int(r.cout_phys), nkb, kbsz, r.res >= 0, c, false);
+        int rc = autotune_conv(c, op, batch, splits, -1, &cfg);
+        if (rc) return rc;
+        std::lock_guard<std::mutex> lock(e->tune_mutex);
+        e->tuned[{int(i), batch}] = cfg;
+        tune_cache_append(e, int(i), batch, cfg);
+    }
+    return B2_OK;
+}
+
 // ---- persistent-kernel runs ----------------------------------------------------------------------
 // Folds every maximal run of consecutive `net_member` convolution launches (launch index == op index here) into one
 // L_NET launch: layer table with the TMA maps already built by make_conv_launch, the input M-tile range every output
@@ -999,6 +1072,35 @@ int fuse_net_runs(b2_context* c, Plan* plan, int batch) {
     return B2_OK;
 }
 
+// global average pool -> FC -> softmax (the classifier tail) as one launch; the pooled tensor and the logits vector of
+// the plan serve as its scratch, so tapping them as outputs still works.
+void fuse_tail(b2_context* c, Plan* plan, int batch) {
+    if (!c->fuse_tail || !c->e->half()) return;
+    std::vector<Launch>& ls = plan->launches;
+    for (size_t i = 0; i + 2 < ls.size(); ++i) {
+        const Launch &P = ls[i], &F = ls[i + 1], &S = ls[i + 2];
+        if (P.kind != L_AVGPOOL || F.kind != L_FC || S.kind != L_SOFTMAX) continue;
+        if (F.in != P.out || S.in != F.out || F.out_binding >= 0 || S.in_binding >= 0 || S.out_binding < 0 || P.C_phys % 8) continue;
+        if (F.K != P.C_phys || S.C != F.Cout || !b2k::tail_f16_applies(batch, P.H * P.W, P.C_phys, F.Cout)) continue;
+        Launch T;
+        T.kind = L_TAIL;
+        T.name = P.name + "+" + F.name + "+" + S.name;
+        T.N = batch;
+        T.flops = F.flops, T.bytes = P.bytes + F.bytes + S.bytes;
+        T.out_binding = S.out_binding;
+        T.tail.in = static_cast<const __half*>(P.in);
+        T.tail.w = static_cast<const __half*>(F.w);
+        T.tail.bias = F.bias;
+        T.tail.pooled = static_cast<__half*>(P.out);
+        T.tail.logits = static_cast<float*>(F.out);
+        T.tail.ctrl = c->d_tail_ctrl;
+        T.tail.N = batch, T.tail.HW = P.H * P.W, T.tail.C = P.C_phys, T.tail.Cout = F.Cout;
+        ls[i] = std::move(T);
+        ls.erase(ls.begin() + long(i) + 1, ls.begin() + long(i) + 3);  // (launches before i keep their indices: side joins stay valid)
+        return;
+    }
+}
+
 // ---- per-batch launch plan ---------------------------------------------------------------------
 int build_plan(b2_context* c, int batch, Plan** out) {
     b2_engine* e = c->e;
@@ -1095,50 +1197,15 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                         cfg.halo = 0;
                         L.net_member = true;
                     } else if (!forced && c->autotune) {
-                        bool have = false;
-                        {
-                            std::lock_guard<std::mutex> lock(e->tune_mutex);
-                            tune_cache_load(e);
-                            auto it = e->tuned.find({op_index, batch});
-                            if (it != e->tuned.end()) cfg = it->second, have = true;
-                        }
-                        std::unique_lock<std::mutex> run_lock(e->tune_run_mutex, std::defer_lock);
-                        if (!have) {  // one context tunes at a time; the others then find the result cached
-                            run_lock.lock();
-                            std::lock_guard<std::mutex> lock(e->tune_mutex);
-                            auto it = e->tuned.find({op_index, batch});
-                            if (it != e->tuned.end()) cfg = it->second, have = true;
-                        }
-                        if (!have) {
-                            // The split-K factor fixes the fp32 summation order, so it is chosen ONCE, at max batch,
-                            // and reused for every batch size: an image's result does not depend on its batch.
-                            // (a side-branch op runs concurrently with its neighbours and must not share the split-K
-                            // workspace / arrival counters with them: it never splits)
-                            const bool side = op.side_join >= 0;
-                            int splits = side ? 1 : 0, halo = -1;
-                            if (batch != e->max_batch && !side) {
-                                ConvConfig top = cfg;
-                                bool have_top = false;
-                                {
-                                    std::lock_guard<std::mutex> lock(e->tune_mutex);
-                                    auto it = e->tuned.find({op_index, e->max_batch});
-                                    if (it != e->tuned.end()) top = it->second, have_top = true;
-                                }
-                                if (!have_top) {
-                                    int rc = autotune_conv(c, op, e->max_batch, 0, -1, &top);
-                                    if (rc) return rc;
-                                    std::lock_guard<std::mutex> lock(e->tune_mutex);
-                                    e->tuned[{op_index, e->max_batch}] = top;
-                                    tune_cache_append(e, op_index, e->max_batch, top);
-                                }
-                                splits = top.splits;
-                            }
-                            int rc = autotune_conv(c, op, batch, splits, halo, &cfg);
-                            if (rc) return rc;
-                            std::lock_guard<std::mutex> lock(e->tune_mutex);
-                            e->tuned[{op_index, batch}] = cfg;
-                            tune_cache_append(e, op_index, batch, cfg);
-                        }
+                        // Tactics are measured ahead of time (b2_engine_tune at model registration, or the table the plan
+                        // blob carries) -- never here, on the request path.  A batch size that was not tuned itself uses
+                        // the max-batch tactic (every tactic is valid for every batch; the split-K factor is shared by
+                        // construction, so an image's result does not depend on its batch); no entry at all = cost model.
+                        std::lock_guard<std::mutex> lock(e->tune_mutex);
+                        tune_cache_load(e);
+                        auto it = e->tuned.find({op_index, batch});
+                        if (it == e->tuned.end()) it = e->tuned.find({op_index, e->max_batch});
+                        if (it != e->tuned.end() && tactic_applies(c, op, batch, it->second)) cfg = it->second;
                     }
                     if (op.side_join >= 0 && cfg.splits > 1) cfg.splits = 1;  // forced / cached tactic on a side-branch op
                     int rc = make_conv_launch(c, op, batch, cfg, &L.conv);
@@ -1211,6 +1278,22 @@ int build_plan(b2_context* c, int batch, Plan** out) {
     }
     int rc = fuse_net_runs(c, plan.get(), batch);
     if (rc) return rc;
+    fuse_tail(c, plan.get(), batch);
+    {   // split into binding-dependent launches and binding-independent (graphable) runs
+        const std::vector<Launch>& ls = plan->launches;
+        size_t i = 0;
+        while (i < ls.size()) {
+            const bool dep = ls[i].in_binding >= 0 || ls[i].out_binding >= 0;
+            size_t j = i + 1;
+            if (!dep)
+                while (j < ls.size() && ls[j].in_binding < 0 && ls[j].out_binding < 0) ++j;
+            Segment sg;
+            sg.begin = int(i), sg.end = int(j);
+            sg.graphable = !dep && (j - i) >= 3 && !plan->has_net;
+            plan->segments.push_back(sg);
+            i = j;
+        }
+    }
     *out = plan.get();
     c->cur->plans[batch] = std::move(plan);
     return B2_OK;
@@ -1240,13 +1323,22 @@ int run_launch(const b2_engine* e, const Launch& L, void* const* bindings, cudaS
             return b2k::launch_softmax(static_cast<const float*>(in), static_cast<float*>(out), L.N, L.C, s);
         case L_NET:
             return b2k::launch_net_f16_tcgen05(L.net->args, L.net->ctas, s);
+        case L_TAIL: {
+            b2k::TailArgs t = L.tail;
+            t.out = static_cast<float*>(out);
+            return b2k::launch_tail_f16(t, s);
+        }
     }
     return int(cudaErrorInvalidValue);
 }
 
 // Launches the plan on `s`.  Side branches go to the context's second stream between a fork and a join event: inside
 // a stream capture that becomes a parallel branch of the graph, outside it is plain two-stream concurrency.
+int run_range(b2_context* c, const Plan& plan, size_t first, size_t last, void* const* bindings, cudaStream_t s);
 int run_all(b2_context* c, const Plan& plan, void* const* bindings, cudaStream_t s) {
+    return run_range(c, plan, 0, plan.launches.size(), bindings, s);
+}
+int run_range(b2_context* c, const Plan& plan, size_t first, size_t last, void* const* bindings, cudaStream_t s) {
     const b2_engine* e = c->e;
     bool fork = c->fork != 0;
     if (fork && !c->side) {
@@ -1258,14 +1350,14 @@ int run_all(b2_context* c, const Plan& plan, void* const* bindings, cudaStream_t
         }
     }
     int pending_join = -1;
-    for (size_t i = 0; i < plan.launches.size(); ++i) {
+    for (size_t i = first; i < last; ++i) {
         const Launch& L = plan.launches[i];
         if (pending_join == int(i)) {
             B2_CUDA(cudaStreamWaitEvent(s, c->join_ev, 0));
             pending_join = -1;
         }
         int rc;
-        if (fork && pending_join < 0 && L.side_join > int(i)) {
+        if (fork && pending_join < 0 && L.side_join > int(i) && L.side_join < int(last)) {
             B2_CUDA(cudaEventRecord(c->fork_ev, s));
             B2_CUDA(cudaStreamWaitEvent(c->side, c->fork_ev, 0));
             rc = run_launch(e, L, bindings, c->side);
@@ -1280,6 +1372,27 @@ int run_all(b2_context* c, const Plan& plan, void* const* bindings, cudaStream_t
             return fail(B2_ECUDA, "launch of %s failed: %s", L.name.c_str(), cudaGetErrorString(cudaError_t(rc)));
     }
     if (pending_join >= 0) B2_CUDA(cudaStreamWaitEvent(s, c->join_ev, 0));  // never leave the branch dangling
+    return B2_OK;
+}
+
+// Captures launches [begin, end) of the plan -- none of which touches a binding -- on `stream` (which must be idle-able:
+// capture only records) and instantiates the graph once for the life of the plan.
+int instantiate_segment(b2_context* c, Plan* plan, Segment* sg, void* const* bindings, cudaStream_t stream) {
+    cudaGraph_t graph = nullptr;
+    B2_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    int rc = run_range(c, *plan, size_t(sg->begin), size_t(sg->end), bindings, stream);
+    cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+    if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (ce != cudaSuccess) return fail(B2_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&sg->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+        sg->exec = nullptr;
+        return fail(B2_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    }
     return B2_OK;
 }
 
@@ -1430,21 +1543,21 @@ int b2_context_create(b2_engine* e, b2_context** out) {
     c->net_ctas = env_int("B2_NET_CTAS", 0);
     c->net_bn = env_int("B2_NET_BN", 0);
     c->net_stages = env_int("B2_NET_STAGES", 0);
+    c->fuse_tail = env_int("B2_FUSE_TAIL", 1);
     if (getenv("B2_PDL")) b2k::set_pdl(env_int("B2_PDL", 1) != 0);
     void* p = nullptr;
-    if (cudaMalloc(&p, kMaxSplitTiles * sizeof(int)) != cudaSuccess || cudaMemset(p, 0, kMaxSplitTiles * sizeof(int)) != cudaSuccess) {
+    if (cudaMalloc(&p, (kMaxSplitTiles + 16) * sizeof(int)) != cudaSuccess || cudaMemset(p, 0, (kMaxSplitTiles + 16) * sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
         delete c;
         return fail(B2_ENOMEM, "cudaMalloc for split-K counters failed");
     }
     c->d_counters = static_cast<int*>(p);
+    c->d_tail_ctrl = c->d_counters + kMaxSplitTiles;
     *out = c;
     return B2_OK;
 }
 
 static void drop_cached(b2_context* c) {
-    for (auto& st : c->states)
-        for (auto& kv : st.second.graphs) cudaGraphExecDestroy(kv.second);
     c->states.clear();
     c->cur = c->scratch ? &c->states[c->scratch] : nullptr;
 }
@@ -1492,6 +1605,7 @@ int b2_context_set_option(b2_context* c, const char* key, int value) {
     else if (k == "net_ctas") c->net_ctas = value;
     else if (k == "net_bn") c->net_bn = value;
     else if (k == "net_stages") c->net_stages = value;
+    else if (k == "fuse_tail") c->fuse_tail = value;
     else if (k == "pdl_trigger") c->pdl_trigger = value;
     else if (k == "autotune") c->autotune = value;
     else if (k == "no_fold") c->no_fold = value;
@@ -1507,6 +1621,84 @@ int b2_context_nb_launches(b2_context* c, int batch) {
     return int(plan->launches.size());
 }
 
+// ---- ahead-of-time work: tactics and graphs never get built on the request path ------------------------------
+int b2_engine_tune(b2_engine* e, int streams, int all_batches) {
+    if (!e) return fail(B2_EINVAL, "null engine");
+    if (e->inspect_only) return fail(B2_ESTATE, "engine was loaded with b2_engine_inspect (no device resources)");
+    if (!e->half() || e->tactics_from_plan) return B2_OK;  // fp32 engines have no tactics; the plan brought its own
+    std::lock_guard<std::mutex> run_lock(e->tune_run_mutex);
+    b2_context* c = nullptr;
+    int rc = b2_context_create(e, &c);
+    if (rc) return rc;
+    c->autotune = streams > 0 ? streams : c->autotune;
+    void* scratch = nullptr;
+    if (c->autotune <= 0) {
+        b2_context_destroy(c);
+        return B2_OK;
+    }
+    if (cudaMalloc(&scratch, std::max<size_t>(e->arena_bytes, 1024)) != cudaSuccess) {
+        cudaGetLastError();
+        b2_context_destroy(c);
+        return fail(B2_ENOMEM, "cudaMalloc(%zu) for the tuning arena failed", e->arena_bytes);
+    }
+    rc = b2_context_set_device_memory(c, scratch);
+    if (!rc && load_driver_entry_points() != 0) rc = fail(B2_ECUDA, "cuTensorMapEncode* driver entry points unavailable");
+    {
+        std::lock_guard<std::mutex> lock(e->tune_mutex);
+        tune_cache_load(e);
+    }
+    if (!rc) rc = tune_engine_batch(c, e->max_batch);
+    for (int b = 1; !rc && all_batches && b < e->max_batch; ++b) rc = tune_engine_batch(c, b);
+    cudaDeviceSynchronize();
+    b2_context_destroy(c);
+    cudaFree(scratch);
+    if (!rc) e->tuned_at_load = true;
+    return rc;
+}
+
+int b2_engine_nb_tactics(const b2_engine* e) {
+    if (!e) return 0;
+    std::lock_guard<std::mutex> lock(const_cast<b2_engine*>(e)->tune_mutex);
+    return int(e->tuned.size());
+}
+// 10 x uint32 per tactic, the TacticRec layout of plan_format.h; returns the number written
+int b2_engine_get_tactics(const b2_engine* e, uint32_t* out, int cap) {
+    if (!e || !out) return 0;
+    std::lock_guard<std::mutex> lock(const_cast<b2_engine*>(e)->tune_mutex);
+    int n = 0;
+    for (const auto& kv : e->tuned) {
+        if (n >= cap) break;
+        const ConvConfig& g = kv.second;
+        const uint32_t rec[10] = {uint32_t(kv.first.first), uint32_t(kv.first.second), uint32_t(g.bn), uint32_t(g.stages), uint32_t(g.splits),
+                                  uint32_t(g.sps), uint32_t(g.ws), uint32_t(g.cn), uint32_t(g.halo), 0u};
+        memcpy(out + size_t(n) * 10, rec, sizeof rec);
+        ++n;
+    }
+    return n;
+}
+
+// Builds the launch plan of `batch` for the context's current arena and instantiates its graph segments, so that the
+// first request at this batch size pays neither.  `stream` is only used to record the capture.
+int b2_context_prepare(b2_context* c, int batch, b2_stream_t stream_) {
+    if (!c) return fail(B2_EINVAL, "null context");
+    if (batch < 1 || batch > c->e->max_batch) return fail(B2_EINVAL, "batch %d outside [1, %d]", batch, c->e->max_batch);
+    Plan* plan = nullptr;
+    int rc = build_plan(c, batch, &plan);
+    if (rc) return rc;
+    if (!c->use_graph || plan->has_net) return B2_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    cudaStream_t own = nullptr;
+    if (!stream) {
+        B2_CUDA(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+        stream = own;
+    }
+    std::vector<void*> dummy(c->e->bindings.size(), reinterpret_cast<void*>(uintptr_t(256)));  // never dereferenced: no launch of a graphable segment reads a binding
+    for (Segment& sg : plan->segments)
+        if (sg.graphable && !sg.exec && (rc = instantiate_segment(c, plan, &sg, dummy.data(), stream))) break;
+    if (own) cudaStreamDestroy(own);
+    return rc;
+}
+
 int b2_context_enqueue(b2_context* c, int batch, void* const* bindings, b2_stream_t stream_, b2_event_t consumed) {
     int rc = check_args(c, batch, bindings);
     if (rc) return rc;
@@ -1515,37 +1707,19 @@ int b2_context_enqueue(b2_context* c, int batch, void* const* bindings, b2_strea
     if ((rc = build_plan(c, batch, &plan))) return rc;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     B2_CUDA(cudaStreamIsCapturing(stream, &cap));
-    // A plan with a persistent network kernel is a handful of launches: it is issued directly.  No captured graph means
-    // no per-(binding pointers) graph cache, no capture or instantiation on the request path.
+    // Inside a caller's capture (the reference graphs enqueueV2 itself, workspace.cc:51-56), with graphs off, or for a plan
+    // that is a handful of launches anyway (persistent network kernel): plain launches.
     if (cap != cudaStreamCaptureStatusNone || !c->use_graph || plan->has_net) {
         if ((rc = run_all(c, *plan, bindings, stream))) return rc;
     } else {
-        b2_context::GraphKey key;
-        key.batch = batch;
-        key.ptrs.assign(bindings, bindings + c->e->bindings.size());
-        auto& graphs = c->cur->graphs;
-        auto it = graphs.find(key);
-        if (it == graphs.end()) {
-            if (graphs.size() >= 256) {  // bound the cache; callers normally cycle through a small Buffers pool
-                for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
-                graphs.clear();
+        for (Segment& sg : plan->segments) {
+            if (!sg.graphable) {
+                if ((rc = run_range(c, *plan, size_t(sg.begin), size_t(sg.end), bindings, stream))) return rc;
+                continue;
             }
-            cudaGraph_t graph = nullptr;
-            B2_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-            rc = run_all(c, *plan, bindings, stream);
-            cudaError_t ce = cudaStreamEndCapture(stream, &graph);
-            if (rc) {
-                if (graph) cudaGraphDestroy(graph);
-                return rc;
-            }
-            if (ce != cudaSuccess) return fail(B2_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
-            cudaGraphExec_t exec = nullptr;
-            ce = cudaGraphInstantiate(&exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (ce != cudaSuccess) return fail(B2_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
-            it = graphs.emplace(std::move(key), exec).first;
+            if (!sg.exec && (rc = instantiate_segment(c, plan, &sg, bindings, stream))) return rc;
+            B2_CUDA(cudaGraphLaunch(sg.exec, stream));
         }
-        B2_CUDA(cudaGraphLaunch(it->second, stream));
     }
     if (consumed) B2_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(consumed), stream));
     return B2_OK;
@@ -1642,7 +1816,7 @@ const char* b2_context_launch_name(b2_context* c, int batch, int i) {
     static thread_local std::string s;
     const Launch* L = get_launch(c, batch, i);
     if (!L) return nullptr;
-    static const char* kinds[] = {"input_cast", "conv_tcgen05", "conv_simt", "maxpool", "avgpool", "fc", "softmax", "output_cast", "net_tcgen05"};
+    static const char* kinds[] = {"input_cast", "conv_tcgen05", "conv_simt", "maxpool", "avgpool", "fc", "softmax", "output_cast", "net_tcgen05", "tail_pool_fc_softmax"};
     s = std::string(kinds[L->kind]) + ":" + L->name;
     if (L->kind == L_CONV_TC)
         s += " bn=" + std::to_string(L->conv.bn) + " kb=" + std::to_string(L->conv.kb) +

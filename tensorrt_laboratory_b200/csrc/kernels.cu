@@ -1696,4 +1696,211 @@ int launch_softmax(const float* in, float* out, int N, int C, cudaStream_t strea
     return B2_LAUNCH_RC;
 }
 
+
+// =================================================================================================
+// tail_f16_kernel -- global average pool + fully connected + bias + softmax in ONE launch (fp16 engines).
+//   The three operators are a dependency chain over tiny tensors (RN50, batch 8: 1.6 MB in, 4.1 MB of weights, 32 KB
+//   out), so as separate kernels they are three launch + drain latencies.  Here the work is one ordered ticket list
+//   -- pool items, then FC items (8 neurons each, one per warp), then one softmax item per image -- drawn by the CTAs of
+//   a single grid; an FC item pulls its weight rows into registers BEFORE it waits for the pooled vector, a softmax item
+//   waits for the logits.  In-order tickets drawn by running CTAs only make the waits deadlock-free without any
+//   co-residency assumption.  The arithmetic (summation orders, fp16 rounding of the pooled vector, expf) is exactly
+//   that of avgpool_h8_kernel / fc_h8_kernel / softmax_kernel: results are bit-identical to the unfused path.
+//   Reference ops: models/ResNet-50-deploy.prototxt:2292-2302 (pool5) + InnerProduct + Softmax.
+// =================================================================================================
+__device__ __forceinline__ int tail_ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tail_wait_counter(const int* p, int need) {
+    uint32_t spins = 0;
+    long long t0 = 0;
+    while (tail_ld_acquire(p) < need) {
+        if ((++spins & 0x3FFFu) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) tail_f16_kernel(const TailArgs a) {
+    extern __shared__ uint4 s_dyn[];  // FC: [8][K/8] staged pooled rows
+    __shared__ float part[8][32][8];
+    __shared__ float red[32];
+    __shared__ int s_ticket;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int C8 = a.C / 8;
+    const int groups_per_img = (C8 + 31) / 32;
+    const int n_pool = a.N * groups_per_img;
+    const int n_fc = (a.Cout + 7) / 8;
+    const int total = n_pool + n_fc + a.N;
+    pdl_launch_dependents();
+    bool waited = false;  // griddepcontrol.wait executed (before the first read of the previous kernel's output)
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = atomicAdd(a.ctrl, 1);
+        __syncthreads();
+        const int t = s_ticket;
+        if (t >= total) break;
+        if (t < n_pool) {
+            // ---------------- global average pool: one (image, 256-channel group) ----------------
+            if (!waited) pdl_wait(), waited = true;
+            const int n = t / groups_per_img;
+            const int cg = (t - n * groups_per_img) * 32 + lane;
+            const int slice = warp;
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+            if (cg < C8) {
+                const uint4* base = reinterpret_cast<const uint4*>(a.in) + static_cast<size_t>(n) * a.HW * C8 + cg;
+                for (int px = slice; px < a.HW; px += 8) {
+                    const uint4 v = __ldg(base + static_cast<size_t>(px) * C8);
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = __half22float2(h2[i]);
+                        acc[2 * i] += f.x;
+                        acc[2 * i + 1] += f.y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) part[slice][lane][i] = acc[i];
+            __syncthreads();
+            if (slice == 0 && cg < C8) {
+                const float inv = 1.0f / static_cast<float>(a.HW);
+                float tot[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float tt = part[0][lane][i];
+#pragma unroll
+                    for (int sl = 1; sl < 8; ++sl) tt += part[sl][lane][i];
+                    tot[i] = tt * inv;
+                }
+                uint4 o;
+                __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(tot[2 * i], tot[2 * i + 1]);
+                reinterpret_cast<uint4*>(a.pooled)[static_cast<size_t>(n) * C8 + cg] = o;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(a.ctrl + 1, 1);
+            }
+        } else if (t < n_pool + n_fc) {
+            // ---------------- fully connected: 8 neurons (one per warp) x all images ----------------
+            const int j = (t - n_pool) * 8 + warp;
+            const int K = a.C;
+            const int kv = K / 8, per_lane = kv / 32;  // uint4 per row / per lane (<= 8)
+            uint4 wreg[8];
+            if (j < a.Cout) {  // constants: fetched before the dependency wait
+                const uint4* wr = reinterpret_cast<const uint4*>(a.w + static_cast<size_t>(j) * K);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < per_lane) wreg[i] = __ldg(wr + lane + 32 * i);
+            }
+            if (!waited) pdl_wait(), waited = true;
+            if (threadIdx.x == 0) tail_wait_counter(a.ctrl + 1, n_pool);
+            __syncthreads();
+            for (int nb = 0; nb < a.N; nb += 8) {
+                const int rows = min(8, a.N - nb);
+                __syncthreads();
+                for (int i = threadIdx.x; i < rows * kv; i += blockDim.x)
+                    s_dyn[i] = __ldcg(reinterpret_cast<const uint4*>(a.pooled + static_cast<size_t>(nb) * K) + i);
+                __syncthreads();
+                if (j < a.Cout) {
+                    float acc[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (i < per_lane) {
+                            const __half2* w2 = reinterpret_cast<const __half2*>(&wreg[i]);
+                            float2 wf[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) wf[q] = __half22float2(w2[q]);
+#pragma unroll
+                            for (int r = 0; r < 8; ++r) {
+                                if (r < rows) {
+                                    const uint4 xv = s_dyn[r * kv + lane + 32 * i];
+                                    const __half2* x2 = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float2 xf = __half22float2(x2[q]);
+                                        acc[r] = fmaf(wf[q].x, xf.x, acc[r]);
+                                        acc[r] = fmaf(wf[q].y, xf.y, acc[r]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        float v = acc[r];
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        if (lane == 0 && r < rows) a.logits[static_cast<size_t>(nb + r) * a.Cout + j] = v + a.bias[j];
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(a.ctrl + 2, 1);
+            }
+        } else {
+            // ---------------- softmax: one image ----------------
+            const int n = t - n_pool - n_fc;
+            if (!waited) pdl_wait(), waited = true;
+            if (threadIdx.x == 0) tail_wait_counter(a.ctrl + 2, n_fc);
+            __syncthreads();
+            const float* x = a.logits + static_cast<size_t>(n) * a.Cout;
+            float* y = a.out + static_cast<size_t>(n) * a.Cout;
+            const int nwarp = blockDim.x >> 5;
+            float m = -INFINITY;
+            for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) m = fmaxf(m, __ldcg(x + i));
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) red[warp] = m;
+            __syncthreads();
+            m = red[0];
+            for (int i = 1; i < nwarp; ++i) m = fmaxf(m, red[i]);
+            __syncthreads();
+            float sum = 0.f;
+            for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) sum += expf(__ldcg(x + i) - m);
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) red[warp] = sum;
+            __syncthreads();
+            sum = 0.f;
+            for (int i = 0; i < nwarp; ++i) sum += red[i];
+            const float inv = 1.0f / sum;
+            for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) y[i] = expf(__ldcg(x + i) - m) * inv;
+        }
+    }
+    // the last CTA to leave re-arms the counters for the next launch
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.ctrl + 3, 1) == static_cast<int>(gridDim.x) - 1) {
+            a.ctrl[0] = 0, a.ctrl[1] = 0, a.ctrl[2] = 0, a.ctrl[3] = 0;
+        }
+    }
+}
+
+bool tail_f16_applies(int N, int HW, int C, int Cout) { return N >= 1 && HW >= 1 && C % 256 == 0 && C <= 2048 && Cout >= 1; }
+
+int launch_tail_f16(const TailArgs& a, cudaStream_t stream) {
+    if (!tail_f16_applies(a.N, a.HW, a.C, a.Cout)) return static_cast<int>(cudaErrorInvalidValue);
+    const int items = a.N * ((a.C / 8 + 31) / 32) + (a.Cout + 7) / 8 + a.N;
+    const unsigned blocks = static_cast<unsigned>(items < 148 ? items : 148);
+    const size_t smem = static_cast<size_t>(a.C) * 2 * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(tail_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_set = true;
+    }
+    B2_LAUNCH_RC = launch_kernel(tail_f16_kernel, dim3(blocks), dim3(256), smem, stream, true, a);
+    return B2_LAUNCH_RC;
+}
+
 }  // namespace b2k

@@ -160,4 +160,18 @@ int launch_fc(const void* in, const void* w, const float* bias, float* out, int 
               bool half_storage, cudaStream_t stream);
 int launch_softmax(const float* in, float* out, int N, int C, cudaStream_t stream);
 
+// global average pool + FC + bias + softmax in one launch (fp16 engines; tail_f16_kernel in kernels.cu)
+struct TailArgs {
+    const __half* in;     // [N][HW][C] NHWC activations
+    const __half* w;      // [Cout][C]
+    const float* bias;    // [Cout]
+    float* out;           // [N][Cout] softmax (the output binding)
+    __half* pooled;       // [N][C] scratch (the pooled activation tensor of the plan)
+    float* logits;        // [N][Cout] scratch (the FC output vector of the plan)
+    int* ctrl;            // 4 ints, zero between launches: ticket, finished pool items, finished FC items, exited CTAs
+    int N, HW, C, Cout;
+};
+bool tail_f16_applies(int N, int HW, int C, int Cout);
+int launch_tail_f16(const TailArgs& a, cudaStream_t stream);
+
 }  // namespace b2k

@@ -34,7 +34,14 @@ struct Header {  // 128 bytes
     uint64_t payload_offset;  // from blob start, 256-byte aligned
     uint64_t payload_bytes;
     char name[64];
-    uint8_t pad[16];
+    // optional tactic table (the role of the tactics a TensorRT plan carries): n_tactics TacticRec records at
+    // tactics_offset from the blob start, behind the weight payload.  0 / 0 = none (tune at load, or cost model)
+    uint32_t n_tactics;
+    uint32_t reserved;
+    uint64_t tactics_offset;
+};
+struct TacticRec {  // 40 bytes: the measured-best kernel configuration of one (conv op, batch)
+    uint32_t op, batch, bn, stages, splits, sps, ws, cn, halo, reserved;
 };
 struct TensorRec {  // 96 bytes
     char name[64];
@@ -72,6 +79,7 @@ struct BindingRec {  // 128 bytes
 #pragma pack(pop)
 
 static_assert(sizeof(Header) == 128, "Header size");
+static_assert(sizeof(TacticRec) == 40, "TacticRec size");
 static_assert(sizeof(TensorRec) == 96, "TensorRec size");
 static_assert(sizeof(OpRec) == 176, "OpRec size");
 static_assert(sizeof(BindingRec) == 128, "BindingRec size");

@@ -95,10 +95,10 @@ int trt_manager_infer(trt_manager* m, const char* model_name, int batch, const v
         },
         [&](std::shared_ptr<Bindings>& b) {  // "post" stage: read the pinned output binding
             memcpy(output, b->HostAddress(out_id), output_bytes);
-            return 0;
+            return b->ComputeTime();  // device time of the forward pass (ExecutionContext::Synchronize, server.cc:169)
         });
-    fut.get();
-    if (compute_seconds) *compute_seconds = 0.0;
+    const double seconds = fut.get();
+    if (compute_seconds) *compute_seconds = seconds;
     return B2_OK;
     TRT_CATCH
 }
@@ -201,6 +201,87 @@ int trt_timed_pipeline(const void* blob, size_t nbytes, int iters, float* h2d_ms
 // Device-resident throughput: `contexts` execution contexts on independent streams, inputs cycled through
 // a device ring (sized by the caller to exceed L2), `steps` forward passes issued round-robin, timed with
 // CUDA events from the first launch to the completion of the last stream.
+// v2 surface: BenchmarkWorkspace (StaticSingleModelGraphWorkspace underneath: the CALLER captures b2_context_enqueue into
+// its own CUDA graph, reference workspace.cc:51-56,75) -- pinned input -> async_h2d -> enqueue() -> async_d2h, `iters`
+// times; the output of the last pass is returned.  `managed_runtime`: weights through ManagedRuntime (allocator.cc:72-77).
+int trt_workspace_infer(const void* blob, size_t nbytes, const void* input, size_t input_bytes, void* output, size_t output_bytes,
+                        int managed_runtime, int iters) {
+    if (!blob || !input || !output || iters < 1) return fail(B2_EINVAL, "bad arguments");
+    TRT_TRY
+    std::shared_ptr<Runtime> rt;
+    if (managed_runtime) rt = std::make_shared<ManagedRuntime>();
+    else rt = std::make_shared<StandardRuntime>();
+    auto model = rt->DeserializeEngine(blob, nbytes);
+    if (model->GetInputBindingIds().size() != 1 || model->GetOutputBindingIds().size() != 1)
+        return fail(B2_EINVAL, "trt_workspace_infer handles single-input single-output models");
+    const uint32_t in_id = model->GetInputBindingIds()[0], out_id = model->GetOutputBindingIds()[0];
+    BenchmarkWorkspace ws(model);
+    if (input_bytes != ws.binding_bytes(in_id) || output_bytes != ws.binding_bytes(out_id))
+        return fail(B2_EINVAL, "binding size mismatch (the workspace runs at max batch): %zu/%zu vs %zu/%zu", input_bytes,
+                    ws.binding_bytes(in_id), output_bytes, ws.binding_bytes(out_id));
+    memcpy(ws.host_binding(in_id), input, input_bytes);
+    for (int i = 0; i < iters; ++i) {
+        ws.async_h2d();
+        ws.enqueue();
+        ws.async_d2h();
+    }
+    if (cudaStreamSynchronize(ws.stream()) != cudaSuccess) return fail(B2_ECUDA, "workspace stream failed: %s", cudaGetErrorString(cudaGetLastError()));
+    memcpy(output, ws.host_binding(out_id), output_bytes);
+    return B2_OK;
+    TRT_CATCH
+}
+
+namespace {
+struct RewindableCyclicBuffers : CyclicBuffers<CudaPinnedHostMemory, CudaDeviceMemory> {
+    using CyclicBuffers<CudaPinnedHostMemory, CudaDeviceMemory>::CyclicBuffers;
+    void Rewind() { Reset(); }  // what InferenceManager::GetBuffers()'s return hook does for pooled Buffers
+};
+}  // namespace
+
+// The hot path by hand over CyclicBuffers<CudaPinnedHostMemory, CudaDeviceMemory> (buffers.h:122-154):
+// `rounds` requests, each cutting its bindings from the segment ring (so the ring wraps and recycles segments), through
+// CreateBindings / CopyToDevice / ExecutionContext::Infer / CopyFromDevice / Synchronize.  Output of the last request.
+int trt_cyclic_infer(const void* blob, size_t nbytes, int batch, const void* input, size_t input_bytes, void* output,
+                     size_t output_bytes, int managed_runtime, int rounds, double* compute_seconds) {
+    if (!blob || !input || !output || rounds < 1 || batch < 1) return fail(B2_EINVAL, "bad arguments");
+    TRT_TRY
+    std::shared_ptr<Runtime> rt;
+    if (managed_runtime) rt = std::make_shared<ManagedRuntime>();
+    else rt = std::make_shared<StandardRuntime>();
+    auto model = rt->DeserializeEngine(blob, nbytes);
+    if (model->GetInputBindingIds().size() != 1 || model->GetOutputBindingIds().size() != 1)
+        return fail(B2_EINVAL, "trt_cyclic_infer handles single-input single-output models");
+    if (batch > model->GetMaxBatchSize()) return fail(B2_EINVAL, "batch %d out of range", batch);
+    const uint32_t in_id = model->GetInputBindingIds()[0], out_id = model->GetOutputBindingIds()[0];
+    if (input_bytes != model->GetBinding(in_id).bytesPerBatchItem * size_t(batch) ||
+        output_bytes != model->GetBinding(out_id).bytesPerBatchItem * size_t(batch))
+        return fail(B2_EINVAL, "binding size mismatch");
+    // every segment holds ONE request's bindings (+ alignment), so each request moves the ring on by one segment
+    const size_t per_request = model->GetBindingMemorySize() + model->GetBindingsCount() * 256;
+    auto buffers = std::make_shared<RewindableCyclicBuffers>(
+        std::make_unique<CyclicAllocator<CudaPinnedHostMemory>>(3, per_request), std::make_unique<CyclicAllocator<CudaDeviceMemory>>(3, per_request));
+    ExecutionContext ctx(std::max<size_t>(model->GetActivationsMemorySize(), 1024));
+    double seconds = 0.0;
+    for (int r = 0; r < rounds; ++r) {
+        auto bindings = buffers->CreateBindings(model);
+        bindings->SetBatchSize(uint32_t(batch));
+        memcpy(bindings->HostAddress(in_id), input, input_bytes);
+        bindings->CopyToDevice(bindings->InputBindings());
+        ctx.SetContext(model->CreateExecutionContext());
+        ctx.Infer(bindings);
+        bindings->CopyFromDevice(bindings->OutputBindings());
+        seconds = ctx.Synchronize();
+        bindings->Synchronize();
+        if (r == rounds - 1) memcpy(output, bindings->HostAddress(out_id), output_bytes);
+        ctx.Reset();
+        bindings.reset();
+        buffers->Rewind();  // releases the request's descriptors: the segment may be recycled
+    }
+    if (compute_seconds) *compute_seconds = seconds;
+    return B2_OK;
+    TRT_CATCH
+}
+
 int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int batch, int steps, int warmup,
                           const void* host_ring, int ring_batches, double* elapsed_ms, int* launches_per_step) {
     if (!blob || contexts < 1 || steps < 1 || !host_ring || ring_batches < 1 || !elapsed_ms) return fail(B2_EINVAL, "bad arguments");
@@ -212,6 +293,15 @@ int trt_device_throughput(const void* blob, size_t nbytes, int contexts, int bat
     if (rc) {
         b2_runtime_destroy(rt);
         return rc;
+    }
+    {   // tactics are timed ahead of the requests, in the regime of the run (`contexts` concurrent streams)
+        const char* at = getenv("B2_AUTOTUNE");
+        if (!at || atoi(at) != 0) rc = b2_engine_tune(eng, at ? atoi(at) : std::max(1, std::min(contexts, 8)), 0);
+        if (rc) {
+            b2_engine_destroy(eng);
+            b2_runtime_destroy(rt);
+            return rc;
+        }
     }
     const int nb = b2_engine_nb_bindings(eng);
     int in_id = -1;

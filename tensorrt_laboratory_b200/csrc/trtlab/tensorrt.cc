@@ -267,9 +267,9 @@ size_t Bindings::BindingSize(uint32_t binding_id) const {  // bindings.cc:171-17
 }
 
 // ---- ExecutionContext ----------------------------------------------------------------------------------
-ExecutionContext::Lane::Lane(size_t workspace_bytes)
+ExecutionContext::Lane::Lane(size_t workspace_bytes, int index_)
     : workspace(CudaDeviceMemory::Allocate(std::max<size_t>(workspace_bytes, 1024))), bytes(std::max<size_t>(workspace_bytes, 1024)),
-      last_done(nullptr) {}
+      index(index_), last_done(nullptr) {}
 ExecutionContext::Lane::~Lane() { CudaDeviceMemory::Free(workspace); }
 
 ExecutionContext::ExecutionContext(size_t workspace_bytes) : ExecutionContext(std::make_shared<Lane>(workspace_bytes)) {}
@@ -385,14 +385,47 @@ void InferenceManager::RegisterModel(const std::string& name, std::shared_ptr<Mo
 
     model->SetName(name);
     m_Models[name] = model;
-    auto pool = Pool<IExecutionContext>::Create();
-    for (uint32_t i = 0; i < max_concurrency * uint32_t(EnqueueDepth()); i++) {
-        auto ctx = model->CreateExecutionContext();
-        // m_MaxExecutions forward passes share the GPU: each persistent network kernel gets its share of the 2 x 148 CTA slots
-        if (!getenv("B2_NET_CTAS")) b2_context_set_option(ctx->handle, "net_ctas", std::max(1, 296 / std::max(1, m_MaxExecutions)));
-        pool->Push(std::move(ctx));
+    // Tactic selection is build-time work (the reference's engines come out of trtexec already tuned, models/setup.py:53-55):
+    // time the kernels now, on a private arena, in the regime they will run in (m_MaxExecutions concurrent streams).
+    // Plans that carry a tactic table skip this; B2_AUTOTUNE=0 leaves the closed-form cost model in charge.
+    {
+        const char* at = getenv("B2_AUTOTUNE");
+        const char* all = getenv("TRTLAB_TUNE_ALL_BATCHES");
+        if (!at || atoi(at) != 0) TRT_CHECK_B2(b2_engine_tune(model->engine(), at ? atoi(at) : std::max(1, std::min(m_MaxExecutions, 8)), all && atoi(all) != 0));
     }
-    m_ModelExecutionContexts[model.get()] = pool;
+    const uint32_t depth = uint32_t(EnqueueDepth());
+    const bool per_lane = max_concurrency == uint32_t(m_MaxExecutions);
+    std::vector<std::shared_ptr<Pool<IExecutionContext>>> pools;
+    for (uint32_t p = 0; p < (per_lane ? max_concurrency : 1u); p++) {
+        auto pool = Pool<IExecutionContext>::Create();
+        for (uint32_t i = 0; i < (per_lane ? depth : max_concurrency * depth); i++) pool->Push(model->CreateExecutionContext());
+        pools.push_back(pool);
+    }
+    m_ModelExecutionContexts[model.get()] = pools;
+    if (m_ExecutionContexts) PrepareModel(model.get());  // registered after AllocateResources(): prepare right away
+}
+
+// Builds every launch plan and CUDA graph the request path will need (lane-pinned contexts x batch sizes 1..max).
+void InferenceManager::PrepareModel(const Model* model) {
+    auto item = m_ModelExecutionContexts.find(model);
+    if (item == m_ModelExecutionContexts.end() || item->second.size() != m_Lanes.size()) return;  // shared pool: lazily, as the reference does
+    const char* env = getenv("TRTLAB_PREPARE_BATCHES");  // "max" = only the max batch, "0" = none, default all (up to 64)
+    const std::string mode = env ? env : "all";
+    if (mode == "0") return;
+    const int max_batch = model->GetMaxBatchSize();
+    for (size_t lane = 0; lane < m_Lanes.size(); lane++) {
+        auto& pool = item->second[lane];
+        std::vector<std::shared_ptr<IExecutionContext>> held;
+        const size_t n = pool->Size();
+        for (size_t k = 0; k < n; k++) held.push_back(pool->PopWithoutReturn());
+        for (auto& ctx : held) {
+            TRT_CHECK_B2(b2_context_set_device_memory(ctx->handle, m_Lanes[lane]->workspace));
+            if (!getenv("B2_NET_CTAS")) b2_context_set_option(ctx->handle, "net_ctas", std::max(1, 296 / std::max(1, m_MaxExecutions)));
+            for (int b = (mode == "max" || max_batch > 64) ? max_batch : 1; b <= max_batch; b++)
+                TRT_CHECK_B2(b2_context_prepare(ctx->handle, b, nullptr));
+        }
+        for (auto& ctx : held) pool->Push(std::move(ctx));
+    }
 }
 
 Runtime& InferenceManager::ActiveRuntime() {
@@ -423,10 +456,11 @@ void InferenceManager::AllocateResources() {  // inference_manager.cc:181-205
 
     // m_MaxExecutions lanes (activation arenas == forward passes that can run at once), EnqueueDepth() tokens queued on each
     m_ExecutionContexts = Pool<ExecutionContext>::Create();
-    std::vector<std::shared_ptr<ExecutionContext::Lane>> lanes;
-    for (int i = 0; i < m_MaxExecutions; i++) lanes.push_back(std::make_shared<ExecutionContext::Lane>(m_ActivationsSize));
+    m_Lanes.clear();
+    for (int i = 0; i < m_MaxExecutions; i++) m_Lanes.push_back(std::make_shared<ExecutionContext::Lane>(m_ActivationsSize, i));
     for (int d = 0; d < EnqueueDepth(); d++)
-        for (int i = 0; i < m_MaxExecutions; i++) m_ExecutionContexts->EmplacePush(new ExecutionContext(lanes[size_t(i)]));
+        for (int i = 0; i < m_MaxExecutions; i++) m_ExecutionContexts->EmplacePush(new ExecutionContext(m_Lanes[size_t(i)]));
+    for (const auto& item : m_Models) PrepareModel(item.second.get());
 }
 
 // Tokens per lane.  1 = the reference's behaviour (a lane is idle from the end of a forward pass until the host has
@@ -460,8 +494,11 @@ auto InferenceManager::GetExecutionContext(const Model* model) -> std::shared_pt
     TRTLAB_CHECK(item != m_ModelExecutionContexts.end()) << "No ExectionContext for model " << model->Name();
     // global concurrency limiter -- owns the activation scratch
     auto ctx = m_ExecutionContexts->Pop([](ExecutionContext* ptr) { ptr->Reset(); });
-    // model concurrency limiter -- owns the engine-side context; it is pointed at the limiter's scratch
-    ctx->SetContext(item->second->Pop([](IExecutionContext*) {}));
+    // model concurrency limiter -- owns the engine-side context; it is pointed at the limiter's scratch.  Lane-pinned
+    // pools: the context comes from the pool of the token's lane (never blocks: as many contexts as tokens per lane).
+    auto& pools = item->second;
+    auto& pool = pools.size() > 1 ? pools[size_t(ctx->LaneIndex()) % pools.size()] : pools[0];
+    ctx->SetContext(pool->Pop([](IExecutionContext*) {}));
     return ctx;
 }
 auto InferenceManager::GetExecutionContext(const std::shared_ptr<Model>& model) -> std::shared_ptr<ExecutionContext> {
