@@ -28,6 +28,15 @@ int b2_device_set_blocking_sync(int blocking);
 int b2_device_info(int device, char* name, int name_cap, int* cc_major, int* cc_minor, int* sm_count,
                    size_t* total_mem, size_t* l2_bytes);
 
+/* DeviceInfo::Affinity (trtlab/cuda/src/device_info.cc:66-85): the host CPUs closest to `device` (NVML
+ * nvmlDeviceGetCpuAffinity), as a bit mask of `n_words` 64-bit words (CPU i = bit i%64 of word i/64).  Returns B2_OK and
+ * an all-zero mask when NVML cannot say (not loadable, no topology information). */
+int b2_device_cpu_affinity(int device, uint64_t* mask, int n_words);
+/* Binds the CALLING thread to that CPU set (intersected with the CPUs the process may use; left unchanged when the
+ * intersection is empty).  Pinned host memory allocated afterwards by this thread lands on the GPU's NUMA node (first
+ * touch under the default local policy).  *n_cpus (optional) = CPUs in the new mask, 0 = unchanged. */
+int b2_bind_thread_to_device(int device, int* n_cpus);
+
 int b2_malloc_device(void** ptr, size_t bytes);      /* cuda_malloc: 256-byte aligned device memory */
 int b2_free_device(void* ptr);
 int b2_malloc_host(void** ptr, size_t bytes);        /* cuda_malloc_host: pinned, portable */

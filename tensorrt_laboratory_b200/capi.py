@@ -61,6 +61,8 @@ SYMBOLS = [
     ("b2_device_get", _I, []),
     ("b2_device_set_blocking_sync", _I, [_I]),
     ("b2_device_info", _I, [_I, _S, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_SZ), C.POINTER(_SZ)]),
+    ("b2_device_cpu_affinity", _I, [_I, C.POINTER(C.c_uint64), _I]),
+    ("b2_bind_thread_to_device", _I, [_I, C.POINTER(_I)]),
     ("b2_malloc_device", _I, [_PVP, _SZ]),
     ("b2_free_device", _I, [_VP]),
     ("b2_malloc_host", _I, [_PVP, _SZ]),
@@ -136,6 +138,20 @@ def check(rc: int):
 
 def device_count() -> int:
     return load().b2_device_count()
+
+
+def device_cpu_affinity(device: int = 0) -> List[int]:
+    """Host CPUs NVML reports as closest to `device` (reference DeviceInfo::Affinity); [] when unknown."""
+    mask = (C.c_uint64 * 16)()
+    check(load().b2_device_cpu_affinity(device, mask, 16))
+    return [i for i in range(1024) if (mask[i // 64] >> (i % 64)) & 1]
+
+
+def bind_thread_to_device(device: int = 0) -> int:
+    """Bind the calling thread to the GPU's CPUs (no-op when unknown / outside the cpuset); -> CPUs bound, 0 = unchanged."""
+    n = _I()
+    check(load().b2_bind_thread_to_device(device, C.byref(n)))
+    return n.value
 
 
 def device_info(device: int = 0) -> dict:

@@ -5,6 +5,10 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <dlfcn.h>
+#include <sched.h>
+
+#include <vector>
 
 #include "../../include/b200cuda.h"
 #include "b2_internal.h"
@@ -63,6 +67,56 @@ int b2_device_info(int device, char* name, int name_cap, int* cc_major, int* cc_
     if (sm_count) *sm_count = p.multiProcessorCount;
     if (total_mem) *total_mem = p.totalGlobalMem;
     if (l2_bytes) *l2_bytes = size_t(p.l2CacheSize);
+    return B2_OK;
+}
+
+// ---- GPU <-> CPU affinity (reference trtlab/cuda/src/device_info.cc:66-85, DeviceInfo::Affinity) ------------------
+// NVML is loaded lazily with dlopen (no link-time dependency); the CUDA device is matched by PCI bus id, so
+// CUDA_VISIBLE_DEVICES remapping does not matter.
+int b2_device_cpu_affinity(int device, uint64_t* mask, int n_words) {
+    if (!mask || n_words < 1) return fail(B2_EINVAL, "bad mask buffer");
+    memset(mask, 0, size_t(n_words) * sizeof(uint64_t));
+    typedef int (*init_t)();
+    typedef int (*by_pci_t)(const char*, void**);
+    typedef int (*affinity_t)(void*, unsigned int, unsigned long*);
+    static void* lib = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return B2_OK;
+    static init_t init = reinterpret_cast<init_t>(dlsym(lib, "nvmlInit_v2"));
+    static by_pci_t by_pci = reinterpret_cast<by_pci_t>(dlsym(lib, "nvmlDeviceGetHandleByPciBusId_v2"));
+    static affinity_t affinity = reinterpret_cast<affinity_t>(dlsym(lib, "nvmlDeviceGetCpuAffinity"));
+    static bool ok = init && by_pci && affinity && init() == 0;
+    if (!ok) return B2_OK;
+    char bus[64];
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B2_EINVAL, "no such device %d", device);
+    }
+    void* h = nullptr;
+    if (by_pci(bus, &h) != 0 || !h) return B2_OK;
+    std::vector<unsigned long> words(static_cast<size_t>(n_words), 0ul);
+    static_assert(sizeof(unsigned long) == sizeof(uint64_t), "NVML cpu-set words are 64-bit here");
+    if (affinity(h, static_cast<unsigned int>(n_words), words.data()) != 0) return B2_OK;
+    for (int i = 0; i < n_words; ++i) mask[i] = words[size_t(i)];
+    return B2_OK;
+}
+
+int b2_bind_thread_to_device(int device, int* n_cpus) {
+    if (n_cpus) *n_cpus = 0;
+    uint64_t mask[16];
+    int rc = b2_device_cpu_affinity(device, mask, 16);
+    if (rc) return rc;
+    cpu_set_t allowed, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return B2_OK;
+    int n = 0;
+    for (int cpu = 0; cpu < 1024 && cpu < CPU_SETSIZE; ++cpu)
+        if (((mask[cpu / 64] >> (cpu % 64)) & 1u) && CPU_ISSET(cpu, &allowed)) {
+            CPU_SET(cpu, &want);
+            ++n;
+        }
+    if (n == 0) return B2_OK;  // NVML silent, or the container's cpuset excludes the GPU's CPUs: leave the thread alone
+    if (sched_setaffinity(0, sizeof want, &want) != 0) return B2_OK;
+    if (n_cpus) *n_cpus = n;
     return B2_OK;
 }
 

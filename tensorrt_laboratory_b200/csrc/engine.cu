@@ -168,14 +168,34 @@ struct Segment {
     bool graphable = false;
     cudaGraphExec_t exec = nullptr;
 };
+// One kernel node of the plan's graph that reads or writes a binding: its pointer argument is re-pointed at the caller's
+// buffer before every launch (cudaGraphExecKernelNodeSetParams) -- the graph itself is captured and instantiated once.
+struct BindPatch {
+    int launch = -1;              // index into Plan::launches
+    cudaGraphNode_t node = nullptr;
+    cudaKernelNodeParams np{};    // func / grid / block / smem as captured
+    std::vector<void*> params;    // argument pointer array handed to the driver (entries point into the graph's storage ...)
+    int n_params = 0;
+    int in_index = -1, out_index = -1;  // ... except these, which point at in_value / out_value below
+    void* in_value = nullptr;
+    void* out_value = nullptr;
+    b2k::TailArgs tail{};         // fused tail: the whole argument struct is replaced (its `out` field is the binding)
+    bool is_tail = false;
+};
 struct Plan {
     int batch = 0;
     bool has_net = false;  // contains a persistent network kernel: a handful of launches, replayed directly (no graph)
     std::vector<Launch> launches;
-    std::vector<Segment> segments;
+    std::vector<Segment> segments;   // graph mode 3: binding-free runs as graphs, binding-dependent launches direct
+    bool graph_failed = false;       // the plan could not be captured as one patchable graph: segments instead
+    cudaGraph_t graph = nullptr;     // graph mode 1 (default): the whole plan, binding arguments patched per launch
+    cudaGraphExec_t exec = nullptr;
+    std::vector<BindPatch> patches;
     ~Plan() {
         for (Segment& sg : segments)
             if (sg.exec) cudaGraphExecDestroy(sg.exec);
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
     }
 };
 
@@ -443,11 +463,12 @@ void plan_arena(b2_engine* e) {
         Tensor& t = e->tensors[ti];
         if (t.last_use < t.def) t.last_use = t.def;
         const size_t size = align_up(t.item_bytes * e->max_batch, 1024);
-        // a buffer may be reused once its last reader has been launched BEFORE the new producer.  fp16 engines keep it
-        // two more ops: the persistent network kernel overlaps consecutive layers tile by tile, and a recycled buffer
-        // makes its new producer wait for the COMPLETION of every earlier layer that touched it -- with the slack those
-        // layers lie >= 3 ops back and are long finished when the producer's first tile is due.
-        const int slack = e->half() ? 2 : 0;
+        // a buffer may be reused once its last reader has been launched BEFORE the new producer.  When the persistent
+        // network kernel is requested (B2_NET=1) fp16 engines keep it two more ops: that kernel overlaps consecutive
+        // layers tile by tile, and a recycled buffer makes its new producer wait for the COMPLETION of every earlier
+        // layer that touched it -- with the slack those layers lie >= 3 ops back and are long finished when the
+        // producer's first tile is due.  (Measured cost of the larger arena on the per-layer path: ~1 %, so it is opt-in.)
+        const int slack = e->half() ? env_int("B2_ARENA_SLACK", env_int("B2_NET", 0) ? 2 : 0) : 0;
         live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.last + slack < t.def; }), live.end());
         std::sort(live.begin(), live.end(), [](const Live& a, const Live& b) { return a.off < b.off; });
         size_t off = 0;
@@ -1396,6 +1417,124 @@ int instantiate_segment(b2_context* c, Plan* plan, Segment* sg, void* const* bin
     return B2_OK;
 }
 
+// Which argument of a binding-dependent launch carries the binding pointer (positions in the kernels' parameter lists,
+// kernels.cu) and how many arguments the kernel has.
+bool patch_layout(const b2_engine* e, const Launch& L, BindPatch* p) {
+    const bool half = e->half();
+    switch (L.kind) {
+        case L_INPUT_CAST:
+            if (L.k == 2) p->n_params = 8;                                  // input_cast_s2d_kernel(src, dst, N, C, H, W, pad_l, pad_r)
+            else if (half && L.C_phys == 8 && L.C <= 8) p->n_params = 5;    // input_cast_c8_kernel(src, dst, N, C, HW)
+            else p->n_params = 6;                                           // input_cast_kernel(src, dst, N, C, HW, C_phys)
+            p->in_index = 0;
+            return true;
+        case L_OUTPUT_CAST:
+            p->n_params = 6, p->out_index = 1;                              // output_cast_kernel(src, dst, N, C, HW, C_phys)
+            return true;
+        case L_FC:
+            p->n_params = 7, p->out_index = 3;                              // fc kernels (in, w, bias, out, N, K, Cout)
+            return L.in_binding < 0;
+        case L_SOFTMAX:
+            p->n_params = 3;                                                // softmax_kernel(in, out, C)
+            if (L.in_binding >= 0) p->in_index = 0;
+            if (L.out_binding >= 0) p->out_index = 1;
+            return true;
+        case L_TAIL:
+            p->n_params = 1, p->is_tail = true, p->tail = L.tail;
+            return true;
+        default:
+            return false;
+    }
+}
+
+// Captures the WHOLE plan once (programmatic edges between all kernels survive) and remembers the kernel nodes that touch
+// a binding.  Returns B2_OK with plan->exec == nullptr if the plan cannot be patched (then graph mode 3 takes over).
+int instantiate_plan_graph(b2_context* c, Plan* plan, void* const* bindings, cudaStream_t stream) {
+    std::vector<BindPatch> patches;
+    cudaGraph_t graph = nullptr;
+    bool patchable = true;
+    B2_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    int rc = B2_OK;
+    for (size_t i = 0; i < plan->launches.size() && !rc; ++i) {
+        const Launch& L = plan->launches[i];
+        rc = run_range(c, *plan, i, i + 1, bindings, stream);
+        if (rc || (L.in_binding < 0 && L.out_binding < 0)) continue;
+        BindPatch p;
+        p.launch = int(i);
+        if (!patch_layout(c->e, L, &p)) {
+            patchable = false;
+            continue;
+        }
+        cudaStreamCaptureStatus st;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t ndeps = 0;
+        if (cudaStreamGetCaptureInfo_v2(stream, &st, nullptr, nullptr, &deps, &ndeps) != cudaSuccess || ndeps != 1) {
+            cudaGetLastError();
+            patchable = false;
+            continue;
+        }
+        p.node = deps[0];
+        patches.push_back(p);
+    }
+    cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+    if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (ce != cudaSuccess) return fail(B2_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+    for (BindPatch& p : patches) {
+        cudaGraphNodeType ty;
+        if (!patchable || cudaGraphNodeGetType(p.node, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel ||
+            cudaGraphKernelNodeGetParams(p.node, &p.np) != cudaSuccess || p.np.kernelParams == nullptr) {
+            cudaGetLastError();
+            patchable = false;
+            break;
+        }
+        p.params.assign(p.np.kernelParams, p.np.kernelParams + p.n_params);
+    }
+    if (!patchable) {
+        cudaGraphDestroy(graph);
+        return B2_OK;
+    }
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (ce != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        return fail(B2_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    }
+    plan->graph = graph, plan->exec = exec, plan->patches = std::move(patches);
+    // the values captured are the ones the graph holds now
+    for (BindPatch& p : plan->patches) {
+        const Launch& L = plan->launches[size_t(p.launch)];
+        p.in_value = L.in_binding >= 0 ? bindings[L.in_binding] : nullptr;
+        p.out_value = L.out_binding >= 0 ? bindings[L.out_binding] : nullptr;
+    }
+    return B2_OK;
+}
+
+// Points the binding-dependent nodes at this request's buffers (no-op for pointers the graph already holds).
+int patch_plan_graph(Plan* plan, void* const* bindings) {
+    for (BindPatch& p : plan->patches) {
+        const Launch& L = plan->launches[size_t(p.launch)];
+        void* in = L.in_binding >= 0 ? bindings[L.in_binding] : nullptr;
+        void* out = L.out_binding >= 0 ? bindings[L.out_binding] : nullptr;
+        if (in == p.in_value && out == p.out_value) continue;
+        p.in_value = in, p.out_value = out;
+        if (p.is_tail) {
+            p.tail.out = static_cast<float*>(out);
+            p.params[0] = &p.tail;
+        } else {
+            if (p.in_index >= 0) p.params[size_t(p.in_index)] = &p.in_value;
+            if (p.out_index >= 0) p.params[size_t(p.out_index)] = &p.out_value;
+        }
+        cudaKernelNodeParams np = p.np;
+        np.kernelParams = p.params.data();
+        np.extra = nullptr;
+        B2_CUDA(cudaGraphExecKernelNodeSetParams(plan->exec, p.node, &np));
+    }
+    return B2_OK;
+}
+
 int check_args(b2_context* c, int batch, void* const* bindings) {
     if (!c || !bindings) return fail(B2_EINVAL, "null context or bindings");
     if (batch < 1 || batch > c->e->max_batch) return fail(B2_EINVAL, "batch %d outside [1, %d]", batch, c->e->max_batch);
@@ -1692,9 +1831,15 @@ int b2_context_prepare(b2_context* c, int batch, b2_stream_t stream_) {
         B2_CUDA(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
         stream = own;
     }
-    std::vector<void*> dummy(c->e->bindings.size(), reinterpret_cast<void*>(uintptr_t(256)));  // never dereferenced: no launch of a graphable segment reads a binding
-    for (Segment& sg : plan->segments)
-        if (sg.graphable && !sg.exec && (rc = instantiate_segment(c, plan, &sg, dummy.data(), stream))) break;
+    // placeholder binding pointers: a capture only RECORDS launches, and every request re-points the nodes that use them
+    std::vector<void*> dummy(c->e->bindings.size(), reinterpret_cast<void*>(uintptr_t(256)));
+    if (c->use_graph != 3 && !plan->exec && !plan->graph_failed) {
+        rc = instantiate_plan_graph(c, plan, dummy.data(), stream);
+        plan->graph_failed = !rc && plan->exec == nullptr;
+    }
+    if (!rc && !plan->exec)
+        for (Segment& sg : plan->segments)
+            if (sg.graphable && !sg.exec && (rc = instantiate_segment(c, plan, &sg, dummy.data(), stream))) break;
     if (own) cudaStreamDestroy(own);
     return rc;
 }
@@ -1712,13 +1857,22 @@ int b2_context_enqueue(b2_context* c, int batch, void* const* bindings, b2_strea
     if (cap != cudaStreamCaptureStatusNone || !c->use_graph || plan->has_net) {
         if ((rc = run_all(c, *plan, bindings, stream))) return rc;
     } else {
-        for (Segment& sg : plan->segments) {
-            if (!sg.graphable) {
-                if ((rc = run_range(c, *plan, size_t(sg.begin), size_t(sg.end), bindings, stream))) return rc;
-                continue;
+        if (c->use_graph != 3 && !plan->exec && !plan->graph_failed) {
+            if ((rc = instantiate_plan_graph(c, plan, bindings, stream))) return rc;
+            plan->graph_failed = plan->exec == nullptr;
+        }
+        if (plan->exec) {  // one graph for the whole forward pass, re-pointed at this request's bindings
+            if ((rc = patch_plan_graph(plan, bindings))) return rc;
+            B2_CUDA(cudaGraphLaunch(plan->exec, stream));
+        } else {
+            for (Segment& sg : plan->segments) {
+                if (!sg.graphable) {
+                    if ((rc = run_range(c, *plan, size_t(sg.begin), size_t(sg.end), bindings, stream))) return rc;
+                    continue;
+                }
+                if (!sg.exec && (rc = instantiate_segment(c, plan, &sg, bindings, stream))) return rc;
+                B2_CUDA(cudaGraphLaunch(sg.exec, stream));
             }
-            if (!sg.exec && (rc = instantiate_segment(c, plan, &sg, bindings, stream))) return rc;
-            B2_CUDA(cudaGraphLaunch(sg.exec, stream));
         }
     }
     if (consumed) B2_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(consumed), stream));

@@ -12,6 +12,7 @@
 #include "kernels.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ptx_sm100.cuh"
@@ -1708,21 +1709,25 @@ int launch_softmax(const float* in, float* out, int N, int C, cudaStream_t strea
 //   that of avgpool_h8_kernel / fc_h8_kernel / softmax_kernel: results are bit-identical to the unfused path.
 //   Reference ops: models/ResNet-50-deploy.prototxt:2292-2302 (pool5) + InnerProduct + Softmax.
 // =================================================================================================
-__device__ __forceinline__ int tail_ld_acquire(const int* p) {
+__device__ __forceinline__ int tail_ld_relaxed(const int* p) {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// A POLITE wait: relaxed loads with back-off while the counter is short, ONE acquire fence once it is not.  (An
+// acquire load per iteration costs an L1 invalidation each time -- on an SM this CTA shares with other streams' kernels.)
 __device__ __forceinline__ void tail_wait_counter(const int* p, int need) {
     uint32_t spins = 0;
     long long t0 = 0;
-    while (tail_ld_acquire(p) < need) {
-        if ((++spins & 0x3FFFu) == 0) {
+    while (tail_ld_relaxed(p) < need) {
+        __nanosleep(200);
+        if ((++spins & 0xFFFu) == 0) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
             else if (now - t0 > 4000000000LL) __trap();
         }
     }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(256) tail_f16_kernel(const TailArgs a) {
@@ -1892,14 +1897,22 @@ bool tail_f16_applies(int N, int HW, int C, int Cout) { return N >= 1 && HW >= 1
 int launch_tail_f16(const TailArgs& a, cudaStream_t stream) {
     if (!tail_f16_applies(a.N, a.HW, a.C, a.Cout)) return static_cast<int>(cudaErrorInvalidValue);
     const int items = a.N * ((a.C / 8 + 31) / 32) + (a.Cout + 7) / 8 + a.N;
-    const unsigned blocks = static_cast<unsigned>(items < 148 ? items : 148);
+    static int cap = -1, use_pdl = -1;
+    if (cap < 0) {
+        const char* v = getenv("B2_TAIL_CTAS");
+        cap = v ? atoi(v) : 64;  // a small grid: the items are tiny and early-launched CTAs hold shared memory other streams want
+        if (cap < 1) cap = 1;
+        v = getenv("B2_TAIL_PDL");
+        use_pdl = v ? atoi(v) : 1;
+    }
+    const unsigned blocks = static_cast<unsigned>(items < cap ? items : cap);
     const size_t smem = static_cast<size_t>(a.C) * 2 * 8;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(tail_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set = true;
     }
-    B2_LAUNCH_RC = launch_kernel(tail_f16_kernel, dim3(blocks), dim3(256), smem, stream, true, a);
+    B2_LAUNCH_RC = launch_kernel(tail_f16_kernel, dim3(blocks), dim3(256), smem, stream, use_pdl != 0, a);
     return B2_LAUNCH_RC;
 }
 

@@ -4,6 +4,7 @@
 #include "trtlab/tensorrt/tensorrt.h"
 
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <fstream>
@@ -334,7 +335,18 @@ InferenceManager::InferenceManager(int max_executions, int max_buffers)  // infe
 
 InferenceManager::~InferenceManager() { JoinAllThreads(); }
 
-void InferenceManager::ActivateDevice() const { TRT_CHECK_CUDA(cudaSetDevice(m_Device)); }
+// Pool threads adopt the manager's device -- and, once per thread, the CPUs closest to it (reference
+// trtlab/cuda/src/device_info.cc:66-85 DeviceInfo::Affinity; TRTLAB_AFFINITY=0 disables): with one replica per GPU the
+// pre / cuda / post stages of replica i then run next to GPU i's PCIe root and its NUMA-local pinned Buffers.
+void InferenceManager::ActivateDevice() const {
+    TRT_CHECK_CUDA(cudaSetDevice(m_Device));
+    static thread_local int bound_to = -1;
+    if (bound_to != m_Device) {
+        bound_to = m_Device;
+        const char* v = getenv("TRTLAB_AFFINITY");
+        if (!v || atoi(v) != 0) b2_bind_thread_to_device(m_Device, nullptr);
+    }
+}
 
 void InferenceManager::RecordComputeTime(double seconds) {
     m_ComputeNs.fetch_add(uint64_t(seconds * 1e9), std::memory_order_relaxed);
@@ -451,8 +463,18 @@ void InferenceManager::AllocateResources() {  // inference_manager.cc:181-205
     TRTLAB_LOG_INFO << "Total GPU Memory: " << BytesToString(m_MaxBuffers * m_DeviceStackSize + m_MaxExecutions * m_ActivationsSize);
 
     m_Buffers = Pool<Buffers>::Create();
-    for (int i = 0; i < m_MaxBuffers; i++)
-        m_Buffers->Push(std::make_shared<FixedBuffers<CudaPinnedHostMemory, CudaDeviceMemory>>(m_HostStackSize, m_DeviceStackSize));
+    {
+        // pinned host stacks on the GPU's NUMA node: the allocating thread sits on the GPU's CPUs while the pages are
+        // first touched (cudaHostAlloc follows the thread's local policy), then gets its own mask back
+        cpu_set_t before;
+        const bool have = sched_getaffinity(0, sizeof before, &before) == 0;
+        const char* v = getenv("TRTLAB_AFFINITY");
+        int bound = 0;
+        if (!v || atoi(v) != 0) b2_bind_thread_to_device(m_Device, &bound);
+        for (int i = 0; i < m_MaxBuffers; i++)
+            m_Buffers->Push(std::make_shared<FixedBuffers<CudaPinnedHostMemory, CudaDeviceMemory>>(m_HostStackSize, m_DeviceStackSize));
+        if (have && bound > 0) sched_setaffinity(0, sizeof before, &before);
+    }
 
     // m_MaxExecutions lanes (activation arenas == forward passes that can run at once), EnqueueDepth() tokens queued on each
     m_ExecutionContexts = Pool<ExecutionContext>::Create();

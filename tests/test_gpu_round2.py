@@ -60,7 +60,7 @@ def test_onnx_imported_resnet50_on_the_gpu(rn50):
     net2, w2 = onnx_import.import_onnx(model, name="ResNet-50-onnx")
     low2 = graph.lower(net2, w2)
     x = rn50["x"][:4]
-    got = helpers.run_engine(low2, x, builder.PREC_FP16, max_batch=8)["prob"]
+    got = list(helpers.run_engine(low2, x, builder.PREC_FP16, max_batch=8).values())[0]  # (the importer names the output after the ONNX value)
     ref32 = caffe_forward(net2, w2, x)
     assert (got.argmax(1) == ref32.argmax(1)).all()
     assert (np.abs(got - ref32) / ref32.max(1, keepdims=True)).max() <= 1e-3

@@ -22,6 +22,20 @@ for st in settings:
         os.environ["B2_NET_CTAS"] = kv["ctas"]
     if "bn" in kv:
         os.environ["B2_NET_BN"] = kv["bn"]
+    for k in ("B2_FUSE_TAIL", "B2_GRAPH", "B2_AUTOTUNE", "B2_ARENA_SLACK", "B2_TAIL_CTAS", "B2_TAIL_PDL"):
+        os.environ.pop(k, None)
+    if "tail" in kv:
+        os.environ["B2_FUSE_TAIL"] = kv["tail"]
+    if "graph" in kv:
+        os.environ["B2_GRAPH"] = kv["graph"]
+    if "tctas" in kv:
+        os.environ["B2_TAIL_CTAS"] = kv["tctas"]
+    if "tpdl" in kv:
+        os.environ["B2_TAIL_PDL"] = kv["tpdl"]
+    if "slack" in kv:
+        os.environ["B2_ARENA_SLACK"] = kv["slack"]
+    if "tune" in kv:
+        os.environ["B2_AUTOTUNE"] = kv["tune"]
     ctx = int(kv.get("ctx", "4"))
     try:
         ms, nl = capi.device_throughput(blob, ctx, BATCH, steps, 40, ring)
