@@ -14,14 +14,14 @@ import numpy as np
 
 from . import graph as G
 
-PREC_FP32, PREC_FP16 = 0, 1
-OP_INPUT_CAST, OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_FC, OP_SOFTMAX, OP_OUTPUT_CAST = range(7)
+PREC_FP32, PREC_FP16, PREC_INT8 = 0, 1, 2
+OP_INPUT_CAST, OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_FC, OP_SOFTMAX, OP_OUTPUT_CAST, OP_QUANTIZE = range(8)
 T_ACT, T_VEC = 0, 1
 MAGIC = b"B2ENGINE"
 VERSION = 1
 
 _HEADER = struct.Struct("<8sIIIIIIQQ64s16x")
-_TENSOR = struct.Struct("<64sIIIIIi8x")
+_TENSOR = struct.Struct("<64sIIIIIif4x")  # ... binding, scale (INT8 tensors: real value = q * scale; 0 = fp16 / fp32 tensor)
 _OP = struct.Struct("<64sIiiiiIIIIIIIIIIIQQQQIIII")
 _BINDING = struct.Struct("<64sIIiI8i16x")
 assert _HEADER.size == 128 and _TENSOR.size == 96 and _OP.size == 176 and _BINDING.size == 128
@@ -81,6 +81,19 @@ def pack_weights_sw128(W: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(out).reshape(-1)
 
 
+def pack_weights_sw128_i8(W: np.ndarray) -> np.ndarray:
+    """INT8 twin of :func:`pack_weights_sw128`: [Cout_phys, K] int8 (K % 128 == 0) -> blocks [K/128][Cout/32][32 rows][128 B],
+    16-byte chunk j of row r at chunk j ^ (r % 8): the shared-memory image of a 128-K weight sub-tile."""
+    cout, K = W.shape
+    assert cout % 32 == 0 and K % 128 == 0 and W.dtype == np.int8
+    blk = W.reshape(cout // 32, 32, K // 128, 8, 16).transpose(2, 0, 1, 3, 4)   # [kb, nb, r, chunk, 16 bytes]
+    out = np.empty_like(blk)
+    r = np.arange(32)
+    for j in range(8):
+        out[:, :, r, j ^ (r % 8), :] = blk[:, :, r, j, :]
+    return np.ascontiguousarray(out).reshape(-1)
+
+
 def _name(s: str) -> bytes:
     b = s.encode()
     if len(b) > 63:
@@ -99,9 +112,17 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
     ``outputs``: tensor names to expose as output bindings (default: the graph output).  4-D activation
     outputs get an ``OUTPUT_CAST`` to fp32 NCHW; vector outputs (fc / softmax) are written in place.
     """
-    if precision not in (PREC_FP32, PREC_FP16):
-        raise ValueError("precision must be PREC_FP32 or PREC_FP16")
-    wdtype = np.float16 if precision == PREC_FP16 else np.float32
+    if precision not in (PREC_FP32, PREC_FP16, PREC_INT8):
+        raise ValueError("precision must be PREC_FP32, PREC_FP16 or PREC_INT8")
+    int8 = precision == PREC_INT8
+    if int8 != bool(lowered.get("int8")):
+        raise ValueError("PREC_INT8 takes a graph quantized by quantize.quantize_lowered (and only that precision does)")
+    tscale = lowered.get("tensor_scales", {})   # INT8 tensors: name -> scale
+    if int8:  # the fp16 part of an INT8 engine follows the fp16 engine's layout rules
+        precision_fp = PREC_FP16
+    else:
+        precision_fp = precision
+    wdtype = np.float16 if precision_fp == PREC_FP16 else np.float32
     outputs = list(outputs) if outputs else [lowered["output"]]
     shapes: Dict[str, tuple] = dict(lowered["tensors"])
     vec_tensors = {op["output"] for op in lowered["ops"] if op["type"] in (G.OP_FC, G.OP_SOFTMAX)}
@@ -115,8 +136,10 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
         c, h, w = shapes[tname]
         if tname in vec_tensors:
             rec = dict(name=tname, kind=T_VEC, h=1, w=1, c=c * h * w, c_phys=c * h * w, binding=-1)
+        elif tname in tscale:  # INT8 activations: one 128-byte swizzle row = 128 channels
+            rec = dict(name=tname, kind=T_ACT, h=h, w=w, c=c, c_phys=_roundup(c, 128), binding=-1, scale=float(np.float32(tscale[tname])))
         else:
-            rec = dict(name=tname, kind=T_ACT, h=h, w=w, c=c, c_phys=phys_channels(c, precision), binding=-1)
+            rec = dict(name=tname, kind=T_ACT, h=h, w=w, c=c, c_phys=phys_channels(c, precision_fp), binding=-1)
         tindex[tname] = len(tensors)
         tensors.append(rec)
         return tindex[tname]
@@ -136,7 +159,7 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
     # input binding + cast
     cin, hin, win = lowered["input_shape"]
     t_in = add_tensor(lowered["input"])
-    if input_dtype not in ("f32", "f16") or (input_dtype == "f16" and precision != PREC_FP16):
+    if input_dtype not in ("f32", "f16") or (input_dtype == "f16" and precision_fp != PREC_FP16):
         raise ValueError("input_dtype is 'f32' (the reference's binding contract) or, for fp16 engines, 'f16'")
     bindings.append(dict(name=lowered["input"], is_input=1, dtype=1 if input_dtype == "f16" else 0, tensor=t_in,
                          dims=[cin, hin, win]))
@@ -145,7 +168,7 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
     # horizontally space-to-depth packed copy of the input (see stem_s2d_transform)
     readers = [o for o in lowered["ops"] if o["input"] == lowered["input"] or o.get("residual") == lowered["input"]]
     s2d_op = None
-    if (precision == PREC_FP16 and stem_s2d and len(readers) == 1 and readers[0]["type"] == G.OP_CONV
+    if (precision_fp == PREC_FP16 and stem_s2d and len(readers) == 1 and readers[0]["type"] == G.OP_CONV
             and readers[0]["stride"] == 2 and cin <= 4 and win % 2 == 0 and lowered["input"] not in outputs
             and readers[0]["k"] >= 3):
         s2d_op = readers[0]
@@ -160,7 +183,26 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
         ti = add_tensor(op["input"])
         to = add_tensor(op["output"])
         rec = dict(name=op["name"], inp=ti, res=-1, out=to, binding=-1)
-        if t == G.OP_CONV:
+        if t == "quantize":
+            rec.update(type=OP_QUANTIZE)
+        elif t == G.OP_CONV and op.get("int8"):
+            cin_phys, cout_phys = tensors[ti]["c_phys"], tensors[to]["c_phys"]
+            k = op["k"]
+            taps = k * k
+            Wq = np.zeros((cout_phys, taps, cin_phys), dtype=np.int8)
+            Wq[:op["cout"], :, :op["cin"]] = op["Wq"].reshape(op["cout"], taps, op["cin"])
+            w_off, w_bytes = add_payload(pack_weights_sw128_i8(Wq.reshape(cout_phys, taps * cin_phys)))
+            rq = np.zeros(2 * cout_phys + 4, dtype=np.float32)   # [m | b | r 0 0 0]; padded channels requantise to 0
+            rq[:op["cout"]] = op["m"]
+            rq[cout_phys:cout_phys + op["cout"]] = op["b"]
+            rq[2 * cout_phys] = op["r"] if op["r"] is not None else 0.0
+            b_off, b_bytes = add_payload(rq)
+            rec.update(type=OP_CONV, k=k, stride=op["stride"], pad=op["pad"], relu=int(op["relu"]) | 2 | 4,
+                       cin=op["cin"], cout=op["cout"], cin_phys=cin_phys, cout_phys=cout_phys, taps=taps, taps_phys=taps,
+                       w_off=w_off, w_bytes=w_bytes, b_off=b_off, b_bytes=b_bytes)
+            if op["residual"] is not None:
+                rec["res"] = add_tensor(op["residual"])
+        elif t == G.OP_CONV:
             if "W" not in op:
                 raise ValueError(f"conv {op['name']}: lowered graph carries no weights")
             cin_phys = tensors[ti]["c_phys"]
@@ -172,12 +214,12 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
                 Wsrc, kw2, pad_lo, pad_hi = stem_s2d_transform(op["W"], k, op["pad"], win)
                 cin_eff, taps = 8, k * kw2
                 extra = dict(kw=kw2, stride_w=1, pad_w_lo=0, pad_w_hi=0, ceil_mode=op["cin"] * k * k)
-            taps_phys = _roundup(taps, 2) if (precision == PREC_FP16 and cin_phys == 8) else taps
+            taps_phys = _roundup(taps, 2) if (precision_fp == PREC_FP16 and cin_phys == 8) else taps
             W = np.zeros((cout_phys, taps_phys, cin_phys), dtype=np.float32)
             W[:op["cout"], :taps, :cin_eff] = Wsrc.reshape(op["cout"], taps, cin_eff)
             bias = np.zeros(cout_phys, dtype=np.float32)
             bias[:op["cout"]] = op["bias"]
-            packed = precision == PREC_FP16 and cin_phys % 64 == 0 and cout_phys % 32 == 0 and pack_weights
+            packed = precision_fp == PREC_FP16 and cin_phys % 64 == 0 and cout_phys % 32 == 0 and pack_weights
             if packed:
                 w_off, w_bytes = add_payload(pack_weights_sw128(W.astype(np.float16).reshape(cout_phys, taps_phys * cin_phys)))
             else:
@@ -229,7 +271,7 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
     blob += _HEADER.pack(MAGIC, VERSION, precision, max_batch, len(tensors), len(ops), len(bindings),
                          payload_offset, len(payload), _name(name or lowered["name"]))
     for t in tensors:
-        blob += _TENSOR.pack(_name(t["name"]), t["kind"], t["h"], t["w"], t["c"], t["c_phys"], t["binding"])
+        blob += _TENSOR.pack(_name(t["name"]), t["kind"], t["h"], t["w"], t["c"], t["c_phys"], t["binding"], t.get("scale", 0.0))
     for o in ops:
         blob += _OP.pack(_name(o["name"]), o["type"], o["inp"], o["res"], o["out"], o["binding"],
                          o.get("k", 0), o.get("stride", 0), o.get("pad", 0), o.get("relu", 0), o.get("ceil_mode", 0),
@@ -246,11 +288,16 @@ def build_plan(lowered: dict, precision: int = PREC_FP16, max_batch: int = 8,
 
 
 def build_resnet_plan(depth: int = 50, precision: int = PREC_FP16, max_batch: int = 8, seed: int = 0,
-                      input_dtype: str = "f32") -> bytes:
-    """Convenience: generated Caffe-v1 ResNet + deterministic weights -> plan."""
+                      input_dtype: str = "f32", calib_batch: int = 8) -> bytes:
+    """Convenience: generated Caffe-v1 ResNet + deterministic weights -> plan.  PREC_INT8: post-training quantization
+    calibrated (max-abs) on ``calib_batch`` synthetic images (seed 4321), see quantize.py."""
     from . import weights as Wt
     net = G.resnet_caffe(depth)
-    return build_plan(G.lower(net, Wt.random_weights(net, seed)), precision, max_batch, input_dtype=input_dtype)
+    low = G.lower(net, Wt.random_weights(net, seed))
+    if precision == PREC_INT8:
+        from . import quantize
+        low = quantize.quantize_lowered(low, Wt.synthetic_input(calib_batch, seed=4321))
+    return build_plan(low, precision, max_batch, input_dtype=input_dtype)
 
 
 def single_conv_net(cin: int, h: int, w: int, cout: int, k: int, stride: int, pad: int, relu: bool = True,

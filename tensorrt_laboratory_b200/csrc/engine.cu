@@ -95,6 +95,7 @@ struct Tensor {
     std::string name;
     uint32_t kind, h, w, c, c_phys;
     int binding;
+    float scale = 0.f;      // > 0: int8 tensor (INT8 engines), real value = q * scale
     size_t item_bytes = 0;  // bytes per batch item
     size_t offset = 0;      // arena offset (binding < 0)
     int def = -1, last_use = -1;
@@ -127,7 +128,7 @@ struct Binding {
     size_t item_bytes;
 };
 
-enum LKind { L_INPUT_CAST, L_CONV_TC, L_CONV_SIMT, L_MAXPOOL, L_AVGPOOL, L_FC, L_SOFTMAX, L_OUTPUT_CAST, L_NET, L_TAIL };
+enum LKind { L_INPUT_CAST, L_CONV_TC, L_CONV_SIMT, L_MAXPOOL, L_AVGPOOL, L_FC, L_SOFTMAX, L_OUTPUT_CAST, L_NET, L_TAIL, L_QUANTIZE, L_CONV_I8, L_AVGPOOL_I8, L_OUTPUT_CAST_I8 };
 
 // A run of consecutive tcgen05 convolution layers executed by ONE persistent kernel (net_kernel.cu): device-side layer
 // table, dependency ranges and arrival counters live in one allocation owned by the plan.
@@ -156,6 +157,9 @@ struct Launch {
     int side_join = -1;     // see Op::side_join (launch index == op index)
     std::shared_ptr<NetRun> net;  // L_NET
     b2k::TailArgs tail{};         // L_TAIL: pool + fc + softmax in one launch (out = the output binding)
+    b2k::I8ConvLaunch i8{};       // L_CONV_I8
+    float qscale = 0.f;           // L_QUANTIZE: 1/s; L_AVGPOOL_I8: s/HW; L_OUTPUT_CAST_I8: s
+    int C_in_phys = 0;            // L_QUANTIZE / L_AVGPOOL_I8: channel pitch of the source tensor
     bool net_member = false;      // L_CONV_TC that build_plan folds into an L_NET launch
     int N = 0, C = 0, H = 0, W = 0, C_phys = 0, Ho = 0, Wo = 0, k = 0, stride = 0, pad = 0, K = 0, Cout = 0;
 };
@@ -252,9 +256,11 @@ struct b2_engine {
     std::mutex tune_run_mutex;  // serialises on-device tactic timing across contexts of this engine
     std::map<std::pair<int, int>, ConvConfig> tuned;  // (op index, batch) -> measured-best configuration
     bool tune_cache_loaded = false;
+    std::map<int, float> requant_r;  // INT8 convs: op index -> r = fl(s_res / s_out) (read from the plan's requantisation block)
     bool tactics_from_plan = false;  // the blob carried a tactic table: nothing left to tune
     bool tuned_at_load = false;      // b2_engine_tune has run
-    bool half() const { return precision == B2_PREC_FP16; }
+    bool half() const { return precision != B2_PREC_FP32; }  // fp16 storage and kernels (INT8 engines: their fp16 part)
+    bool int8() const { return precision == B2_PREC_INT8; }
 };
 
 struct b2_context {
@@ -291,6 +297,7 @@ struct b2_context {
     int net_ctas = 0;  // CTAs of that kernel (0 = one per SM); a server running N contexts gives each about 148 / N
     int net_bn = 0;    // force its N tile (64 / 128); 0 = 128 wherever the channel count allows
     int net_stages = 0;  // force its shared-memory ring depth (2..4); 0 = the deepest that lets two CTAs share an SM
+    int i8_bn = 0;       // INT8 convolutions: force the N tile (128 / 256); 0 = 128
     int fuse_tail = 1;   // global average pool + FC + softmax as one launch (tail_f16_kernel)
     int* d_tail_ctrl = nullptr;  // its ticket / arrival counters (zero between launches)
     cudaStream_t side = nullptr;
@@ -314,7 +321,7 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
     memcpy(&h, base, sizeof h);
     if (memcmp(h.magic, kMagic, 8) != 0) return fail(B2_EINVAL, "plan: bad magic (not a B2ENGINE blob)");
     if (h.version != kVersion) return fail(B2_EINVAL, "plan: version %u, this library reads %u", h.version, kVersion);
-    if (h.precision > 1) return fail(B2_EINVAL, "plan: unknown precision %u", h.precision);
+    if (h.precision > 2) return fail(B2_EINVAL, "plan: unknown precision %u", h.precision);
     if (h.max_batch == 0 || h.max_batch > 4096) return fail(B2_EINVAL, "plan: bad max_batch %u", h.max_batch);
     const size_t tbl = sizeof(Header) + size_t(h.n_tensors) * sizeof(TensorRec) + size_t(h.n_ops) * sizeof(OpRec) +
                        size_t(h.n_bindings) * sizeof(BindingRec);
@@ -325,7 +332,7 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
     e->precision = h.precision;
     e->max_batch = h.max_batch;
     e->payload_bytes = h.payload_bytes;
-    const size_t elt = h.precision == B2_PREC_FP16 ? 2 : 4;
+    const size_t elt = h.precision == B2_PREC_FP32 ? 4 : 2;
     const uint8_t* p = base + sizeof(Header);
     for (uint32_t i = 0; i < h.n_tensors; ++i, p += sizeof(TensorRec)) {
         TensorRec r;
@@ -335,9 +342,12 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
         t.kind = r.kind;
         t.h = r.h, t.w = r.w, t.c = r.c, t.c_phys = r.c_phys;
         t.binding = r.binding;
+        t.scale = h.precision == B2_PREC_INT8 ? r.scale : 0.f;
+        if (!(t.scale >= 0.f) || (t.scale > 0.f && (r.kind != T_ACT || r.c_phys % 128)))
+            return fail(B2_EINVAL, "plan: tensor %s has a bad INT8 scale / layout", t.name.c_str());
         if (r.kind == T_ACT) {
             if (r.c_phys < r.c || r.h == 0 || r.w == 0) return fail(B2_EINVAL, "plan: tensor %s has bad dims", t.name.c_str());
-            t.item_bytes = size_t(r.h) * r.w * r.c_phys * elt;
+            t.item_bytes = size_t(r.h) * r.w * r.c_phys * (t.scale > 0.f ? 1 : elt);
         } else if (r.kind == T_VEC) {
             t.item_bytes = size_t(r.c) * 4;
         } else {
@@ -352,7 +362,7 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
         memcpy(&op.r, p, sizeof(OpRec));
         op.name = fixed_str(op.r.name, 64);
         const OpRec& r = op.r;
-        if (r.type > OP_OUTPUT_CAST) return fail(B2_EINVAL, "plan: op %s has unknown type %u", op.name.c_str(), r.type);
+        if (r.type > OP_QUANTIZE) return fail(B2_EINVAL, "plan: op %s has unknown type %u", op.name.c_str(), r.type);
         const bool in_opt = r.type == OP_INPUT_CAST, out_opt = r.type == OP_OUTPUT_CAST;
         if (!tensor_ok(r.in, in_opt) || !tensor_ok(r.out, out_opt) || !tensor_ok(r.res, true))
             return fail(B2_EINVAL, "plan: op %s references a missing tensor", op.name.c_str());
@@ -360,11 +370,28 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
             return fail(B2_EINVAL, "plan: cast op %s has a bad binding", op.name.c_str());
         if (r.w_off + r.w_bytes > h.payload_bytes || r.b_off + r.b_bytes > h.payload_bytes)
             return fail(B2_EINVAL, "plan: op %s weights outside payload", op.name.c_str());
+        if (r.type == OP_QUANTIZE) {
+            const Tensor& ti = e->tensors[r.in];
+            const Tensor& to = e->tensors[r.out];
+            if (h.precision != B2_PREC_INT8 || ti.scale > 0.f || !(to.scale > 0.f) || ti.h != to.h || ti.w != to.w || ti.c != to.c)
+                return fail(B2_EINVAL, "plan: quantize %s needs an fp16 input and an int8 output of the same shape", op.name.c_str());
+        }
         if (r.type == OP_CONV) {
             if (r.k == 0 || r.stride == 0 || int(r.taps) != op.kh() * op.kw() || r.taps_phys < r.taps || op.sw() == 0)
                 return fail(B2_EINVAL, "plan: conv %s has bad geometry", op.name.c_str());
-            if (r.w_bytes != size_t(r.cout_phys) * r.taps_phys * r.cin_phys * elt || r.b_bytes != size_t(r.cout_phys) * 4)
+            const bool i8 = (r.relu & 4) != 0;
+            if (i8) {
+                const Tensor& qi = e->tensors[r.in];
+                const Tensor& qo = e->tensors[r.out];
+                if (h.precision != B2_PREC_INT8 || !(qi.scale > 0.f) || !(qo.scale > 0.f) || (r.res >= 0 && !(e->tensors[r.res].scale > 0.f)) ||
+                    r.cin_phys % 128 || r.cout_phys % 128 || r.taps_phys != r.taps || r.kw != 0 || !(r.relu & 2))
+                    return fail(B2_EINVAL, "plan: int8 conv %s: tensors must be int8 with 128-channel rows", op.name.c_str());
+                if (r.w_bytes != size_t(r.cout_phys) * r.taps_phys * r.cin_phys || r.b_bytes != (size_t(r.cout_phys) * 2 + 4) * 4)
+                    return fail(B2_EINVAL, "plan: int8 conv %s weight / requantisation size mismatch", op.name.c_str());
+            } else if (r.w_bytes != size_t(r.cout_phys) * r.taps_phys * r.cin_phys * elt || r.b_bytes != size_t(r.cout_phys) * 4)
                 return fail(B2_EINVAL, "plan: conv %s weight size mismatch", op.name.c_str());
+            if (!i8 && (e->tensors[r.in].scale > 0.f || e->tensors[r.out].scale > 0.f))
+                return fail(B2_EINVAL, "plan: fp16 conv %s touches an int8 tensor", op.name.c_str());
             const Tensor& ti = e->tensors[r.in];
             const Tensor& to = e->tensors[r.out];
             if (ti.c_phys != r.cin_phys || to.c_phys != r.cout_phys || ti.c != r.cin || to.c != r.cout)
@@ -487,12 +514,12 @@ void plan_arena(b2_engine* e) {
 
 // ---- tensor maps ------------------------------------------------------------------------------
 int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
-                uint32_t box_outer, CUtensorMapSwizzle swz) {
+                uint32_t box_outer, CUtensorMapSwizzle swz, bool int8 = false) {
     cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {inner * 2};
+    cuuint64_t strides[1] = {inner * (int8 ? 1u : 2u)};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+    CUresult r = g_encode_tiled(map, int8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -520,14 +547,14 @@ int make_map_nhwc(CUtensorMap* map, const void* base, int C, int W, int H, int N
 int make_map_im2col(CUtensorMap* map, const void* base, int C, int W, int H, int N, uint64_t pix_bytes,
                     uint64_t row_bytes, uint64_t img_bytes, int kh, int kw, int stride_h, int stride_w, int pad_h,
                     int pad_w_lo, int pad_w_hi, uint32_t channels_per_pixel, uint32_t pixels_per_column,
-                    CUtensorMapSwizzle swz) {
+                    CUtensorMapSwizzle swz, bool int8 = false) {
     cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
     cuuint64_t strides[3] = {pix_bytes, row_bytes, img_bytes};
     // fprop bounding box: base pixel positions run over [-pad, dim - 1 + pad - (k-1)] (dilation 1)
     int lower[2] = {-pad_w_lo, -pad_h};                            // (W, H) order
     int upper[2] = {pad_w_hi - (kw - 1), pad_h - (kh - 1)};
     cuuint32_t estr[4] = {1, cuuint32_t(stride_w), cuuint32_t(stride_h), 1};
-    CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
+    CUresult r = g_encode_im2col(map, int8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
                                  upper, channels_per_pixel, pixels_per_column, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -707,6 +734,50 @@ int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& c
     rc = make_map_2d(&cl.mapOut, tptr(r.out), r.cout_phys, uint64_t(M), ow, 128, oswz);
     if (rc) return rc;
     if (r.res >= 0) rc = make_map_2d(&cl.mapRes, tptr(r.res), r.cout_phys, uint64_t(M), ow, 128, oswz);
+    else cl.mapRes = cl.mapOut;
+    return rc;
+}
+
+// INT8 convolution launch (i8_kernels.cu): TMA maps over 1-byte tensors whose 128-byte rows hold 128 channels.
+int make_i8_conv_launch(b2_context* c, const Op& op, int batch, int bn, b2k::I8ConvLaunch* out) {
+    b2_engine* e = c->e;
+    const b2plan::OpRec& r = op.r;
+    const Tensor& ti = e->tensors[r.in];
+    const Tensor& to = e->tensors[r.out];
+    auto tptr = [&](int idx) -> uint8_t* { return c->scratch + e->tensors[idx].offset; };
+    b2k::I8ConvLaunch& cl = *out;
+    memset(&cl, 0, sizeof cl);
+    const int M = batch * int(to.h) * int(to.w);
+    cl.bn = bn;
+    cl.grid_m = (M + 127) / 128;
+    cl.grid_n = int(r.cout_phys) / bn;
+    b2k::I8ConvArgs& a = cl.args;
+    a.wpacked = e->d_payload + r.w_off;
+    const float* rq = reinterpret_cast<const float*>(e->d_payload + r.b_off);
+    a.m = rq;
+    a.b = rq + r.cout_phys;
+    a.r = e->requant_r.at(int(&op - &e->ops[0]));
+    a.has_res = r.res >= 0 ? 1 : 0;
+    a.relu = int(r.relu & 1);
+    a.M = M, a.Cout = int(r.cout_phys);
+    a.cblocks = int(r.cin_phys) / 128;
+    a.num_kblocks = int(r.taps) * a.cblocks;
+    a.kw = op.kw(), a.HoWo = int(to.h * to.w), a.Wo = int(to.w);
+    a.stride_h = op.sh(), a.stride_w = op.sw(), a.pad_h = op.ph(), a.pad_w = op.pw_lo();
+    const bool tiled = r.k == 1 && r.stride == 1 && r.pad_ == 0;
+    a.a_mode = tiled ? b2k::A_TILED : b2k::A_IM2COL;
+    int rc;
+    if (tiled)
+        rc = make_map_2d(&cl.mapA, tptr(r.in), r.cin_phys, uint64_t(M), 128, 128, CU_TENSOR_MAP_SWIZZLE_128B, true);
+    else {
+        const uint64_t pix = uint64_t(r.cin_phys), rowb = uint64_t(ti.w) * pix, imgb = uint64_t(ti.h) * rowb;
+        rc = make_map_im2col(&cl.mapA, tptr(r.in), int(r.cin_phys), int(ti.w), int(ti.h), batch, pix, rowb, imgb, op.kh(), op.kw(), op.sh(),
+                             op.sw(), op.ph(), op.pw_lo(), op.pw_hi(), 128, 128, CU_TENSOR_MAP_SWIZZLE_128B, true);
+    }
+    if (rc) return rc;
+    rc = make_map_2d(&cl.mapOut, tptr(r.out), r.cout_phys, uint64_t(M), 128, 128, CU_TENSOR_MAP_SWIZZLE_128B, true);
+    if (rc) return rc;
+    if (r.res >= 0) rc = make_map_2d(&cl.mapRes, tptr(r.res), r.cout_phys, uint64_t(M), 128, 128, CU_TENSOR_MAP_SWIZZLE_128B, true);
     else cl.mapRes = cl.mapOut;
     return rc;
 }
@@ -921,7 +992,7 @@ int tune_engine_batch(b2_context* c, int batch) {
     for (size_t i = 0; i < e->ops.size(); ++i) {
         const Op& op = e->ops[i];
         const b2plan::OpRec& r = op.r;
-        if (r.type != b2plan::OP_CONV || !e->half()) continue;
+        if (r.type != b2plan::OP_CONV || !e->half() || (r.relu & 4)) continue;  // (INT8 convolutions have one tactic)
         const bool kb64 = r.cin_phys % 64 == 0, kb8 = r.cin_phys == 8;
         if (!((kb64 || kb8) && r.cout_phys % 32 == 0 && (kb64 || r.taps_phys % 2 == 0))) continue;
         {
@@ -1166,9 +1237,20 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                 L.bytes = double(batch) * t.h * t.w * (t.c * 4.0 + t.c_phys * elt);
                 break;
             }
+            case b2plan::OP_QUANTIZE: {
+                const Tensor& ti = e->tensors[r.in];
+                const Tensor& to = e->tensors[r.out];
+                L.kind = L_QUANTIZE;
+                L.in = tptr(r.in), L.out = tptr(r.out);
+                L.C = ti.c, L.H = ti.h, L.W = ti.w, L.C_in_phys = ti.c_phys, L.C_phys = to.c_phys;
+                L.qscale = float(1.0 / double(to.scale));
+                L.bytes = double(batch) * (ti.item_bytes + to.item_bytes);
+                break;
+            }
             case b2plan::OP_OUTPUT_CAST: {
                 const Tensor& t = e->tensors[r.in];
-                L.kind = L_OUTPUT_CAST;
+                L.kind = t.scale > 0.f ? L_OUTPUT_CAST_I8 : L_OUTPUT_CAST;
+                L.qscale = t.scale;
                 L.in = tptr(r.in);
                 L.out_binding = r.binding;
                 L.C = t.c, L.H = t.h, L.W = t.w, L.C_phys = t.c_phys;
@@ -1187,7 +1269,13 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                 const bool kb8 = r.cin_phys == 8;
                 const bool tc_ok = half && !c->force_simt && (kb64 || kb8) && r.cout_phys % 32 == 0 &&
                                    (kb64 || r.taps_phys % 2 == 0);
-                if (tc_ok) {
+                if (r.relu & 4) {  // INT8 tensor path
+                    L.kind = L_CONV_I8;
+                    int bn = c->i8_bn > 0 ? c->i8_bn : 128;
+                    if (int(r.cout_phys) % bn || !b2k::conv_i8_config_exists(bn)) bn = 128;
+                    int rc = make_i8_conv_launch(c, op, batch, bn, &L.i8);
+                    if (rc) return rc;
+                } else if (tc_ok) {
                     L.kind = L_CONV_TC;
                     const int kbsz = conv_kb(c, op);
                     const int nkb = conv_num_kblocks(c, op);
@@ -1259,9 +1347,13 @@ int build_plan(b2_context* c, int batch, Plan** out) {
             }
             case b2plan::OP_AVGPOOL: {
                 const Tensor& ti = e->tensors[r.in];
-                L.kind = L_AVGPOOL;
+                L.kind = ti.scale > 0.f ? L_AVGPOOL_I8 : L_AVGPOOL;
                 L.in = tptr(r.in), L.out = tptr(r.out);
                 L.H = ti.h, L.W = ti.w, L.C_phys = ti.c_phys;
+                if (ti.scale > 0.f) {  // int8 in, fp16 out
+                    L.C = ti.c, L.C_in_phys = ti.c_phys, L.C_phys = e->tensors[r.out].c_phys;
+                    L.qscale = float(double(ti.scale) / double(ti.h * ti.w));
+                }
                 L.bytes = double(batch) * ti.item_bytes;
                 break;
             }
@@ -1344,6 +1436,14 @@ int run_launch(const b2_engine* e, const Launch& L, void* const* bindings, cudaS
             return b2k::launch_softmax(static_cast<const float*>(in), static_cast<float*>(out), L.N, L.C, s);
         case L_NET:
             return b2k::launch_net_f16_tcgen05(L.net->args, L.net->ctas, s);
+        case L_QUANTIZE:
+            return b2k::launch_quantize_h_to_i8(in, out, static_cast<long long>(L.N) * L.H * L.W, L.C, L.C_in_phys, L.C_phys, L.qscale, s);
+        case L_CONV_I8:
+            return b2k::launch_conv_i8_tcgen05(L.i8, s);
+        case L_AVGPOOL_I8:
+            return b2k::launch_avgpool_i8(in, out, L.N, L.H * L.W, L.C, L.C_in_phys, L.C_phys, L.qscale, s);
+        case L_OUTPUT_CAST_I8:
+            return b2k::launch_output_cast_i8(in, static_cast<float*>(out), L.N, L.C, L.H, L.W, L.C_phys, L.qscale, s);
         case L_TAIL: {
             b2k::TailArgs t = L.tail;
             t.out = static_cast<float*>(out);
@@ -1430,6 +1530,9 @@ bool patch_layout(const b2_engine* e, const Launch& L, BindPatch* p) {
             return true;
         case L_OUTPUT_CAST:
             p->n_params = 6, p->out_index = 1;                              // output_cast_kernel(src, dst, N, C, HW, C_phys)
+            return true;
+        case L_OUTPUT_CAST_I8:
+            p->n_params = 7, p->out_index = 1;                              // output_cast_i8_kernel(src, dst, N, C, HW, C_phys, s)
             return true;
         case L_FC:
             p->n_params = 7, p->out_index = 3;                              // fc kernels (in, w, bias, out, N, K, Cout)
@@ -1576,6 +1679,14 @@ static int deserialize_impl(b2_runtime* rt, const void* blob, size_t nbytes, boo
     const uint8_t* payload = nullptr;
     int rc = parse_blob(blob, nbytes, e.get(), &payload);
     if (rc) return rc;
+    for (size_t i = 0; i < e->ops.size(); ++i) {  // the fused-residual rescale factor is a kernel ARGUMENT: keep a host copy
+        const b2plan::OpRec& r = e->ops[i].r;
+        if (r.type == b2plan::OP_CONV && (r.relu & 4)) {
+            float rr = 0.f;
+            memcpy(&rr, payload + r.b_off + size_t(r.cout_phys) * 8, sizeof rr);
+            e->requant_r[int(i)] = rr;
+        }
+    }
     plan_arena(e.get());
     if (!inspect_only) {
         int dev = -1;
@@ -1590,6 +1701,7 @@ static int deserialize_impl(b2_runtime* rt, const void* blob, size_t nbytes, boo
         e->device = dev;
         rc = b2k::init_conv_kernels();
         if (!rc) rc = b2k::init_net_kernel();
+        if (!rc) rc = b2k::init_conv_i8_kernels();
         if (rc) return fail(B2_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaError_t(rc)));
         const size_t bytes = std::max<size_t>(e->payload_bytes, 256);
         if (rt && rt->alloc) {
@@ -1683,6 +1795,7 @@ int b2_context_create(b2_engine* e, b2_context** out) {
     c->net_bn = env_int("B2_NET_BN", 0);
     c->net_stages = env_int("B2_NET_STAGES", 0);
     c->fuse_tail = env_int("B2_FUSE_TAIL", 1);
+    c->i8_bn = env_int("B2_I8_BN", 0);
     if (getenv("B2_PDL")) b2k::set_pdl(env_int("B2_PDL", 1) != 0);
     void* p = nullptr;
     if (cudaMalloc(&p, (kMaxSplitTiles + 16) * sizeof(int)) != cudaSuccess || cudaMemset(p, 0, (kMaxSplitTiles + 16) * sizeof(int)) != cudaSuccess) {
@@ -1745,6 +1858,7 @@ int b2_context_set_option(b2_context* c, const char* key, int value) {
     else if (k == "net_bn") c->net_bn = value;
     else if (k == "net_stages") c->net_stages = value;
     else if (k == "fuse_tail") c->fuse_tail = value;
+    else if (k == "i8_bn") c->i8_bn = value;
     else if (k == "pdl_trigger") c->pdl_trigger = value;
     else if (k == "autotune") c->autotune = value;
     else if (k == "no_fold") c->no_fold = value;
@@ -1970,7 +2084,8 @@ const char* b2_context_launch_name(b2_context* c, int batch, int i) {
     static thread_local std::string s;
     const Launch* L = get_launch(c, batch, i);
     if (!L) return nullptr;
-    static const char* kinds[] = {"input_cast", "conv_tcgen05", "conv_simt", "maxpool", "avgpool", "fc", "softmax", "output_cast", "net_tcgen05", "tail_pool_fc_softmax"};
+    static const char* kinds[] = {"input_cast", "conv_tcgen05", "conv_simt", "maxpool", "avgpool", "fc", "softmax", "output_cast", "net_tcgen05", "tail_pool_fc_softmax",
+                                  "quantize", "conv_i8_tcgen05", "avgpool_i8", "output_cast_i8"};
     s = std::string(kinds[L->kind]) + ":" + L->name;
     if (L->kind == L_CONV_TC)
         s += " bn=" + std::to_string(L->conv.bn) + " kb=" + std::to_string(L->conv.kb) +
@@ -1980,6 +2095,9 @@ const char* b2_context_launch_name(b2_context* c, int batch, int i) {
              (L->conv.args.a_mode == b2k::A_TILED ? " tiled" : " im2col") +
              " grid=" + std::to_string(L->conv.grid_n) + "x" + std::to_string(L->conv.grid_m) + "x" +
              std::to_string(L->conv.args.splits) + " kblk=" + std::to_string(L->conv.args.num_kblocks);
+    if (L->kind == L_CONV_I8)
+        s += " bn=" + std::to_string(L->i8.bn) + (L->i8.args.a_mode == b2k::A_TILED ? " tiled" : " im2col") + " grid=" +
+             std::to_string(L->i8.grid_n) + "x" + std::to_string(L->i8.grid_m) + " kblk=" + std::to_string(L->i8.args.num_kblocks);
     if (L->kind == L_NET)
         s += " layers=" + std::to_string(L->net->args.n_layers) + " tiles=" + std::to_string(L->net->args.total_tiles) +
              " ctas=" + std::to_string(L->net->ctas) + " stages=" + std::to_string(L->net->args.stages);

@@ -125,6 +125,37 @@ int net_smem_bytes(int n_layers, int stages);
 int launch_net_f16_tcgen05(const NetArgs& a, int ctas, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
+// INT8 path (i8_kernels.cu): tcgen05.mma.kind::i8 convolution with a requantising epilogue + its SIMT helpers
+// ---------------------------------------------------------------------------------------------
+struct I8ConvArgs {
+    const uint8_t* wpacked;  // int8 weights as pre-swizzled blocks [num_kblocks][Cout/32][32][128 B] (K-block = 128 bytes)
+    const float* m;          // [Cout] fl(s_in * s_w[c] / s_out)
+    const float* b;          // [Cout] fl(bias[c] / s_out)
+    float r;                 // fl(s_res / s_out) (fused residual)
+    int has_res, relu;
+    int M, Cout, num_kblocks, cblocks;  // cblocks = Cin_phys / 128
+    int kw, HoWo, Wo, stride_h, stride_w, pad_h, pad_w, a_mode;
+};
+struct I8ConvLaunch {
+    CUtensorMap mapA;    // int8 activations: 2-D tiled [M, Cin] (box 128 rows x 128 B) or 4-D im2col
+    CUtensorMap mapOut;  // int8 output store: 2-D tiled [M, Cout], box 128 x 128 B, 128B swizzle
+    CUtensorMap mapRes;  // int8 residual load, same geometry
+    I8ConvArgs args;
+    int bn, grid_m, grid_n;
+};
+int init_conv_i8_kernels();
+bool conv_i8_config_exists(int bn);
+int conv_i8_smem_bytes(int bn, bool residual);
+int launch_conv_i8_tcgen05(const I8ConvLaunch& L, cudaStream_t stream);
+// fp16 NHWC -> int8 NHWC, q = clip(rint(fl(float(h) * inv_s)), +-127); channels >= C are written as zeros
+int launch_quantize_h_to_i8(const void* src, void* dst, long long pixels, int C, int C_in_phys, int C_out_phys, float inv_s,
+                            cudaStream_t stream);
+// global average pool int8 NHWC -> fp16 [N][C_out_phys]: h = fp16(fl(float(sum q) * k))
+int launch_avgpool_i8(const void* src, void* dst, int N, int HW, int C, int C_in_phys, int C_out_phys, float k, cudaStream_t stream);
+// int8 NHWC -> fp32 NCHW binding: y = fl(float(q) * s)
+int launch_output_cast_i8(const void* src, float* dst, int N, int C, int H, int W, int C_phys, float s, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
 // SIMT kernels (reference/fp32 engine path, and the non-GEMM operators of the fp16 path)
 // ---------------------------------------------------------------------------------------------
 struct SimtConvArgs {

@@ -17,7 +17,8 @@ enum OpType : uint32_t {
     OP_AVGPOOL = 3,      // global average pool
     OP_FC = 4,           // inner product -> fp32 vector
     OP_SOFTMAX = 5,      // fp32 vector -> fp32 vector
-    OP_OUTPUT_CAST = 6,  // NHWC activation tensor -> fp32 NCHW binding
+    OP_OUTPUT_CAST = 6,  // NHWC activation tensor -> fp32 NCHW binding (dequantised when the tensor is int8)
+    OP_QUANTIZE = 7,     // fp16 NHWC tensor -> int8 NHWC tensor (INT8 engines: in front of the first int8 convolution)
 };
 
 enum TensorKind : uint32_t { T_ACT = 0 /* NHWC, engine precision */, T_VEC = 1 /* [N, c] fp32 */ };
@@ -48,7 +49,8 @@ struct TensorRec {  // 96 bytes
     uint32_t kind;
     uint32_t h, w, c, c_phys;
     int32_t binding;  // >= 0: storage is bindings[binding] (T_VEC only), -1: activation arena
-    uint8_t pad[8];
+    float scale;      // INT8 engines: > 0 marks an int8 tensor (1 byte per element, real value = q * scale); 0 = fp16 / fp32
+    uint8_t pad[4];
 };
 struct OpRec {  // 176 bytes
     char name[64];
@@ -56,7 +58,9 @@ struct OpRec {  // 176 bytes
     int32_t in, res, out;  // tensor indices (-1 = none)
     int32_t binding;       // cast ops: binding index
     uint32_t k, stride, pad_;
-    uint32_t relu;         // bit 0: fused ReLU.  bit 1 (convs): weights are stored as pre-swizzled 4 KiB blocks
+    uint32_t relu;         // bit 0: fused ReLU.  bit 2 (convs): INT8 convolution -- int8 weights in 128-byte K blocks, and the
+                           // "bias" region holds [m: cout_phys fp32][b: cout_phys fp32][r, 0, 0, 0] (quantize.py).
+                           // bit 1 (convs): weights are stored as pre-swizzled 4 KiB blocks
                            // [K/64][Cout/32][32 rows][128 B] (builder.pack_weights_sw128) instead of row-major [Cout][K]
     uint32_t ceil_mode;    // pools: Caffe ceil mode.  convs: algorithmic K (Cin*kh*kw of the ORIGINAL conv) when the
                            // builder re-expressed the layer (0 = cin*taps)
