@@ -298,6 +298,7 @@ struct b2_context {
     int net_bn = 0;    // force its N tile (64 / 128); 0 = 128 wherever the channel count allows
     int net_stages = 0;  // force its shared-memory ring depth (2..4); 0 = the deepest that lets two CTAs share an SM
     int i8_bn = 0;       // INT8 convolutions: force the N tile (128 / 256); 0 = 128
+    int i8_stages = 0;   // ... and the shared-memory ring depth (2..4); 0 = by rule
     int fuse_tail = 1;   // global average pool + FC + softmax as one launch (tail_f16_kernel)
     int* d_tail_ctrl = nullptr;  // its ticket / arrival counters (zero between launches)
     cudaStream_t side = nullptr;
@@ -739,7 +740,7 @@ int make_conv_launch(b2_context* c, const Op& op, int batch, const ConvConfig& c
 }
 
 // INT8 convolution launch (i8_kernels.cu): TMA maps over 1-byte tensors whose 128-byte rows hold 128 channels.
-int make_i8_conv_launch(b2_context* c, const Op& op, int batch, int bn, b2k::I8ConvLaunch* out) {
+int make_i8_conv_launch(b2_context* c, const Op& op, int batch, int bn, int stages, b2k::I8ConvLaunch* out) {
     b2_engine* e = c->e;
     const b2plan::OpRec& r = op.r;
     const Tensor& ti = e->tensors[r.in];
@@ -748,7 +749,7 @@ int make_i8_conv_launch(b2_context* c, const Op& op, int batch, int bn, b2k::I8C
     b2k::I8ConvLaunch& cl = *out;
     memset(&cl, 0, sizeof cl);
     const int M = batch * int(to.h) * int(to.w);
-    cl.bn = bn;
+    cl.bn = bn, cl.stages = stages;
     cl.grid_m = (M + 127) / 128;
     cl.grid_n = int(r.cout_phys) / bn;
     b2k::I8ConvArgs& a = cl.args;
@@ -985,6 +986,76 @@ bool tactic_applies(const b2_context* c, const Op& op, int batch, const ConvConf
     return true;
 }
 
+// INT8 twin of autotune_conv: times every (N tile, ring depth) of conv_i8_tcgen05 on `c->autotune` concurrent streams.
+int autotune_i8_conv(b2_context* c, const Op& op, int batch, ConvConfig* best_out) {
+    const b2plan::OpRec& r = op.r;
+    const int ns = std::max(1, std::min(c->autotune, 8));
+    std::vector<cudaStream_t> ss(size_t(ns), nullptr);
+    std::vector<cudaEvent_t> done(size_t(ns), nullptr);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool ok = cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
+    for (int i = 0; i < ns && ok; ++i)
+        ok = cudaStreamCreateWithFlags(&ss[size_t(i)], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&done[size_t(i)], cudaEventDisableTiming) == cudaSuccess;
+    auto cleanup = [&] {
+        for (auto s_ : ss)
+            if (s_) cudaStreamDestroy(s_);
+        for (auto d : done)
+            if (d) cudaEventDestroy(d);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+    if (!ok) {
+        cudaGetLastError();
+        cleanup();
+        return fail(B2_ECUDA, "autotune: cannot create streams/events");
+    }
+    const int iters = std::max(4, env_int("B2_TUNE_ITERS", 12));
+    const int reps = std::max(1, env_int("B2_TUNE_REPS", 2));
+    double best_ms = 1e30;
+    ConvConfig best = *best_out;
+    int status = B2_OK;
+    for (int bn : {128, 256}) {
+        if (int(r.cout_phys) % bn) continue;
+        for (int st = 1; st <= 4 && !status; ++st) {
+            if (!b2k::conv_i8_config_exists(bn, st)) continue;
+            b2k::I8ConvLaunch cl;
+            if ((status = make_i8_conv_launch(c, op, batch, bn, st, &cl))) break;
+            int rc = 0;
+            for (int i = 0; i < 2 && !rc; ++i)
+                for (int k = 0; k < ns && !rc; ++k) rc = b2k::launch_conv_i8_tcgen05(cl, ss[size_t(k)]);
+            for (int k = 0; k < ns; ++k) cudaStreamSynchronize(ss[size_t(k)]);
+            float ms = 1e30f;
+            cudaError_t se = cudaSuccess;
+            for (int rep = 0; rep < reps && !rc && se == cudaSuccess; ++rep) {
+                cudaEventRecord(e0, ss[0]);
+                for (int k = 1; k < ns; ++k) cudaStreamWaitEvent(ss[size_t(k)], e0, 0);
+                for (int i = 0; i < iters && !rc; ++i)
+                    for (int k = 0; k < ns && !rc; ++k) rc = b2k::launch_conv_i8_tcgen05(cl, ss[size_t(k)]);
+                for (int k = 1; k < ns; ++k) {
+                    cudaEventRecord(done[size_t(k)], ss[size_t(k)]);
+                    cudaStreamWaitEvent(ss[0], done[size_t(k)], 0);
+                }
+                cudaEventRecord(e1, ss[0]);
+                se = cudaStreamSynchronize(ss[0]);
+                float t = 0.f;
+                if (se == cudaSuccess && cudaEventElapsedTime(&t, e0, e1) == cudaSuccess) ms = std::min(ms, t);
+            }
+            if (rc || se != cudaSuccess) {
+                status = fail(B2_ECUDA, "autotune of %s (int8 bn=%d st=%d) failed: %s", op.name.c_str(), bn, st,
+                              cudaGetErrorString(rc ? cudaError_t(rc) : se));
+                break;
+            }
+            if (ms < best_ms) best_ms = ms, best = ConvConfig{bn, st, 1, 0.0, 1, 0, 1};
+        }
+    }
+    cleanup();
+    if (status) return status;
+    best.est_us = best_ms * 1e3 / (iters * ns);
+    *best_out = best;
+    return B2_OK;
+}
+
 // Times the tactics of every tcgen05 convolution of the engine at `batch` (and, first, at max batch: the split-K factor
 // is chosen once there) on a context with a PRIVATE arena -- never on memory a request may be using.
 int tune_engine_batch(b2_context* c, int batch) {
@@ -992,7 +1063,20 @@ int tune_engine_batch(b2_context* c, int batch) {
     for (size_t i = 0; i < e->ops.size(); ++i) {
         const Op& op = e->ops[i];
         const b2plan::OpRec& r = op.r;
-        if (r.type != b2plan::OP_CONV || !e->half() || (r.relu & 4)) continue;  // (INT8 convolutions have one tactic)
+        if (r.type != b2plan::OP_CONV || !e->half()) continue;
+        if (r.relu & 4) {  // INT8 convolution: (N tile, ring depth)
+            {
+                std::lock_guard<std::mutex> lock(e->tune_mutex);
+                if (e->tuned.count({int(i), batch})) continue;
+            }
+            ConvConfig cfg{128, 2, 1, 0.0, 1, 0, 1};
+            int rc = autotune_i8_conv(c, op, batch, &cfg);
+            if (rc) return rc;
+            std::lock_guard<std::mutex> lock(e->tune_mutex);
+            e->tuned[{int(i), batch}] = cfg;
+            tune_cache_append(e, int(i), batch, cfg);
+            continue;
+        }
         const bool kb64 = r.cin_phys % 64 == 0, kb8 = r.cin_phys == 8;
         if (!((kb64 || kb8) && r.cout_phys % 32 == 0 && (kb64 || r.taps_phys % 2 == 0))) continue;
         {
@@ -1271,9 +1355,25 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                                    (kb64 || r.taps_phys % 2 == 0);
                 if (r.relu & 4) {  // INT8 tensor path
                     L.kind = L_CONV_I8;
-                    int bn = c->i8_bn > 0 ? c->i8_bn : 128;
-                    if (int(r.cout_phys) % bn || !b2k::conv_i8_config_exists(bn)) bn = 128;
-                    int rc = make_i8_conv_launch(c, op, batch, bn, &L.i8);
+                    // one tactic, by rule: the 128-wide N tile with a ring no deeper than the K loop, shallow enough (2-3
+                    // stages) that two CTAs share an SM (measured: profiles/probe_r2_int8_*.log); "i8_bn" / "i8_stages" override
+                    // tactic = (N tile, ring depth): timed at load (b2_engine_tune) or carried by the plan; untuned engines use
+                    // a rule -- many CTAs want shallow rings (more CTAs per SM), few CTAs a 2-deep one (profiles/probe_r2_int8*)
+                    const int m_tiles = (batch * int(e->tensors[r.out].h * e->tensors[r.out].w) + 127) / 128;
+                    int bn = 128, st = m_tiles * (int(r.cout_phys) / 128) >= 2 * 148 ? 1 : 2;
+                    if (c->autotune) {
+                        std::lock_guard<std::mutex> lock(e->tune_mutex);
+                        tune_cache_load(e);
+                        const int op_index = int(&op - &e->ops[0]);
+                        auto it = e->tuned.find({op_index, batch});
+                        if (it == e->tuned.end()) it = e->tuned.find({op_index, e->max_batch});
+                        if (it != e->tuned.end()) bn = it->second.bn, st = it->second.stages;
+                    }
+                    if (c->i8_bn > 0) bn = c->i8_bn;
+                    if (c->i8_stages > 0) st = c->i8_stages;
+                    if (int(r.cout_phys) % bn) bn = 128;
+                    if (!b2k::conv_i8_config_exists(bn, st)) bn = 128, st = 2;
+                    int rc = make_i8_conv_launch(c, op, batch, bn, st, &L.i8);
                     if (rc) return rc;
                 } else if (tc_ok) {
                     L.kind = L_CONV_TC;
@@ -1796,6 +1896,7 @@ int b2_context_create(b2_engine* e, b2_context** out) {
     c->net_stages = env_int("B2_NET_STAGES", 0);
     c->fuse_tail = env_int("B2_FUSE_TAIL", 1);
     c->i8_bn = env_int("B2_I8_BN", 0);
+    c->i8_stages = env_int("B2_I8_STAGES", 0);
     if (getenv("B2_PDL")) b2k::set_pdl(env_int("B2_PDL", 1) != 0);
     void* p = nullptr;
     if (cudaMalloc(&p, (kMaxSplitTiles + 16) * sizeof(int)) != cudaSuccess || cudaMemset(p, 0, (kMaxSplitTiles + 16) * sizeof(int)) != cudaSuccess) {
@@ -1859,6 +1960,7 @@ int b2_context_set_option(b2_context* c, const char* key, int value) {
     else if (k == "net_stages") c->net_stages = value;
     else if (k == "fuse_tail") c->fuse_tail = value;
     else if (k == "i8_bn") c->i8_bn = value;
+    else if (k == "i8_stages") c->i8_stages = value;
     else if (k == "pdl_trigger") c->pdl_trigger = value;
     else if (k == "autotune") c->autotune = value;
     else if (k == "no_fold") c->no_fold = value;
@@ -2096,7 +2198,7 @@ const char* b2_context_launch_name(b2_context* c, int batch, int i) {
              " grid=" + std::to_string(L->conv.grid_n) + "x" + std::to_string(L->conv.grid_m) + "x" +
              std::to_string(L->conv.args.splits) + " kblk=" + std::to_string(L->conv.args.num_kblocks);
     if (L->kind == L_CONV_I8)
-        s += " bn=" + std::to_string(L->i8.bn) + (L->i8.args.a_mode == b2k::A_TILED ? " tiled" : " im2col") + " grid=" +
+        s += " bn=" + std::to_string(L->i8.bn) + " st=" + std::to_string(L->i8.stages) + (L->i8.args.a_mode == b2k::A_TILED ? " tiled" : " im2col") + " grid=" +
              std::to_string(L->i8.grid_n) + "x" + std::to_string(L->i8.grid_m) + " kblk=" + std::to_string(L->i8.args.num_kblocks);
     if (L->kind == L_NET)
         s += " layers=" + std::to_string(L->net->args.n_layers) + " tiles=" + std::to_string(L->net->args.total_tiles) +

@@ -33,20 +33,18 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int m, int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-__host__ __device__ constexpr int i8_stages(int bn) { return bn >= 256 ? 3 : 4; }  // ring depth that fits 227 KiB with a residual tile
 constexpr int kI8ASub = 128 * 128;  // 128 rows x 128 K-bytes
 
-__host__ __device__ constexpr int conv_i8_smem_layout_bytes(int bn, bool residual) {
-    return i8_stages(bn) * (kI8ASub + bn * 128) + (residual ? 128 * bn : 0) + 256 + 2 * bn * 4 + 1024;
+__host__ __device__ constexpr int conv_i8_smem_layout_bytes(int bn, int stages, bool residual) {
+    return stages * (kI8ASub + bn * 128) + (residual ? 128 * bn : 0) + 256 + 2 * bn * 4 + 1024;
 }
 
 }  // namespace
 
-template <int BN>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(128)
 conv_i8_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapOut,
                 const __grid_constant__ CUtensorMap mapRes, const I8ConvArgs p) {
-    constexpr int STAGES = i8_stages(BN);
     constexpr int A_STAGE = kI8ASub, B_STAGE = BN * 128;
     constexpr int PIPE_BYTES = STAGES * (A_STAGE + B_STAGE);
     constexpr int TILE_BYTES = 128 * BN;     // int8 output / residual tile
@@ -227,30 +225,39 @@ conv_i8_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
 }
 
-int conv_i8_smem_bytes(int bn, bool residual) { return conv_i8_smem_layout_bytes(bn, residual); }
-bool conv_i8_config_exists(int bn) { return bn == 128 || bn == 256; }
+int conv_i8_smem_bytes(int bn, int stages, bool residual) { return conv_i8_smem_layout_bytes(bn, stages, residual); }
+bool conv_i8_config_exists(int bn, int stages) {
+    return (bn == 128 || bn == 256) && stages >= 1 && stages <= 4 && conv_i8_smem_layout_bytes(bn, stages, true) <= 227 * 1024;
+}
+
+#define B2_FOR_EACH_I8(X) X(128, 1) X(128, 2) X(128, 3) X(128, 4) X(256, 1) X(256, 2) X(256, 3)
 
 int init_conv_i8_kernels() {
-    int e = static_cast<int>(
-        cudaFuncSetAttribute(conv_i8_tcgen05<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_i8_smem_layout_bytes(128, true)));
-    if (e) return e;
-    return static_cast<int>(
-        cudaFuncSetAttribute(conv_i8_tcgen05<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_i8_smem_layout_bytes(256, true)));
+    int e = 0;
+#define B2_I8_INIT(BN_, ST_)                                                                                                  \
+    if ((e = static_cast<int>(cudaFuncSetAttribute(conv_i8_tcgen05<BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                   conv_i8_smem_layout_bytes(BN_, ST_, true)))))                             \
+        return e;
+    B2_FOR_EACH_I8(B2_I8_INIT)
+#undef B2_I8_INIT
+    return 0;
 }
 
 int launch_conv_i8_tcgen05(const I8ConvLaunch& L, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(L.grid_n), static_cast<unsigned>(L.grid_m), 1);
     cfg.blockDim = dim3(128);
-    cfg.dynamicSmemBytes = static_cast<size_t>(conv_i8_smem_layout_bytes(L.bn, L.args.has_res != 0));
+    cfg.dynamicSmemBytes = static_cast<size_t>(conv_i8_smem_layout_bytes(L.bn, L.stages, L.args.has_res != 0));
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = get_pdl() ? 1 : 0;
-    if (L.bn == 128) return static_cast<int>(cudaLaunchKernelEx(&cfg, conv_i8_tcgen05<128>, L.mapA, L.mapOut, L.mapRes, L.args));
-    if (L.bn == 256) return static_cast<int>(cudaLaunchKernelEx(&cfg, conv_i8_tcgen05<256>, L.mapA, L.mapOut, L.mapRes, L.args));
+#define B2_I8_CASE(BN_, ST_) \
+    if (L.bn == BN_ && L.stages == ST_) return static_cast<int>(cudaLaunchKernelEx(&cfg, conv_i8_tcgen05<BN_, ST_>, L.mapA, L.mapOut, L.mapRes, L.args));
+    B2_FOR_EACH_I8(B2_I8_CASE)
+#undef B2_I8_CASE
     return static_cast<int>(cudaErrorInvalidValue);
 }
 

@@ -141,11 +141,11 @@ struct I8ConvLaunch {
     CUtensorMap mapOut;  // int8 output store: 2-D tiled [M, Cout], box 128 x 128 B, 128B swizzle
     CUtensorMap mapRes;  // int8 residual load, same geometry
     I8ConvArgs args;
-    int bn, grid_m, grid_n;
+    int bn, stages, grid_m, grid_n;  // N tile 128 / 256, shared-memory ring depth 2..4
 };
 int init_conv_i8_kernels();
-bool conv_i8_config_exists(int bn);
-int conv_i8_smem_bytes(int bn, bool residual);
+bool conv_i8_config_exists(int bn, int stages);
+int conv_i8_smem_bytes(int bn, int stages, bool residual);
 int launch_conv_i8_tcgen05(const I8ConvLaunch& L, cudaStream_t stream);
 // fp16 NHWC -> int8 NHWC, q = clip(rint(fl(float(h) * inv_s)), +-127); channels >= C are written as zeros
 int launch_quantize_h_to_i8(const void* src, void* dst, long long pixels, int C, int C_in_phys, int C_out_phys, float inv_s,
