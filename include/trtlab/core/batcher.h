@@ -8,6 +8,7 @@
 // file is never reached; the guard below keeps it inert if it is.
 #pragma once
 #ifndef B2_USE_TRTLAB_CORE
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <functional>
@@ -209,16 +210,16 @@ class Dispatcher<BatcherT<T, standard_threads>> : private BatcherT<T, standard_t
         auto shared_batch = std::make_shared<typename batcher_type::Batch>(std::move(batch));
         auto fn = m_Fn;
         m_Workers->enqueue([state, shared_batch, fn] {
-            bool released = false;
-            auto release = [&] {
-                if (!released) shared_batch->promise.set_value();
-                released = true;
+            // shared and captured BY VALUE: the execute function may keep `release` and call it later, from another thread
+            auto released = std::make_shared<std::atomic<bool>>(false);
+            auto release = [released, shared_batch] {
+                if (!released->exchange(true)) shared_batch->promise.set_value();
             };
             try {
                 fn(shared_batch->items, release);
                 release();  // a function that forgot to release must not strand its callers
             } catch (...) {
-                if (!released) shared_batch->promise.set_exception(std::current_exception());
+                if (!released->exchange(true)) shared_batch->promise.set_exception(std::current_exception());
             }
             {
                 std::lock_guard<std::mutex> l(state->mutex);

@@ -587,7 +587,10 @@ class BatchedInferRunner {
                 }
                 b.reset();
             });
-            done.wait();  // `reqs` lives in the batch, which the dispatcher keeps alive until this function returns
+            // get(), not wait(): an exception thrown in the cuda / post stage must reach the batch promise (the dispatcher
+            // turns it into set_exception) instead of being reported as success over unwritten outputs.
+            // `reqs` lives in the batch, which the dispatcher keeps alive until this function returns.
+            done.get();
             batches->fetch_add(1);
             release();
         };

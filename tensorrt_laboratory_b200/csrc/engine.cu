@@ -326,7 +326,8 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
     if (h.max_batch == 0 || h.max_batch > 4096) return fail(B2_EINVAL, "plan: bad max_batch %u", h.max_batch);
     const size_t tbl = sizeof(Header) + size_t(h.n_tensors) * sizeof(TensorRec) + size_t(h.n_ops) * sizeof(OpRec) +
                        size_t(h.n_bindings) * sizeof(BindingRec);
-    if (tbl > nbytes || h.payload_offset < tbl || h.payload_offset + h.payload_bytes > nbytes)
+    // (overflow-safe: a > n || b > n - a instead of a + b > n)
+    if (tbl > nbytes || h.payload_offset < tbl || h.payload_offset > nbytes || h.payload_bytes > nbytes - h.payload_offset)
         return fail(B2_EINVAL, "plan: truncated (tables %zu, payload %llu+%llu, blob %zu)", tbl,
                     (unsigned long long)h.payload_offset, (unsigned long long)h.payload_bytes, nbytes);
     e->name = fixed_str(h.name, 64);
@@ -369,8 +370,22 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
             return fail(B2_EINVAL, "plan: op %s references a missing tensor", op.name.c_str());
         if ((r.type == OP_INPUT_CAST || r.type == OP_OUTPUT_CAST) && (r.binding < 0 || r.binding >= int(h.n_bindings)))
             return fail(B2_EINVAL, "plan: cast op %s has a bad binding", op.name.c_str());
-        if (r.w_off + r.w_bytes > h.payload_bytes || r.b_off + r.b_bytes > h.payload_bytes)
+        if (r.w_off > h.payload_bytes || r.w_bytes > h.payload_bytes - r.w_off || r.b_off > h.payload_bytes ||
+            r.b_bytes > h.payload_bytes - r.b_off)
             return fail(B2_EINVAL, "plan: op %s weights outside payload", op.name.c_str());
+        if ((r.type == OP_MAXPOOL || r.type == OP_AVGPOOL) && (r.k == 0 || r.stride == 0))
+            return fail(B2_EINVAL, "plan: pool %s has a zero window or stride", op.name.c_str());
+        if (r.type == OP_MAXPOOL) {
+            const Tensor& ti = e->tensors[r.in];
+            const Tensor& to = e->tensors[r.out];
+            if (ti.kind != T_ACT || to.kind != T_ACT || ti.c_phys != to.c_phys || to.h == 0 || to.w == 0 ||
+                uint64_t(to.h - 1) * r.stride >= uint64_t(ti.h) + r.pad_ || uint64_t(to.w - 1) * r.stride >= uint64_t(ti.w) + r.pad_)
+                return fail(B2_EINVAL, "plan: pool %s output dims do not fit its input", op.name.c_str());
+        }
+        if (r.type == OP_INPUT_CAST || r.type == OP_OUTPUT_CAST) {  // the caller's Buffers are sized from the BINDING dims
+            const Tensor& tt = e->tensors[r.type == OP_INPUT_CAST ? r.out : r.in];
+            if (tt.kind != T_ACT) return fail(B2_EINVAL, "plan: cast op %s needs an activation tensor", op.name.c_str());
+        }
         if (r.type == OP_QUANTIZE) {
             const Tensor& ti = e->tensors[r.in];
             const Tensor& to = e->tensors[r.out];
@@ -397,6 +412,8 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
             const Tensor& to = e->tensors[r.out];
             if (ti.c_phys != r.cin_phys || to.c_phys != r.cout_phys || ti.c != r.cin || to.c != r.cout)
                 return fail(B2_EINVAL, "plan: conv %s channel mismatch with its tensors", op.name.c_str());
+            if (uint64_t(ti.h) + 2 * uint64_t(r.pad_) < r.k || int64_t(ti.w) + op.pw_lo() + op.pw_hi() < op.kw())
+                return fail(B2_EINVAL, "plan: conv %s window larger than its padded input", op.name.c_str());
             const uint32_t ho = (ti.h + 2 * r.pad_ - r.k) / r.stride + 1;
             const uint32_t wo = uint32_t((int(ti.w) + op.pw_lo() + op.pw_hi() - op.kw()) / op.sw() + 1);
             if (to.h != ho || to.w != wo) return fail(B2_EINVAL, "plan: conv %s output dims mismatch", op.name.c_str());
@@ -430,6 +447,18 @@ int parse_blob(const void* blob, size_t nbytes, b2_engine* e, const uint8_t** pa
         }
         b.item_bytes = n * (r.dtype == B2_DT_HALF ? 2 : 4);
         e->bindings.push_back(b);
+    }
+    // cast ops move a binding <-> a tensor: the caller sizes its Buffers from the BINDING dims, so the two must agree
+    for (const Op& op : e->ops) {
+        const OpRec& r = op.r;
+        if (r.type != OP_INPUT_CAST && r.type != OP_OUTPUT_CAST) continue;
+        const Binding& b = e->bindings[size_t(r.binding)];
+        const Tensor& t = e->tensors[size_t(r.type == OP_INPUT_CAST ? r.out : r.in)];
+        size_t n = 1;
+        for (int d = 0; d < b.nd; ++d) n *= size_t(b.dims[d] > 0 ? b.dims[d] : 0);
+        const bool s2d = r.type == OP_INPUT_CAST && r.k == 2;  // (its geometry is re-checked when the launch plan is built)
+        if (b.is_input != (r.type == OP_INPUT_CAST) || (!s2d && n != size_t(t.c) * t.h * t.w))
+            return fail(B2_EINVAL, "plan: cast op %s: binding %s and tensor %s disagree", op.name.c_str(), b.name.c_str(), t.name.c_str());
     }
     if (h.n_tactics) {  // tactic table written by an offline tuning run (b2_engine_get_tactics -> builder.attach_tactics)
         if (h.tactics_offset > nbytes || size_t(h.n_tactics) > (nbytes - h.tactics_offset) / sizeof(TacticRec))

@@ -44,8 +44,16 @@ py::dict binding_info(const Model& model, uint32_t id) {
     return value;
 }
 
-using InferResults = py::dict;
+// The result dict lives in the future's shared state, whose LAST reference may be dropped by a pool thread (the caller
+// discarded its InferFuture): the holder's deleter takes the GIL before touching Python reference counts.
+using InferResults = std::shared_ptr<py::dict>;
 using InferFuture = std::shared_future<InferResults>;
+static InferResults make_results() {
+    return InferResults(new py::dict(), [](py::dict* p) {
+        py::gil_scoped_acquire acquire;
+        delete p;
+    });
+}
 
 struct PyInferRunner : public InferRunner {
     using InferRunner::InferRunner;
@@ -53,9 +61,15 @@ struct PyInferRunner : public InferRunner {
     // keyword = input binding name, value = numpy array [batch, ...] of the binding's dtype
     InferFuture Infer(py::kwargs kwargs) {
         const Model& model = GetModel();
-        auto buffers = Resources().GetBuffers();
-        auto bindings = buffers->CreateBindings(GetModelSmartPtr());
-        buffers.reset();
+        std::shared_ptr<Bindings> bindings;
+        {
+            // GetBuffers() BLOCKS while every Buffers is in flight, and the post stage of those requests needs the GIL
+            // to build their result dicts before it releases them: waiting here with the GIL held would deadlock as soon
+            // as more requests are issued than there are Buffers (`[runner.infer(...) for x in xs]`).
+            py::gil_scoped_release release;
+            auto buffers = Resources().GetBuffers();
+            bindings = buffers->CreateBindings(GetModelSmartPtr());
+        }
         long batch_size = -1;
         size_t seen = 0;
         for (auto item : kwargs) {
@@ -85,7 +99,7 @@ struct PyInferRunner : public InferRunner {
         py::gil_scoped_release release;  // the pipeline's post stage re-acquires the GIL to build the result dict
         auto fut = InferRunner::Infer(bindings, [](std::shared_ptr<Bindings>& b) -> InferResults {
             py::gil_scoped_acquire acquire;
-            InferResults results;
+            InferResults results = make_results();
             for (uint32_t id : b->OutputBindings()) {
                 const auto& info = b->GetModel()->GetBinding(id);
                 std::vector<py::ssize_t> dims;
@@ -93,7 +107,7 @@ struct PyInferRunner : public InferRunner {
                 for (auto d : info.dims) dims.push_back(py::ssize_t(d));
                 py::array value(numpy_dtype(int(info.dtype)), dims);
                 std::memcpy(value.mutable_data(), b->HostAddress(id), b->BindingSize(id));
-                results[py::str(info.name)] = value;
+                (*results)[py::str(info.name)] = value;
             }
             return results;
         });
@@ -170,6 +184,6 @@ PYBIND11_MODULE(trtlab, m) {
                 py::gil_scoped_release release;
                 f.wait();
             }
-            return f.get();
+            return py::dict(*f.get());
         });
 }

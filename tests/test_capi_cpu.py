@@ -76,6 +76,34 @@ def test_malformed_plans_are_rejected(lib):
         capi.Engine(b"short", inspect_only=True)
 
 
+def test_corrupted_offsets_and_geometry_are_rejected_not_wrapped(lib):
+    """Bounds checks must not wrap in uint64, and geometry that would divide by zero or underflow is refused (B2_EINVAL)
+    instead of reaching a kernel."""
+    blob = bytes(_small_plan(builder.PREC_FP16))
+    hdr = builder._HEADER
+    n_t, n_o = struct.unpack_from("<II", blob, 20)[0], struct.unpack_from("<II", blob, 24)[0]
+    n_t, n_o = struct.unpack_from("<III", blob, 20)[0:2]
+    op0 = hdr.size + n_t * builder._TENSOR.size
+    conv = next(op0 + i * builder._OP.size for i in range(n_o) if struct.unpack_from("<I", blob, op0 + i * builder._OP.size + 64)[0] == builder.OP_CONV)
+
+    def mutated(offset, fmt, *vals):
+        bad = bytearray(blob)
+        struct.pack_into(fmt, bad, offset, *vals)
+        return bytes(bad)
+
+    cases = {
+        "payload offset+bytes wraps": mutated(32, "<QQ", 2 ** 64 - 16, 64),
+        "weight offset+bytes wraps": mutated(conv + 64 + 4 + 16 + 4 * 11, "<QQ", 2 ** 64 - 8, 64),
+        "conv stride 0": mutated(conv + 64 + 4 + 16 + 4, "<I", 0),
+        "conv window larger than the padded input": mutated(conv + 64 + 4 + 16, "<I", 1000),
+        "tactic table outside the blob": mutated(112, "<IIQ", 5, 0, 2 ** 63),
+    }
+    for name, bad in cases.items():
+        with pytest.raises(capi.B2Error) as ei:
+            capi.Engine(bad, inspect_only=True)
+        assert ei.value.code == 1, name
+
+
 def test_inspect_only_engine_cannot_execute(lib):
     eng = capi.Engine(_small_plan(builder.PREC_FP16), inspect_only=True)
     ctx = C.c_void_p()

@@ -59,3 +59,9 @@ def test_mnist_known_answer_through_the_python_surface(gpu, tmp_path):
     with pytest.raises(KeyError):
         mnist.infer(Nope=np.zeros((1, 1, 28, 28), np.float32))
     np.testing.assert_almost_equal(mnist.infer(Input3=xs[0]).get()[list(outs)[0]].reshape(1, 10), ys[0], decimal=3)  # still serving
+    # more requests in flight than pooled Buffers (2 x max_exec_concurrency = 4): infer() must not wait for a Buffers with
+    # the GIL held (the post stage of the requests in flight needs it to release theirs); dropped futures are harmless
+    futs = [mnist.infer(Input3=xs[i % 3]) for i in range(24)]
+    del futs[::2]
+    for i, f in zip(range(1, 24, 2), futs):
+        assert int(f.get()[list(outs)[0]].argmax()) == (2, 0, 9)[i % 3]
