@@ -182,6 +182,44 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_config2(capi, builder, peaks_int8_tops: float = 4500.0):
+    """BASELINE.json configs[2]: ResNet-152 INT8, batch 32, dynamic batching (examples/03_Batching), 8 streams, 1 GPU.
+    Device-resident throughput of 8 execution contexts + the end-to-end rate of single-image requests merged by
+    BatchedInferRunner (2 ms window) -- a SECONDARY line; the headline stays on configs[1]."""
+    from tensorrt_laboratory_b200 import weights
+    batch, contexts, steps = 32, 8, 96
+    blob = builder.build_resnet_plan(152, builder.PREC_INT8, batch, seed=0)
+    ring = weights.synthetic_input(batch, seed=4242, ring=8)                     # 8 x 19.3 MB = 154 MB > L2
+    ms, launches = capi.device_throughput(blob, contexts, batch, steps, 16, ring)
+    value = steps * batch / (ms * 1e-3)
+    ops = capi.Engine(blob, inspect_only=True).flops(batch)                      # 2 * MACs of one batch-32 forward pass
+    mgr = capi.InferenceManager(contexts, 2 * contexts, pre_threads=1, cuda_threads=1, post_threads=3)
+    try:
+        mgr.register_model("rn152i8", blob)
+        mgr.update_resources()
+        n_img = 2048
+        x = ring.reshape(-1, *ring.shape[2:])[:256]
+        x = np.concatenate([x] * (n_img // 256), 0)
+        mgr.infer_batched("rn152i8", x[:256], window_us=2000)                    # warm-up
+        t0 = time.perf_counter()
+        _, nb = mgr.infer_batched("rn152i8", x, window_us=2000)
+        dt = time.perf_counter() - t0
+    finally:
+        mgr.close()
+    return {
+        "workload": "ResNet-152 int8 batch=32, dynamic batching, 8 streams, 1xB200 (BASELINE.json configs[2])",
+        "metric": "ResNet-152 int8 b=32 inferences/sec", "value": value, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+        "contexts": contexts, "dtype": "s8 (bottleneck convolutions; fp16 stem and classifier)", "gpu_launches": launches * steps,
+        "e2e": {"value": n_img / dt, "unit": UNIT, "requests": n_img, "merged_batches": nb,
+                "api": "single-image requests -> BatchedInferRunner (Dispatcher<StandardBatcher>, 2000 us window) -> InferRunner; pinned H2D/D2H per merged batch",
+                "h2d_bytes_per_request": 3 * 224 * 224 * 4, "d2h_bytes_per_request": 4000},
+        "roofline": {"bound": "tensor", "kernel": "conv_i8_tcgen05 (the 154 INT8 convolutions of one forward pass)",
+                     "achieved": ops * steps / (ms * 1e-3) / 1e12, "peak": peaks_int8_tops, "unit": "TOP/s",
+                     "frac": ops * steps / (ms * 1e-3) / 1e12 / peaks_int8_tops,
+                     "peak_source": "NOMINAL dense int8 4.5 POP/s (B200_PROFILING.md table; MEASURED_PEAKS.json has no int8 entry)"},
+    }
+
+
 def run_b200(args):
     rank, world, local = _dist_env()
     from tensorrt_laboratory_b200 import builder, capi
@@ -190,6 +228,8 @@ def run_b200(args):
     if capi.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device visible and there is no CPU fallback for the product path")
     capi.check(lib.b2_device_set(local))
+    # this replica's threads next to its GPU (NVML cpu affinity, reference DeviceInfo::Affinity); pool threads bind themselves
+    affinity_cpus = capi.bind_thread_to_device(local) if os.environ.get("TRTLAB_AFFINITY", "1") != "0" else 0
     # Each replica keeps ~6 host threads (bench loop, pre/cuda pools, 3 post threads).  When the replicas of this box
     # outnumber its usable cores, spin-waiting on CUDA events starves the threads that feed the GPUs: block instead.
     sync_mode = os.environ.get("B2_BENCH_SYNC", "auto")
@@ -215,6 +255,15 @@ def run_b200(args):
         if dist is not None:
             dist.barrier()
 
+    def gather_over_ranks(x: float):
+        if dist is None:
+            return [x]
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     def max_over_ranks(x: float) -> float:
         if dist is None:
             return x
@@ -239,6 +288,7 @@ def run_b200(args):
     # AllocateResources, so nothing is tuned, captured or instantiated inside the timed region; the warm-up still
     # cycles through every pooled Buffers / execution token at least twice.
     e2e_warm = max(max(args.warmup, 3) * CONTEXTS, 2 * BUFFERS * 2)
+    per_rank = []  # per leg: every rank's own end-to-end rate
 
     def e2e_run(plan_blob):
         mgr = capi.InferenceManager(CONTEXTS, BUFFERS, pre_threads=1, cuda_threads=1, post_threads=3)
@@ -249,6 +299,7 @@ def run_b200(args):
         barrier()
         res, lats = mgr.bench("rn50", BATCH, seconds=600.0, max_batches=args.steps, want_latencies=True)
         barrier()
+        per_rank.append(gather_over_ranks(args.steps * BATCH / res["kWalltime"]))
         wall = max_over_ranks(res["kWalltime"])
         mgr.close()
         return (world * args.steps * BATCH / wall,
@@ -313,12 +364,24 @@ def run_b200(args):
                      "achieved_gbs": ALGO_BYTES_PER_STEP / (ms_per_step * 1e-3) / 1e9, "peak_gbs": peak_hbm},
     }
 
+    config2 = None
+    if world == 1 and not args.no_config2:
+        try:
+            config2 = run_config2(capi, builder)
+        except Exception as ex:  # the secondary line must never take the headline down
+            config2 = {"error": f"{type(ex).__name__}: {ex}"}
+
     cpu = None
+    try:
+        import onnxruntime  # noqa: F401  (the north star names ONNX Runtime for the CPU leg)
+        ort = "importable but unused: the torch oracle port is what the tests pin"
+    except Exception:
+        ort = "onnxruntime is not installed on this box: torch-CPU oracle port instead"
     if not args.no_cpu:
         net, wts = cpu_forward_setup()
         cores = pick_cpu_threads(net, wts, ring)
         ips, spb = time_cpu(net, wts, ring, 3, args.cpu_batches, cores)
-        cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+        cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "onnxruntime": ort,
                "sample": f"3 warm-up + {args.cpu_batches} timed batches of {BATCH} (same graph/weights/inputs), fp32 torch-CPU oracle port, {cores} threads of {usable_cores()} usable cores, {spb*1e3:.1f} ms/batch"}
 
     line = {
@@ -330,11 +393,13 @@ def run_b200(args):
                    "l2_policy": f"inputs larger than L2: ring of {RING} distinct batches = {RING * in_bytes / 1e6:.0f} MB",
                    "parallelism": f"replicas x{world} (no collective)",
                    "host_sync": "blocking" if blocking else "spin", "host_cores": usable_cores(),
+                   "gpu_affinity_cpus": affinity_cpus,
                    "enqueue_depth": int(os.environ.get("TRTLAB_ENQUEUE_DEPTH", "2"))},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                 "p50_ms": p50, "p99_ms": p99, "gpu_ms_per_request": e2e_gpu_ms,
                 "requests": args.steps, "warm_requests": e2e_warm,
+                "per_rank": per_rank[0], "h2d_gbs_per_rank": [v / BATCH * in_bytes / 1e9 for v in per_rank[0]],
                 "api": "InferenceManager+InferRunner+InferBench (pinned host Buffers, H2D/D2H per request)"},
         "e2e_fp16_input": {"value": e2e_h_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes // 2, "d2h_bytes_per_step": out_bytes,
                            "p50_ms": p50_h, "p99_ms": p99_h,
@@ -343,6 +408,7 @@ def run_b200(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "tflops_whole_forward": flops_step / (ms_per_step * 1e-3) / 1e12,
+        "config2": config2,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -357,6 +423,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-batches", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-config2", action="store_true", help="skip the secondary ResNet-152 INT8 line (BASELINE configs[2])")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: re-launch ourselves one rank per GPU (the driver does this itself via torchrun)

@@ -4,10 +4,18 @@
 //   yais_inference_request_duration_ms{model=...}   summary
 //   yais_inference_load_ratio                       histogram, buckets 1.25 1.5 2 10 100 (request / compute time)
 //   yais_gpus_power_usage{gpu="N"}                  gauge (watts, NVML; absent when NVML is not loadable)
-// `Expose()` renders the Prometheus text format 0.0.4; serving it over HTTP is the embedding service's job
-// (the reference uses prometheus::Exposer for that).
+// `Expose()` renders the Prometheus text format 0.0.4; `MetricsExposer` serves it over HTTP (GET /metrics), the role of
+// the prometheus::Exposer the reference service starts (examples/02_TensorRT_GRPC/src/metrics.cc:34-60).
 #pragma once
+#include <arpa/inet.h>
 #include <dlfcn.h>
+#include <netinet/in.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <functional>
+#include <thread>
 
 #include <algorithm>
 #include <cstdint>
@@ -16,6 +24,7 @@
 #include <memory>
 #include <mutex>
 #include <sstream>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -158,6 +167,70 @@ class Metrics {
     std::map<std::string, std::unique_ptr<Summary>> m_Compute, m_Request;
     Histogram m_LoadRatio;
     std::map<int, double> m_Power;
+};
+
+
+// Minimal HTTP/1.0 endpoint for the Prometheus scraper: one accept thread, one response per connection.
+// GET /metrics (or /) -> 200 text/plain; version=0.0.4 with `render()`; anything else -> 404.
+class MetricsExposer {
+  public:
+    // port 0 = let the kernel pick (see Port()); binds 0.0.0.0 like prometheus::Exposer("0.0.0.0:port")
+    MetricsExposer(int port, std::function<std::string()> render) : m_Render(std::move(render)) {
+        m_Fd = ::socket(AF_INET, SOCK_STREAM, 0);
+        if (m_Fd < 0) throw std::runtime_error("MetricsExposer: socket() failed");
+        int one = 1;
+        ::setsockopt(m_Fd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
+        sockaddr_in addr{};
+        addr.sin_family = AF_INET;
+        addr.sin_addr.s_addr = htonl(INADDR_ANY);
+        addr.sin_port = htons(static_cast<uint16_t>(port));
+        socklen_t len = sizeof addr;
+        if (::bind(m_Fd, reinterpret_cast<sockaddr*>(&addr), sizeof addr) != 0 || ::listen(m_Fd, 16) != 0 ||
+            ::getsockname(m_Fd, reinterpret_cast<sockaddr*>(&addr), &len) != 0) {
+            ::close(m_Fd);
+            throw std::runtime_error("MetricsExposer: cannot listen on port " + std::to_string(port));
+        }
+        m_Port = ntohs(addr.sin_port);
+        m_Thread = std::thread([this] { Serve(); });
+    }
+    ~MetricsExposer() {
+        m_Stop = true;
+        ::shutdown(m_Fd, SHUT_RDWR);
+        ::close(m_Fd);
+        if (m_Thread.joinable()) m_Thread.join();
+    }
+    MetricsExposer(const MetricsExposer&) = delete;
+    MetricsExposer& operator=(const MetricsExposer&) = delete;
+    int Port() const { return m_Port; }
+
+  private:
+    void Serve() {
+        while (!m_Stop) {
+            const int c = ::accept(m_Fd, nullptr, nullptr);
+            if (c < 0) {
+                if (m_Stop) break;
+                continue;
+            }
+            char req[1024];
+            const ssize_t n = ::recv(c, req, sizeof req - 1, 0);
+            std::string head(req, n > 0 ? size_t(n) : 0);
+            const bool ok = head.rfind("GET /metrics", 0) == 0 || head.rfind("GET / ", 0) == 0;
+            const std::string body = ok ? m_Render() : std::string("not found\n");
+            std::string resp = std::string(ok ? "HTTP/1.0 200 OK\r\n" : "HTTP/1.0 404 Not Found\r\n") +
+                               "Content-Type: text/plain; version=0.0.4\r\nContent-Length: " + std::to_string(body.size()) + "\r\n\r\n" + body;
+            size_t off = 0;
+            while (off < resp.size()) {
+                const ssize_t w = ::send(c, resp.data() + off, resp.size() - off, MSG_NOSIGNAL);
+                if (w <= 0) break;
+                off += size_t(w);
+            }
+            ::close(c);
+        }
+    }
+    std::function<std::string()> m_Render;
+    int m_Fd = -1, m_Port = 0;
+    std::atomic<bool> m_Stop{false};
+    std::thread m_Thread;
 };
 
 }  // namespace trtlab

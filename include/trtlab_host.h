@@ -34,6 +34,9 @@ int trt_manager_infer_batched(trt_manager* m, const char* model, int n, const vo
  * GPU power gauge sampled now through NVML); returns the text length (excluding the NUL) or a negative B2_E* code;
  * at most cap-1 bytes are written */
 int trt_manager_metrics_text(trt_manager* m, char* buf, size_t cap);
+/* serve that text over HTTP (GET /metrics) from a background thread, the role of prometheus::Exposer in the reference
+ * service (metrics.cc:34-60); port 0 = kernel-chosen, reported through *bound_port; stops with the manager */
+int trt_manager_serve_metrics(trt_manager* m, int port, int* bound_port);
 /* write a distinct batch from `ring` into the pinned input region of every pooled Buffers */
 int trt_manager_prefill_inputs(trt_manager* m, const char* model, const void* ring, size_t ring_batches);
 /* InferBench::Run closed loop; results16[InferBenchKey]; optional per-request latencies (seconds) */

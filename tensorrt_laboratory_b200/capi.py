@@ -93,6 +93,7 @@ SYMBOLS = [
     ("trt_manager_infer", _I, [_VP, _S, _I, _VP, _SZ, _VP, _SZ, C.POINTER(_D)]),
     ("trt_manager_infer_batched", _I, [_VP, _S, _I, _VP, _VP, _I, C.POINTER(_I)]),
     ("trt_manager_metrics_text", _I, [_VP, C.c_char_p, _SZ]),
+    ("trt_manager_serve_metrics", _I, [_VP, _I, C.POINTER(_I)]),
     ("trt_manager_prefill_inputs", _I, [_VP, _S, _VP, _SZ]),
     ("trt_manager_bench", _I, [_VP, _S, _I, _D, _SZ, C.POINTER(_D), C.POINTER(_D), _SZ, C.POINTER(_SZ)]),
     ("trt_timed_pipeline", _I, [_VP, _SZ, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -488,6 +489,12 @@ class InferenceManager:
         if n < 0:
             raise RuntimeError(self._lib.b2_last_error().decode())
         return buf.value.decode()
+
+    def serve_metrics(self, port: int = 0) -> int:
+        """Start the Prometheus HTTP endpoint (GET /metrics); -> the bound port."""
+        bound = _I()
+        check(self._lib.trt_manager_serve_metrics(self.handle, port, C.byref(bound)))
+        return bound.value
 
     def prefill_inputs(self, name: str, ring: np.ndarray):
         ring = np.ascontiguousarray(ring, dtype=[b["np_dtype"] for b in self.models[name].bindings if b["is_input"]][0])

@@ -21,6 +21,7 @@ using b2i::fail;
 struct trt_manager {
     std::shared_ptr<InferenceManager> mgr;
     std::shared_ptr<Runtime> runtime;
+    std::unique_ptr<trtlab::MetricsExposer> exposer;  // declared last: stops serving before the manager goes away
 };
 
 #define TRT_TRY try {
@@ -137,6 +138,20 @@ int trt_manager_metrics_text(trt_manager* m, char* buf, size_t cap) {
 
 // Give every pooled Buffers a distinct input batch in its pinned host stack.  Bindings are bump-allocated
 // from a stack that is Reset() on return, so the addresses (and contents) persist across requests.
+// HTTP endpoint for the Prometheus scraper (reference examples/02_TensorRT_GRPC/src/metrics.cc:34-60: Exposer on a port)
+int trt_manager_serve_metrics(trt_manager* m, int port, int* bound_port) {
+    if (!m) return fail(B2_EINVAL, "null manager");
+    TRT_TRY
+    auto mgr = m->mgr;
+    m->exposer = std::make_unique<trtlab::MetricsExposer>(port, [mgr] {
+        mgr->GetMetrics().SamplePower(mgr->Device());
+        return mgr->GetMetrics().Expose();
+    });
+    if (bound_port) *bound_port = m->exposer->Port();
+    return B2_OK;
+    TRT_CATCH
+}
+
 int trt_manager_prefill_inputs(trt_manager* m, const char* model_name, const void* ring, size_t ring_batches) {
     if (!m || !model_name || !ring || ring_batches == 0) return fail(B2_EINVAL, "bad arguments");
     TRT_TRY

@@ -196,3 +196,22 @@ def test_fp16_input_binding_is_recorded_in_the_plan():
         builder.build_plan(low, builder.PREC_FP32, 2, input_dtype="f16")
     with pytest.raises(ValueError):
         builder.build_plan(low, builder.PREC_FP16, 2, input_dtype="int8")
+
+
+def test_prometheus_http_endpoint(lib):
+    """GET /metrics on the manager's exposer returns the text exposition (reference metrics.cc:34-60: prometheus::Exposer);
+    runs without a GPU: the endpoint only renders counters."""
+    import urllib.error
+    import urllib.request
+    mgr = capi.InferenceManager(max_exec_concurrency=1, max_copy_concurrency=2)
+    try:
+        port = mgr.serve_metrics(0)
+        assert 1024 <= port < 65536
+        body = urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=5).read().decode()
+        assert "# TYPE yais_inference_load_ratio histogram" in body and 'yais_inference_load_ratio_bucket{le="+Inf"} 0' in body
+        assert body == mgr.metrics_text() or "yais_gpus_power_usage" in body
+        with pytest.raises(urllib.error.HTTPError) as ei:
+            urllib.request.urlopen(f"http://127.0.0.1:{port}/nope", timeout=5)
+        assert ei.value.code == 404
+    finally:
+        mgr.close()

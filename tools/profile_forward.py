@@ -16,22 +16,26 @@ def main():
     for kv in sys.argv[2:]:
         k, v = kv.split("=")
         opts[k] = int(v)
-    blob = builder.build_resnet_plan(50, builder.PREC_FP16, 8)
+    depth = int(os.environ.get("PROFILE_DEPTH", "50"))
+    batch = int(os.environ.get("PROFILE_BATCH", "8"))
+    prec = builder.PREC_INT8 if os.environ.get("PROFILE_PREC", "fp16") == "int8" else builder.PREC_FP16
+    blob = builder.build_resnet_plan(depth, prec, batch)
     eng = capi.Engine(blob)
+    eng.tune(streams=int(os.environ.get("PROFILE_TUNE_STREAMS", "4")))  # tactics are timed at load (B2_TUNE_CACHE pins them)
     sess = capi.Session(eng, opts)
-    x = weights.synthetic_input(8)
-    sess.host_array(0, 8)[...] = x
-    sess.h2d(8)
-    for _ in range(3):  # builds the plan, runs the autotuner, warms caches -- not profiled
-        sess.enqueue(8)
+    x = weights.synthetic_input(batch)
+    sess.host_array(0, batch)[...] = x
+    sess.h2d(batch)
+    for _ in range(3):  # builds the plan, warms caches -- not profiled
+        sess.enqueue(batch)
         sess.stream.sync()
     capi.check(capi.load().b2_profiler_start())
     for _ in range(passes):
-        sess.enqueue(8)
+        sess.enqueue(batch)
         sess.stream.sync()
     capi.check(capi.load().b2_profiler_stop())
-    n = sess.nb_launches(8)
-    names = [capi.load().b2_context_launch_name(sess.ctx, 8, i).decode() for i in range(n)]
+    n = sess.nb_launches(batch)
+    names = [capi.load().b2_context_launch_name(sess.ctx, batch, i).decode() for i in range(n)]
     with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "launch_names.txt"), "w") as f:
         f.write("\n".join(names) + "\n")
     sess.close()
