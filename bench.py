@@ -289,6 +289,7 @@ def run_b200(args):
     # cycles through every pooled Buffers / execution token at least twice.
     e2e_warm = max(max(args.warmup, 3) * CONTEXTS, 2 * BUFFERS * 2)
     per_rank = []  # per leg: every rank's own end-to-end rate
+    steady = []    # per leg: the mid-stream window measurement
 
     def e2e_run(plan_blob):
         mgr = capi.InferenceManager(CONTEXTS, BUFFERS, pre_threads=1, cuda_threads=1, post_threads=3)
@@ -301,6 +302,16 @@ def run_b200(args):
         barrier()
         per_rank.append(gather_over_ranks(args.steps * BATCH / res["kWalltime"]))
         wall = max_over_ranks(res["kWalltime"])
+        # the same K requests rated INSIDE one continuous loop (pipeline full on both sides of the window): a bracketed run
+        # of K = 20 requests is mostly the fill and drain of an 8-deep pipeline (1.4 ms each way against 3.4 ms of work)
+        win_s, win_lat = mgr.bench_window("rn50", BATCH, warm=e2e_warm, steps=args.steps, cool=2 * BUFFERS)
+        barrier()
+        steady.append({"value": world * args.steps * BATCH / max_over_ranks(win_s), "unit": UNIT,
+                       "p50_ms": float(np.percentile(win_lat, 50) * 1e3), "p99_ms": float(np.percentile(win_lat, 99) * 1e3),
+                       "requests": args.steps,
+                       "how": f"completions {e2e_warm + 1}..{e2e_warm + args.steps} of ONE continuous closed loop of "
+                              f"{e2e_warm + args.steps + 2 * BUFFERS} requests (InferBench::Run); every request still does its pinned H2D, "
+                              "forward and D2H inside the loop"})
         mgr.close()
         return (world * args.steps * BATCH / wall,
                 float(np.percentile(lats, 50) * 1e3) if len(lats) else None,
@@ -400,6 +411,7 @@ def run_b200(args):
                 "p50_ms": p50, "p99_ms": p99, "gpu_ms_per_request": e2e_gpu_ms,
                 "requests": args.steps, "warm_requests": e2e_warm,
                 "per_rank": per_rank[0], "h2d_gbs_per_rank": [v / BATCH * in_bytes / 1e9 for v in per_rank[0]],
+                "steady_state": steady[0],
                 "api": "InferenceManager+InferRunner+InferBench (pinned host Buffers, H2D/D2H per request)"},
         "e2e_fp16_input": {"value": e2e_h_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes // 2, "d2h_bytes_per_step": out_bytes,
                            "p50_ms": p50_h, "p99_ms": p99_h,

@@ -111,6 +111,11 @@ int b2_context_nb_launches(b2_context* c, int batch);
  * size 1..max when `all_batches` != 0) with `streams` concurrent streams (0 = default 4); results are kept on the engine.
  * No-op for fp32 engines and for plans that carry a tactic table.  Untuned engines run on a closed-form cost model. */
 int b2_engine_tune(b2_engine* e, int streams, int all_batches);
+/* Network-level refinement of the tactic table (build-time work, tens of seconds): starting from b2_engine_tune's
+ * per-layer choices, keep a tactic change when it raises the throughput of `streams` contexts running whole forward passes
+ * concurrently (the serving regime), up to `passes` sweeps over the convolutions.  *gain (optional) = rate after / before.
+ * Export the result with b2_engine_get_tactics and ship it in the plan (builder.attach_tactics). */
+int b2_engine_refine_tactics(b2_engine* e, int streams, int passes, double* gain);
 int b2_engine_nb_tactics(const b2_engine* e);
 /* exports the tactic table, 10 x uint32 per record {op, batch, bn, stages, splits, sps, ws, cn, halo, 0} (the TacticRec
  * layout of the plan format); builder.attach_tactics() appends it to a plan blob.  Returns the records written. */

@@ -629,6 +629,10 @@ class InferBench {
     // (Infer() call -> future ready) are appended to *latencies_s when non-null
     std::unique_ptr<Results> Run(const ModelsList& models, uint32_t batch_size, double seconds, size_t max_batches,
                                  std::vector<double>* latencies_s);
+    // ... and the completion time of every request (seconds since the loop started, same order as the latencies): lets a
+    // caller rate a window in the MIDDLE of one continuous closed loop, free of the pipeline's fill and drain
+    std::unique_ptr<Results> Run(const ModelsList& models, uint32_t batch_size, double seconds, size_t max_batches,
+                                 std::vector<double>* latencies_s, std::vector<double>* completions_s);
 
   protected:
     InferenceManager& InferResources() { return *m_Resources; }

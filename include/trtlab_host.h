@@ -42,6 +42,10 @@ int trt_manager_prefill_inputs(trt_manager* m, const char* model, const void* ri
 /* InferBench::Run closed loop; results16[InferBenchKey]; optional per-request latencies (seconds) */
 int trt_manager_bench(trt_manager* m, const char* model, int batch, double seconds, size_t max_batches,
                       double* results16, double* latencies, size_t lat_cap, size_t* lat_count);
+/* one continuous closed loop of warm + steps + cool requests; *window_seconds spans the `steps` completions in the middle
+ * (pipeline full on both sides), latencies[] = those requests' latencies */
+int trt_manager_bench_window(trt_manager* m, const char* model, int batch, size_t warm, size_t steps, size_t cool,
+                             double* window_seconds, double* latencies, size_t lat_cap, size_t* lat_count);
 /* TimedBenchmarkWorkspace::enqueue_pipeline averaged over iters */
 int trt_timed_pipeline(const void* blob, size_t nbytes, int iters, float* h2d_ms, float* compute_ms, float* d2h_ms);
 /* v2 surface: BenchmarkWorkspace (caller-captured graph of the forward pass, reference workspace.cc:21-124) at max batch:

@@ -48,6 +48,7 @@ SYMBOLS = [
     ("b2_context_nb_launches", _I, [_VP, _I]),
     ("b2_context_set_option", _I, [_VP, _S, _I]),
     ("b2_engine_tune", _I, [_VP, _I, _I]),
+    ("b2_engine_refine_tactics", _I, [_VP, _I, _I, C.POINTER(_D)]),
     ("b2_engine_nb_tactics", _I, [_VP]),
     ("b2_engine_get_tactics", _I, [_VP, C.POINTER(C.c_uint32), _I]),
     ("b2_context_prepare", _I, [_VP, _I, _VP]),
@@ -96,6 +97,7 @@ SYMBOLS = [
     ("trt_manager_serve_metrics", _I, [_VP, _I, C.POINTER(_I)]),
     ("trt_manager_prefill_inputs", _I, [_VP, _S, _VP, _SZ]),
     ("trt_manager_bench", _I, [_VP, _S, _I, _D, _SZ, C.POINTER(_D), C.POINTER(_D), _SZ, C.POINTER(_SZ)]),
+    ("trt_manager_bench_window", _I, [_VP, _S, _I, _SZ, _SZ, _SZ, C.POINTER(_D), C.POINTER(_D), _SZ, C.POINTER(_SZ)]),
     ("trt_timed_pipeline", _I, [_VP, _SZ, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("trt_device_throughput", _I, [_VP, _SZ, _I, _I, _I, _I, _VP, _I, C.POINTER(_D), C.POINTER(_I)]),
     ("trt_workspace_infer", _I, [_VP, _SZ, _VP, _SZ, _VP, _SZ, _I, _I]),
@@ -306,6 +308,13 @@ class Engine:
         check(self._lib.b2_engine_tune(self.handle, int(streams), 1 if all_batches else 0))
         return self._lib.b2_engine_nb_tactics(self.handle)
 
+    def refine_tactics(self, streams: int = 4, passes: int = 1) -> float:
+        """Network-level refinement of the tactic table in the serving regime (`streams` concurrent contexts);
+        -> throughput after / before."""
+        gain = _D()
+        check(self._lib.b2_engine_refine_tactics(self.handle, int(streams), int(passes), C.byref(gain)))
+        return gain.value
+
     def tactics(self) -> np.ndarray:
         """[n, 10] uint32: {op, batch, bn, stages, splits, sps, ws, cn, halo, 0} -- builder.attach_tactics() input."""
         n = self._lib.b2_engine_nb_tactics(self.handle)
@@ -509,6 +518,15 @@ class InferenceManager:
         out = {k: res[i] for i, k in enumerate(BENCH_KEYS)}
         lats = np.frombuffer(lat, dtype=np.float64, count=n.value).copy() if cap else np.zeros(0)
         return out, lats
+
+    def bench_window(self, name: str, batch: int, warm: int, steps: int, cool: int):
+        """One continuous closed loop of warm + steps + cool requests; -> (seconds spanned by the `steps` completions in the
+        middle, their latencies)."""
+        win = _D()
+        lat = (C.c_double * steps)()
+        n = _SZ()
+        check(self._lib.trt_manager_bench_window(self.handle, name.encode(), batch, warm, steps, cool, C.byref(win), lat, steps, C.byref(n)))
+        return win.value, np.array(lat[: n.value])
 
     def close(self):
         if self.handle and self.handle.value:

@@ -2040,6 +2040,155 @@ int b2_engine_tune(b2_engine* e, int streams, int all_batches) {
     return rc;
 }
 
+// ---- network-level refinement of the tactic table ---------------------------------------------------------------
+// The per-layer tuner times a layer against copies of ITSELF on N streams.  In service the N contexts are at DIFFERENT
+// layers and each forward pass is a chain of dependent launches, so what a tactic costs the others (shared memory it
+// holds while it waits) and what it gains (a shorter chain) only shows in the whole-network rate.  This pass walks the
+// convolutions and keeps a tactic change when it raises the measured throughput of `streams` contexts running whole
+// forward passes concurrently.  Every tactic computes the same bits, so this is purely a performance choice.
+namespace {
+struct RefineCtx {
+    b2_context* c = nullptr;
+    void* scratch = nullptr;
+    std::vector<void*> bind;
+    cudaStream_t s = nullptr;
+};
+}  // namespace
+
+int b2_engine_refine_tactics(b2_engine* e, int streams, int passes, double* gain_out) {
+    if (gain_out) *gain_out = 1.0;
+    if (!e) return fail(B2_EINVAL, "null engine");
+    if (e->inspect_only) return fail(B2_ESTATE, "engine was loaded with b2_engine_inspect (no device resources)");
+    if (!e->half() || e->tactics_from_plan) return B2_OK;
+    streams = std::max(1, std::min(streams > 0 ? streams : 4, 8));
+    int rc = b2_engine_tune(e, streams, 0);  // start from the per-layer table
+    if (rc) return rc;
+    std::lock_guard<std::mutex> run_lock(e->tune_run_mutex);
+    const int batch = e->max_batch;
+    std::vector<RefineCtx> ctx(static_cast<size_t>(streams));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&] {
+        cudaDeviceSynchronize();
+        for (auto& x : ctx) {
+            if (x.c) b2_context_destroy(x.c);
+            if (x.scratch) cudaFree(x.scratch);
+            for (void* p : x.bind)
+                if (p) cudaFree(p);
+            if (x.s) cudaStreamDestroy(x.s);
+        }
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+    bool ok = cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
+    for (auto& x : ctx) {
+        if (!ok) break;
+        ok = b2_context_create(e, &x.c) == B2_OK && cudaMalloc(&x.scratch, std::max<size_t>(e->arena_bytes, 1024)) == cudaSuccess &&
+             b2_context_set_device_memory(x.c, x.scratch) == B2_OK && cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) == cudaSuccess;
+        x.bind.assign(e->bindings.size(), nullptr);
+        for (size_t i = 0; i < e->bindings.size() && ok; ++i) {
+            const size_t bytes = e->bindings[i].item_bytes * size_t(e->max_batch);
+            ok = cudaMalloc(&x.bind[i], bytes) == cudaSuccess && cudaMemset(x.bind[i], 0, bytes) == cudaSuccess;
+        }
+    }
+    if (!ok) {
+        cudaGetLastError();
+        cleanup();
+        return fail(B2_ENOMEM, "refine: cannot set up %d contexts", streams);
+    }
+    const int iters = std::max(8, env_int("B2_REFINE_ITERS", 24));  // forward passes per context and measurement
+    int status = B2_OK;
+    auto measure = [&]() -> double {  // ms per forward pass of the whole job (all contexts), best of 2
+        for (auto& x : ctx) {
+            drop_cached(x.c);
+            if ((status = b2_context_prepare(x.c, batch, x.s))) return 1e30;
+        }
+        double best = 1e30;
+        for (int rep = 0; rep < 3 && !status; ++rep) {  // rep 0 = warm-up
+            for (auto& x : ctx) cudaStreamSynchronize(x.s);
+            cudaEventRecord(e0, ctx[0].s);
+            for (size_t k = 1; k < ctx.size(); ++k) cudaStreamWaitEvent(ctx[k].s, e0, 0);
+            const int n = rep == 0 ? 4 : iters;
+            for (int i = 0; i < n && !status; ++i)
+                for (auto& x : ctx)
+                    if ((status = b2_context_enqueue(x.c, batch, x.bind.data(), x.s, nullptr))) break;
+            for (size_t k = 1; k < ctx.size(); ++k) {
+                cudaEvent_t d = nullptr;
+                cudaEventCreateWithFlags(&d, cudaEventDisableTiming);
+                cudaEventRecord(d, ctx[k].s);
+                cudaStreamWaitEvent(ctx[0].s, d, 0);
+                cudaEventDestroy(d);
+            }
+            cudaEventRecord(e1, ctx[0].s);
+            if (cudaStreamSynchronize(ctx[0].s) != cudaSuccess) {
+                status = fail(B2_ECUDA, "refine: forward pass failed: %s", cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0) best = std::min(best, double(ms) / (double(n) * double(ctx.size())));
+        }
+        return best;
+    };
+    double base = measure();
+    const double first = base;
+    const double keep = 1.0 - std::max(0.0, double(env_int("B2_REFINE_MIN_GAIN_PERMILLE", 7))) / 1000.0;  // accept only clear wins
+    for (int pass = 0; pass < std::max(1, passes) && !status; ++pass) {
+        int changed = 0;
+        for (size_t i = 0; i < e->ops.size() && !status; ++i) {
+            const Op& op = e->ops[i];
+            const b2plan::OpRec& r = op.r;
+            if (r.type != b2plan::OP_CONV || (r.relu & 4)) continue;
+            ConvConfig cur;
+            {
+                std::lock_guard<std::mutex> lock(e->tune_mutex);
+                auto it = e->tuned.find({int(i), batch});
+                if (it == e->tuned.end()) continue;
+                cur = it->second;
+            }
+            const int kbsz = conv_kb(ctx[0].c, op);
+            if (kbsz != 64 || cur.splits > 1 || cur.ws || cur.cn > 1) continue;  // (the split factor is part of the results' order)
+            const int nkb = conv_num_kblocks(ctx[0].c, op);
+            std::vector<ConvConfig> cands;
+            for (int bn : {64, 128, 256}) {
+                if (int(r.cout_phys) % bn) continue;
+                for (int sps = 1; sps <= 2; ++sps)
+                    for (int st : {1, 2, 4, 8}) {
+                        if (!b2k::conv_config_exists(bn, kbsz, st, sps) || b2k::conv_smem_bytes(bn, st, r.res >= 0, sps) > 227 * 1024) continue;
+                        if (st * sps > nkb + 1 && st > 1) continue;  // a ring deeper than the K loop only costs shared memory
+                        if (sps == 2 && nkb < 4) continue;
+                        if (bn == cur.bn && st == cur.stages && sps == cur.sps && !cur.halo) continue;
+                        cands.push_back(ConvConfig{bn, st, 1, 0.0, sps, 0, 1});
+                    }
+                if (conv_halo_rows(ctx[0].c, op) && b2k::conv_halo_config_exists(bn) && int(r.cin_phys) / 64 <= 8 && !(cur.halo && cur.bn == bn) &&
+                    b2k::conv_halo_smem(bn, int(e->tensors[r.out].w), conv_halo_rows(ctx[0].c, op), int(r.cin_phys) / 64) <= 227 * 1024) {
+                    ConvConfig hc{bn, kHaloStagesTag, 1, 0.0, 1, 0, 1};
+                    hc.halo = 1;
+                    cands.push_back(hc);
+                }
+            }
+            ConvConfig best = cur;
+            for (const ConvConfig& cand : cands) {
+                {
+                    std::lock_guard<std::mutex> lock(e->tune_mutex);
+                    e->tuned[{int(i), batch}] = cand;
+                }
+                const double t = measure();
+                if (status) break;
+                if (t < base * keep) base = t, best = cand, ++changed;
+            }
+            std::lock_guard<std::mutex> lock(e->tune_mutex);
+            e->tuned[{int(i), batch}] = best;
+        }
+        if (!changed) break;
+    }
+    if (!status) {
+        const double last = measure();  // (re-measured with the final table)
+        if (gain_out && last > 0 && last < 1e29) *gain_out = first / last;
+    }
+    cleanup();
+    return status;
+}
+
 int b2_engine_nb_tactics(const b2_engine* e) {
     if (!e) return 0;
     std::lock_guard<std::mutex> lock(const_cast<b2_engine*>(e)->tune_mutex);

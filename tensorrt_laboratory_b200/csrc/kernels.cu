@@ -1900,7 +1900,7 @@ int launch_tail_f16(const TailArgs& a, cudaStream_t stream) {
     static int cap = -1, use_pdl = -1;
     if (cap < 0) {
         const char* v = getenv("B2_TAIL_CTAS");
-        cap = v ? atoi(v) : 64;  // a small grid: the items are tiny and early-launched CTAs hold shared memory other streams want
+        cap = v ? atoi(v) : 148;  // one wave: every FC item (8 neurons) gets its own CTA, so the weight rows stream in one round
         if (cap < 1) cap = 1;
         v = getenv("B2_TAIL_PDL");
         use_pdl = v ? atoi(v) : 1;

@@ -189,6 +189,32 @@ int trt_manager_bench(trt_manager* m, const char* model_name, int batch, double 
     TRT_CATCH
 }
 
+// One CONTINUOUS closed loop of warm + steps + cool requests (InferBench::Run); rates the `steps` completions in the
+// middle: *window_seconds = time from the warm-th completion to the (warm + steps)-th, latencies[] = those requests'
+// latencies.  The pipeline (8 Buffers, 4 lanes) is full on both sides of the window, so a short window measures the
+// steady state instead of the fill / drain transients a bracketed run of the same length is dominated by.
+int trt_manager_bench_window(trt_manager* m, const char* model_name, int batch, size_t warm, size_t steps, size_t cool,
+                             double* window_seconds, double* latencies, size_t lat_cap, size_t* lat_count) {
+    if (!m || !model_name || !window_seconds || steps < 1) return fail(B2_EINVAL, "bad arguments");
+    TRT_TRY
+    auto model = m->mgr->GetModel(model_name);
+    InferBench bench(m->mgr);
+    std::vector<double> lat, done;
+    InferBench::ModelsList models = {model};
+    bench.Run(models, uint32_t(batch), 3600.0, warm + steps + cool, &lat, &done);
+    if (done.size() != warm + steps + cool) return fail(B2_EINVAL, "bench loop ended early (%zu of %zu requests)", done.size(), warm + steps + cool);
+    std::vector<size_t> order(done.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return done[a] < done[b]; });
+    const double t_begin = warm ? done[order[warm - 1]] : 0.0;
+    *window_seconds = done[order[warm + steps - 1]] - t_begin;
+    size_t n = 0;
+    for (size_t k = warm; k < warm + steps && latencies && n < lat_cap; ++k) latencies[n++] = lat[order[k]];
+    if (lat_count) *lat_count = n;
+    return B2_OK;
+    TRT_CATCH
+}
+
 // H2D / compute / D2H breakdown of the v2 single-stream pipeline (TimedBenchmarkWorkspace)
 int trt_timed_pipeline(const void* blob, size_t nbytes, int iters, float* h2d_ms, float* compute_ms, float* d2h_ms) {
     if (!blob || iters < 1) return fail(B2_EINVAL, "bad arguments");

@@ -563,6 +563,12 @@ std::unique_ptr<InferBench::Results> InferBench::Run(const ModelsList& models, u
 
 std::unique_ptr<InferBench::Results> InferBench::Run(const ModelsList& models, uint32_t batch_size, double seconds,
                                                      size_t max_batches, std::vector<double>* latencies_s) {
+    return Run(models, batch_size, seconds, max_batches, latencies_s, nullptr);
+}
+
+std::unique_ptr<InferBench::Results> InferBench::Run(const ModelsList& models, uint32_t batch_size, double seconds,
+                                                     size_t max_batches, std::vector<double>* latencies_s,
+                                                     std::vector<double>* completions_s) {
     // infer_bench.cc:46-110: closed loop -- GetBuffers() blocks when all Buffers are in flight
     using clock = std::chrono::high_resolution_clock;
     size_t batch_count = 0;
@@ -571,6 +577,7 @@ std::unique_ptr<InferBench::Results> InferBench::Run(const ModelsList& models, u
     for (const auto& model : models) TRTLAB_CHECK_OP(batch_size, <=, uint32_t(model->GetMaxBatchSize()));
 
     auto lat = std::make_shared<std::vector<double>>();
+    auto done_at = std::make_shared<std::vector<double>>();  // completion time of every request, seconds since the loop started
     auto lat_mutex = std::make_shared<std::mutex>();
     if (latencies_s) lat->reserve(max_batches ? max_batches : 1 << 16);
 
@@ -587,13 +594,16 @@ std::unique_ptr<InferBench::Results> InferBench::Run(const ModelsList& models, u
         const auto t0 = clock::now();
         InferRunner runner(model, m_Resources);
         const bool want_lat = latencies_s != nullptr;
+        const bool want_done = completions_s != nullptr;
         auto resources = m_Resources;
-        futures.push_back(runner.Infer(bindings, [t0, lat, lat_mutex, want_lat, resources](std::shared_ptr<Bindings>& b) mutable {
-            const double dt = std::chrono::duration<double>(clock::now() - t0).count();
+        futures.push_back(runner.Infer(bindings, [t0, start, lat, done_at, lat_mutex, want_lat, want_done, resources](std::shared_ptr<Bindings>& b) mutable {
+            const auto now = clock::now();
+            const double dt = std::chrono::duration<double>(now - t0).count();
             resources->GetMetrics().ObserveRequest(b->GetModel()->Name(), b->ComputeTime(), dt);
-            if (want_lat) {
+            if (want_lat || want_done) {
                 std::lock_guard<std::mutex> l(*lat_mutex);
-                lat->push_back(dt);
+                if (want_lat) lat->push_back(dt);
+                if (want_done) done_at->push_back(std::chrono::duration<double>(now - start).count());  // same order as `lat`
             }
             b.reset();
         }));
@@ -624,6 +634,7 @@ std::unique_ptr<InferBench::Results> InferBench::Run(const ModelsList& models, u
         results[kLatencyMax] = sorted.back();
         latencies_s->insert(latencies_s->end(), lat->begin(), lat->end());
     }
+    if (completions_s) completions_s->insert(completions_s->end(), done_at->begin(), done_at->end());
     return results_ptr;
 }
 
