@@ -2146,9 +2146,28 @@ int b2_engine_refine_tactics(b2_engine* e, int streams, int passes, double* gain
                 cur = it->second;
             }
             const int kbsz = conv_kb(ctx[0].c, op);
-            if (kbsz != 64 || cur.splits > 1 || cur.ws || cur.cn > 1) continue;  // (the split factor is part of the results' order)
+            if (kbsz != 64 || cur.ws || cur.cn > 1) continue;
             const int nkb = conv_num_kblocks(ctx[0].c, op);
             std::vector<ConvConfig> cands;
+            // split-K: a deep-K layer with few tiles (res4 / res5 3x3) is a LONG link of the dependency chain on a handful
+            // of SMs; splitting K shortens the link and puts more SMs on it.  The per-layer tuner rejects it (more total
+            // work), the chain-bound whole-network rate is where it can pay.  (The split factor fixes the fp32 summation
+            // order; it is chosen here, at max batch, and shared by every batch size.)
+            if (!(op.side_join >= 0) && cur.splits == 1 && !cur.halo) {
+                const int m_tiles = (batch * int(e->tensors[r.out].h * e->tensors[r.out].w) + 127) / 128;
+                for (int sp : {2, 4}) {
+                    const int tiles = m_tiles * (int(r.cout_phys) / cur.bn);
+                    const int kpc = (nkb + sp - 1) / sp;
+                    if (nkb < 16 || tiles >= 100 || tiles * sp > 160 || kpc < 4 || (sp - 1) * kpc >= nkb || tiles > kMaxSplitTiles / 8 ||
+                        size_t(tiles) * sp * 128 * cur.bn * 4 > kSplitWorkspaceBytes)
+                        continue;
+                    for (int st : {2, 4}) {
+                        if (!b2k::conv_config_exists(cur.bn, kbsz, st, 1) || b2k::conv_smem_bytes(cur.bn, st, r.res >= 0, 1) > 227 * 1024) continue;
+                        cands.push_back(ConvConfig{cur.bn, st, sp, 0.0, 1, 0, 1});
+                    }
+                }
+            }
+            if (cur.splits > 1) continue;  // already split: leave it
             for (int bn : {64, 128, 256}) {
                 if (int(r.cout_phys) % bn) continue;
                 for (int sps = 1; sps <= 2; ++sps)
