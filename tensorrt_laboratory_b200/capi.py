@@ -476,9 +476,24 @@ class InferenceManager:
         batch = x.shape[0]
         ob = [b for b in meta.bindings if not b["is_input"]][0]
         out = np.empty((batch,) + ob["shape"], dtype=np.float32)
+        sec = _D()
         check(self._lib.trt_manager_infer(self.handle, name.encode(), batch, x.ctypes.data, x.nbytes,
-                                          out.ctypes.data, out.nbytes, None))
+                                          out.ctypes.data, out.nbytes, C.byref(sec)))
+        self.last_compute_seconds = sec.value  # device time of the forward pass (ExecutionContext::Synchronize)
         return out
+
+    def infer_timed(self, name: str, x: np.ndarray):
+        """-> (output, device seconds of the forward pass), what the reference service reports as compute_time
+        (examples/02_TensorRT_GRPC/src/server.cc:169)."""
+        meta = self.models[name]
+        x = np.ascontiguousarray(x, dtype=[b["np_dtype"] for b in meta.bindings if b["is_input"]][0])
+        batch = x.shape[0]
+        ob = [b for b in meta.bindings if not b["is_input"]][0]
+        out = np.empty((batch,) + ob["shape"], dtype=np.float32)
+        sec = _D()
+        check(self._lib.trt_manager_infer(self.handle, name.encode(), batch, x.ctypes.data, x.nbytes,
+                                          out.ctypes.data, out.nbytes, C.byref(sec)))
+        return out, sec.value
 
     def infer_batched(self, name: str, x: np.ndarray, window_us: int = 2000):
         """Every image of ``x`` as its own request through BatchedInferRunner -> (outputs [n, ...], merged forward passes)."""

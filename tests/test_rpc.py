@@ -134,6 +134,7 @@ def test_inference_service_matches_direct_path(gpu):
         for (i, n), f in zip(enumerate((8, 3, 8, 1), start=1), futs):
             out = f.result(timeout=120)
             assert out.batch_id == i and len(out.elements) == n and out.total_time > 0
+            assert 0 < out.compute_time < out.total_time  # device time of the forward pass (server.cc:169), not the wall time
             assert [e.predictions[0].class_id for e in out.elements] == list(direct[:n].argmax(axis=1))
             np.testing.assert_allclose([e.predictions[0].score for e in out.elements], direct[:n].max(axis=1), rtol=1e-6)
         client.close()
