@@ -26,6 +26,7 @@
 #include "trtlab/core/batcher.h"
 #include "trtlab/tensorrt/metrics.h"
 #include "trtlab/core/hotpath_core.h"
+#include "trtlab/cuda/sync.h"
 
 // CUDA handle aliases: when the CUDA runtime header is present use its types, otherwise opaque pointers
 #if defined(__CUDACC__) || defined(__CUDA_RUNTIME_H__) || defined(B2_WITH_CUDA_RUNTIME)
@@ -307,6 +308,8 @@ class Bindings {
 
     inline cudaStream_t Stream() const { return m_Buffers->Stream(); }
     void Synchronize() const { m_Buffers->Synchronize(); }
+    template <typename ThreadType>
+    void Synchronize() const { cuda_sync<ThreadType>::stream_sync(reinterpret_cast<b2_stream_t>(Stream())); }
     // device time of this request's forward pass, filled in by InferRunner's post stage before the user's function runs
     // (what the reference's service reads from ctx->Synchronize(), server.cc:169)
     double ComputeTime() const { return m_ComputeSeconds; }
@@ -320,6 +323,7 @@ class Bindings {
     uint32_t m_BatchSize;
     std::vector<void*> m_HostAddresses;
     std::vector<void*> m_DeviceAddresses;
+    std::map<uint32_t, void*> m_StagedDevice;  // zero-copy inputs: the device staging address the binding would have used
     void* m_ActivationsAddress;
     double m_ComputeSeconds = 0.0;
     friend class Buffers;
@@ -354,6 +358,14 @@ class ExecutionContext {
     void Infer(const std::shared_ptr<Bindings>&);
     // waits for the completion event, returns the GPU compute time in seconds
     double Synchronize();
+    // the same wait under an explicit threading policy: Synchronize<userspace_threads>() polls and yields
+    // (cuda_sync, trtlab/cuda/sync.h) instead of parking the OS thread in the driver
+    template <typename ThreadType>
+    double Synchronize() {
+        cuda_sync<ThreadType>::event_sync(reinterpret_cast<b2_event_t>(m_Done));
+        return ElapsedSeconds();
+    }
+    double ElapsedSeconds() const;  // start -> done of the last Infer(); valid once the completion event has fired
     // fiber-friendly variant: 0 when done, 1 while running (cuda_sync<userspace_threads>, sync.h:19-47)
     int Query();
     void Reset();
@@ -396,6 +408,12 @@ class InferenceManager : public ::trtlab::Resources {
     void ForEachModel(std::function<void(const Model&)>);
 
     int MaxExecConcurrency() const;
+    // how the post stage waits for the device: false = cuda_sync<standard_threads> (park in the driver, the default),
+    // true = cuda_sync<userspace_threads> (poll + yield; TRTLAB_SYNC=yield), reference trtlab/cuda/sync.h:13-62
+    static bool YieldingSync();
+    // TRTLAB_ZERO_COPY_INPUT=1: Bindings::CopyToDevice(input) stages nothing -- the engine's input cast reads the mapped
+    // pinned host buffer over PCIe itself (the transfer is fused into the first kernel of the forward pass)
+    static bool ZeroCopyInput();
     static int EnqueueDepth();  // tokens queued per execution lane (TRTLAB_ENQUEUE_DEPTH, default 2)
     // request / compute summaries, load-ratio histogram, power gauge (metrics.h); fed by InferBench and by services
     Metrics& GetMetrics() { return m_Metrics; }
@@ -496,11 +514,16 @@ struct InferRunner : public AsyncComputeWrapper<void(std::shared_ptr<Bindings>&)
             bindings->CopyFromDevice(bindings->OutputBindings());                  // D2H
             resources->AcquireThreadPool("post").enqueue([resources, bindings, trt_ctx, Post]() mutable {
                 resources->ActivateDevice();
-                const double compute_seconds = trt_ctx->Synchronize();
+                const bool yielding = InferenceManager::YieldingSync();
+                const double compute_seconds =
+                    yielding ? trt_ctx->template Synchronize<userspace_threads>() : trt_ctx->Synchronize();
                 resources->RecordComputeTime(compute_seconds);
                 bindings->SetComputeTime(compute_seconds);
                 trt_ctx.reset();  // returns both pool tokens
-                bindings->Synchronize();
+                if (yielding)
+                    bindings->template Synchronize<userspace_threads>();
+                else
+                    bindings->Synchronize();
                 (*Post)(bindings);
                 bindings.reset();  // returns the Buffers
             });

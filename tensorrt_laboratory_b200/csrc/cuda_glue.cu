@@ -131,7 +131,7 @@ int b2_free_device(void* ptr) {
 }
 int b2_malloc_host(void** ptr, size_t bytes) {
     if (!ptr) return fail(B2_EINVAL, "null ptr");
-    B2G_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    B2G_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));  // mapped: kernels may read it in place
     return B2_OK;
 }
 int b2_free_host(void* ptr) {

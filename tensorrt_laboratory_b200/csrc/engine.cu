@@ -154,6 +154,7 @@ struct Launch {
     const float* bias = nullptr;
     int in_binding = -1, out_binding = -1;
     bool src_half = false;  // input cast: the binding is fp16
+    int max_blocks = 0;     // input cast: grid cap (option input_ctas), 0 = one thread per element group
     int side_join = -1;     // see Op::side_join (launch index == op index)
     std::shared_ptr<NetRun> net;  // L_NET
     b2k::TailArgs tail{};         // L_TAIL: pool + fc + softmax in one launch (out = the output binding)
@@ -300,6 +301,7 @@ struct b2_context {
     int i8_bn = 0;       // INT8 convolutions: force the N tile (128 / 256); 0 = 128
     int i8_stages = 0;   // ... and the shared-memory ring depth (2..4); 0 = by rule
     int fuse_tail = 1;   // global average pool + FC + softmax as one launch (tail_f16_kernel)
+    int input_ctas = 0;  // grid cap of the input cast (0 = none); set when the input binding is read over PCIe (zero-copy)
     int* d_tail_ctrl = nullptr;  // its ticket / arrival counters (zero between launches)
     cudaStream_t side = nullptr;
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
@@ -852,6 +854,7 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, int 
     const int bns[4] = {256, 128, 64, 32};
     const int stgs[4] = {1, 2, 4, 8};
     int status = B2_OK;
+    const int verbose = env_int("B2_TUNE_VERBOSE", 0);             // 1: the winner per layer, 2: every candidate
     const int iters = std::max(4, env_int("B2_TUNE_ITERS", 12));   // launches per stream and measurement
     const int reps = std::max(1, env_int("B2_TUNE_REPS", 2));      // measurements per candidate (the quietest counts)
     const int m_tiles = (M + 127) / 128;
@@ -878,6 +881,8 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, int 
             if (ws) {
                 candidates.push_back(ConvConfig{bn, st, 1, 0.0, sps, std::min(tiles, 148), 1});
                 if (tiles > 74) candidates.push_back(ConvConfig{bn, st, 1, 0.0, sps, 74, 1});  // half the SMs per stream
+                if (tiles >= 592 && b2k::conv_ws_smem(bn, st, sps, r.res >= 0) <= 113 * 1024)
+                    candidates.push_back(ConvConfig{bn, st, 1, 0.0, sps, 296, 1});  // two co-resident CTAs per SM
                 continue;
             }
             if (sps == 2 && kpc < 4) continue;  // double-width stages only pay on long K loops
@@ -959,6 +964,9 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, int 
                               cudaGetErrorString(rc ? cudaError_t(rc) : se));
                 break;
             }
+            if (verbose > 1)
+                fprintf(stderr, "[b2 tune]   %s b=%d cand bn=%d st=%d sp=%d sps=%d ws=%d cn=%d halo=%d : %.3f us/launch\n", op.name.c_str(),
+                        batch, cand.bn, cand.stages, cand.splits, cand.sps, cand.ws, cand.cn, cand.halo, ms * 1e3 / (iters * ns));
             if (ms < best_ms) best_ms = ms, best = cand;
         }
         if (status) break;
@@ -966,6 +974,10 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, int 
     cleanup();
     if (status) return status;
     best.est_us = best_ms * 1e3 / (iters * ns);
+    if (verbose)
+        fprintf(stderr, "[b2 tune] %s b=%d M=%d N=%d K=%d best bn=%d st=%d sp=%d sps=%d ws=%d cn=%d halo=%d : %.3f us/launch (%d streams)\n",
+                op.name.c_str(), batch, M, int(r.cout_phys), nkb * kbsz, best.bn, best.stages, best.splits, best.sps, best.ws, best.cn,
+                best.halo, best.est_us, ns);
     *best_out = best;
     (void)M;
     return B2_OK;
@@ -1039,6 +1051,7 @@ int autotune_i8_conv(b2_context* c, const Op& op, int batch, ConvConfig* best_ou
         cleanup();
         return fail(B2_ECUDA, "autotune: cannot create streams/events");
     }
+    const int verbose = env_int("B2_TUNE_VERBOSE", 0);
     const int iters = std::max(4, env_int("B2_TUNE_ITERS", 12));
     const int reps = std::max(1, env_int("B2_TUNE_REPS", 2));
     double best_ms = 1e30;
@@ -1075,12 +1088,22 @@ int autotune_i8_conv(b2_context* c, const Op& op, int batch, ConvConfig* best_ou
                               cudaGetErrorString(rc ? cudaError_t(rc) : se));
                 break;
             }
+            if (verbose > 1)
+                fprintf(stderr, "[b2 tune]   %s b=%d cand int8 bn=%d st=%d : %.3f us/launch\n", op.name.c_str(), batch, bn, st,
+                        ms * 1e3 / (iters * ns));
             if (ms < best_ms) best_ms = ms, best = ConvConfig{bn, st, 1, 0.0, 1, 0, 1};
         }
     }
     cleanup();
     if (status) return status;
     best.est_us = best_ms * 1e3 / (iters * ns);
+    if (verbose) {
+        const Tensor& to = c->e->tensors[r.out];
+        const long long M = (long long)batch * to.h * to.w, K = (long long)r.k * r.k * r.cin_phys;
+        fprintf(stderr, "[b2 tune] %s b=%d M=%lld N=%d K=%lld best int8 bn=%d st=%d : %.3f us/launch (%d streams) %.0f TOP/s\n",
+                op.name.c_str(), batch, M, int(r.cout_phys), K, best.bn, best.stages, best.est_us, ns,
+                2.0 * M * r.cout_phys * K / best.est_us * 1e-6);
+    }
     *best_out = best;
     return B2_OK;
 }
@@ -1339,6 +1362,7 @@ int build_plan(b2_context* c, int batch, Plan** out) {
                 L.out = tptr(r.out);
                 L.C = t.c, L.H = t.h, L.W = t.w, L.C_phys = t.c_phys;
                 L.k = int(r.k);  // 2: horizontal space-to-depth (tensor is [H, W/2, 8]; binding is [C, H, W])
+                L.max_blocks = c->input_ctas;
                 if (r.k == 2) {  // pad_ / stride = zero pixels written left / right of every packed row
                     const Binding& b = e->bindings[r.binding];
                     if (!half || b.nd != 3 || b.dims[0] > 4 || t.c_phys != 8 || int(t.h) != b.dims[1] ||
@@ -1547,8 +1571,8 @@ int run_launch(const b2_engine* e, const Launch& L, void* const* bindings, cudaS
     void* out = L.out_binding >= 0 ? bindings[L.out_binding] : L.out;
     switch (L.kind) {
         case L_INPUT_CAST:
-            if (L.k == 2) return b2k::launch_input_cast_s2d(in, L.src_half, out, L.N, L.C, L.H, L.W, L.pad, L.stride, s);
-            return b2k::launch_input_cast(in, L.src_half, out, L.N, L.C, L.H, L.W, L.C_phys, half, s);
+            if (L.k == 2) return b2k::launch_input_cast_s2d(in, L.src_half, out, L.N, L.C, L.H, L.W, L.pad, L.stride, L.max_blocks, s);
+            return b2k::launch_input_cast(in, L.src_half, out, L.N, L.C, L.H, L.W, L.C_phys, half, L.max_blocks, s);
         case L_OUTPUT_CAST:
             return b2k::launch_output_cast(in, static_cast<float*>(out), L.N, L.C, L.H, L.W, L.C_phys, half, s);
         case L_CONV_TC:
@@ -1924,6 +1948,7 @@ int b2_context_create(b2_engine* e, b2_context** out) {
     c->net_bn = env_int("B2_NET_BN", 0);
     c->net_stages = env_int("B2_NET_STAGES", 0);
     c->fuse_tail = env_int("B2_FUSE_TAIL", 1);
+    c->input_ctas = env_int("B2_INPUT_CTAS", 0);
     c->i8_bn = env_int("B2_I8_BN", 0);
     c->i8_stages = env_int("B2_I8_STAGES", 0);
     if (getenv("B2_PDL")) b2k::set_pdl(env_int("B2_PDL", 1) != 0);
@@ -1990,6 +2015,7 @@ int b2_context_set_option(b2_context* c, const char* key, int value) {
     else if (k == "fuse_tail") c->fuse_tail = value;
     else if (k == "i8_bn") c->i8_bn = value;
     else if (k == "i8_stages") c->i8_stages = value;
+    else if (k == "input_ctas") c->input_ctas = value;
     else if (k == "pdl_trigger") c->pdl_trigger = value;
     else if (k == "autotune") c->autotune = value;
     else if (k == "no_fold") c->no_fold = value;
@@ -2333,7 +2359,7 @@ int b2_context_debug_conv_timing(b2_context* c, int batch, int i, int reps, b2_s
     if (!c || build_plan(c, batch, &plan)) return fail(B2_EINVAL, "no plan");
     if (i < 0 || i >= int(plan->launches.size()) || plan->launches[i].kind != L_CONV_TC) return fail(B2_EINVAL, "not a tcgen05 conv launch");
     b2k::ConvLaunch cl = plan->launches[i].conv;
-    const int ctas = cl.grid_m * cl.grid_n * cl.args.splits;
+    const int ctas = cl.ws_ctas > 0 ? cl.ws_ctas : cl.grid_m * cl.grid_n * cl.args.splits;
     if (n_ctas) *n_ctas = ctas;
     if (ctas > cap_ctas) return fail(B2_EINVAL, "stamp buffer too small (%d CTAs)", ctas);
     long long* d = nullptr;

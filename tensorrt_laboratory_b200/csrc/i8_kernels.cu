@@ -41,6 +41,14 @@ __host__ __device__ constexpr int conv_i8_smem_layout_bytes(int bn, int stages, 
 
 }  // namespace
 
+// four s32 -> one word of four s8 (byte i = sat_s8(q_i)): two saturating pack conversions
+__device__ __forceinline__ uint32_t pack4_sat_s8(int q0, int q1, int q2, int q3) {
+    uint32_t hi, out;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(q3), "r"(q2), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(q1), "r"(q0), "r"(hi));
+    return out;
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(128)
 conv_i8_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapOut,
@@ -199,18 +207,23 @@ conv_i8_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             uint4 rv = make_uint4(0u, 0u, 0u, 0u);
             if (has_res) rv = *reinterpret_cast<const uint4*>(sRes + so);
             const int8_t* rq = reinterpret_cast<const int8_t*>(&rv);
-            uint4 o;
-            int8_t* oq = reinterpret_cast<int8_t*>(&o);
+            // q = clip(rint(max(t, relu ? 0 : -inf)), -127, 127) with as few issue slots as the contract allows (this loop is
+            // what bounds the wide, short-K layers): the lower clamp and the ReLU are ONE fp32 max before the conversion
+            // (rint is monotonic and rint(-127) = -127), the upper clamp is the saturation of the s32 -> s8 pack.
+            const float lo = relu ? 0.0f : -127.0f;
+            int q[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int c = col + i;
                 float t = __fadd_rn(__fmul_rn(__int2float_rn(static_cast<int>(acc[h * 16 + i])), s_m[c]), s_b[c]);
                 if (has_res) t = __fadd_rn(t, __fmul_rn(__int2float_rn(static_cast<int>(rq[i])), r));
-                if (relu) t = fmaxf(t, 0.0f);
-                int q = __float2int_rn(t);
-                q = q < -127 ? -127 : (q > 127 ? 127 : q);
-                oq[i] = static_cast<int8_t>(q);
+                q[i] = __float2int_rn(fmaxf(t, lo));  // > 127 (up to INT_MAX for huge t) saturates in the pack
             }
+            uint4 o;
+            o.x = pack4_sat_s8(q[0], q[1], q[2], q[3]);
+            o.y = pack4_sat_s8(q[4], q[5], q[6], q[7]);
+            o.z = pack4_sat_s8(q[8], q[9], q[10], q[11]);
+            o.w = pack4_sat_s8(q[12], q[13], q[14], q[15]);
             *reinterpret_cast<uint4*>(sOut + so) = o;
         }
     }

@@ -506,20 +506,27 @@ conv_f16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
 // =================================================================================================
 // conv_f16_tcgen05_ws -- persistent, warp-specialised variant (a TACTIC next to the one-tile-per-CTA kernel).
-//   gridDim.x CTAs walk the tile list with a static stride.  8 warps:
-//     warp 0  activation producer (TMA, also the residual tile)      warp 1  MMA issuer
-//     warp 2  weight producer (cp.async.bulk) + TMEM owner           warp 3  idle
-//     warps 4-7  epilogue (TMEM lane quadrant = warp % 4)
-//   Two TMEM accumulators: the epilogue of tile i (TMEM -> regs -> swizzled smem -> TMA store) overlaps the loads
-//   and MMAs of tile i+1; the prologue (barrier init, TMEM alloc) and the first TMA round trip are paid once per CTA
-//   instead of once per tile.  64-channel K-blocks with packed weights only; no split-K.
+//   gridDim.x CTAs walk the tile list with a static stride.  12 warps:
+//     warp 0  activation producer (TMA)                              warp 1  MMA issuer
+//     warp 2  weight producer (cp.async.bulk) + TMEM owner           warp 3  residual producer (TMA)
+//     warps 4-7   epilogue group 0: the CTA's even tiles, accumulator 0, staging / residual buffer 0
+//     warps 8-11  epilogue group 1: the odd tiles, accumulator 1, staging / residual buffer 1
+//   (TMEM lane quadrant of an epilogue warp = warp % 4.)
+//   Everything a tile needs is double-buffered, so the stream never drains: while group g turns tile i into fp16
+//   (TMEM -> regs -> +bias +residual, ReLU -> swizzled smem -> TMA store), the other group does the same for tile i+1,
+//   the MMA warp fills the accumulator of tile i+2's parity as soon as it is drained, the producers run STAGES K-blocks
+//   and one residual tile ahead, and the TMA store of a staging buffer is awaited only right before that buffer is
+//   written again (two tiles later).  For the wide, short-K 1x1 convolutions with a residual -- memory-shaped layers
+//   whose roofline is the L2 read+write stream (tools/micro/l2_stream.cu) -- this keeps loads, math and stores of
+//   three tiles in flight per CTA.  The prologue (barrier init, TMEM alloc) and the first TMA round trip are paid once
+//   per CTA instead of once per tile.  64-channel K-blocks with packed weights only; no split-K.
 // =================================================================================================
 __host__ __device__ constexpr int conv_ws_smem_bytes(int bn, int stages, int sps, bool residual) {
-    return stages * sps * (128 * 64 * 2 + bn * 64 * 2) + 128 * bn * 2 + (residual ? 128 * bn * 2 : 0) + 256 + 1024;
+    return stages * sps * (128 * 64 * 2 + bn * 64 * 2) + 2 * 128 * bn * 2 + (residual ? 2 * 128 * bn * 2 : 0) + 256 + 1024;
 }
 
 template <int BN, int STAGES, int SPS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(384)
 conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapOut,
                     const __grid_constant__ CUtensorMap mapRes, const ConvArgs p) {
     constexpr int A_SUBBLK = 128 * 64 * 2;
@@ -540,16 +547,16 @@ conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const bool has_res = p.residual != nullptr;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE;
-    uint8_t* sOut = smem + PIPE_BYTES;
-    uint8_t* sRes = sOut + TILE_BYTES;
-    uint8_t* tail = sRes + (has_res ? TILE_BYTES : 0);
+    uint8_t* sOut = smem + PIPE_BYTES;           // [2][TILE_BYTES]
+    uint8_t* sRes = sOut + 2 * TILE_BYTES;       // [2][TILE_BYTES] when the layer has a residual
+    uint8_t* tail = sRes + (has_res ? 2 * TILE_BYTES : 0);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_full = empty_bar + STAGES;   // [2]
     uint64_t* acc_empty = acc_full + 2;        // [2]
-    uint64_t* res_full = acc_empty + 2;
-    uint64_t* res_empty = res_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 1);
+    uint64_t* res_full = acc_empty + 2;        // [2]
+    uint64_t* res_empty = res_full + 2;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -561,6 +568,7 @@ conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_const
     };
 
     if (threadIdx.x == 0) {
+        if (p.dbg) p.dbg[static_cast<size_t>(blockIdx.x) * 16] = clock64();
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapOut);
         if (has_res) tma_prefetch_desc(&mapRes);
@@ -571,9 +579,9 @@ conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_const
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
             mbar_init(&acc_empty[b], 1);
+            mbar_init(&res_full[b], 1);
+            mbar_init(&res_empty[b], 1);
         }
-        mbar_init(res_full, 1);
-        mbar_init(res_empty, 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -583,10 +591,18 @@ conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (p.pdl_trigger == 0) pdl_launch_dependents();
+    // optional phase accounting (debug aid, b2_context_debug_conv_timing): 16 int64 per CTA
+    //  0 start  1 roles begin  2 epilogue group 0 done  3 tiles of group 0   group 0, summed over its tiles: 4 wait accumulator
+    //  5 wait residual  6 wait own previous store + barrier A  7 TMEM -> regs -> smem  8 barrier B + store issue
+    //  9 MMA warp: wait accumulator free  10 MMA warp: wait operands  11 producer: wait residual buffer  12 producer: wait stage
+    //  13 MMA warp done
+    long long* const dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
     if (warp == 0) {
         // ================= activation producer =================
         pdl_wait();
+        long long w_stage = 0;
         int g = 0;   // global pipeline step counter of this CTA (across tiles)
         int lt = 0;  // local tile counter
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
@@ -602,19 +618,12 @@ conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
             const int base_w = q0 * p.stride_w - p.pad_w;
             const int base_h = p0 * p.stride_h - p.pad_h;
-            if (has_res) {  // residual tile of THIS tile: wait until the epilogue has consumed the previous one
-                mbar_wait(res_empty, (lt & 1) ^ 1);
-                if (elect_one_sync()) {
-                    mbar_expect_tx(res_full, TILE_BYTES);
-#pragma unroll
-                    for (int b = 0; b < NBOX; ++b) tma_load_2d(&mapRes, res_full, sRes + b * (128 * OROWB), n0 + b * OW, m0);
-                }
-                __syncwarp();
-            }
             int cur_cb = 0, cur_r = 0, cur_sx = 0;
             for (int i = 0; i < nsteps; ++i, ++g) {
                 const int s = g % STAGES;
+                const long long t1 = dbg ? clock64() : 0;
                 mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+                if (dbg) w_stage += clock64() - t1;
                 if (elect_one_sync()) {
                     const int ns = subs_in_step(i);
                     mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(ns * (A_SUBBLK + B_SUBBLK)));
@@ -637,6 +646,31 @@ conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 __syncwarp();
             }
         }
+        if (dbg && lane == 0) dbg[12] = w_stage;
+    } else if (warp == 3) {
+        // ================= residual producer: its waits never hold back the operand stream =================
+        if (has_res) {
+            pdl_wait();
+            long long w_res = 0;
+            int lt = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+                const int mt = tile / p.tiles_n;
+                const int nt = tile - mt * p.tiles_n;
+                const int m0 = mt * 128, n0 = nt * BN;
+                const int rb = lt & 1;  // buffer lt&1 is free once the epilogue of tile lt-2 has read it
+                const long long t0 = dbg ? clock64() : 0;
+                mbar_wait(&res_empty[rb], ((lt >> 1) & 1) ^ 1);
+                if (dbg) w_res += clock64() - t0;
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&res_full[rb], TILE_BYTES);
+#pragma unroll
+                    for (int b = 0; b < NBOX; ++b)
+                        tma_load_2d(&mapRes, &res_full[rb], sRes + rb * TILE_BYTES + b * (128 * OROWB), n0 + b * OW, m0);
+                }
+                __syncwarp();
+            }
+            if (dbg && lane == 0) dbg[11] = w_res;
+        }
     } else if (warp == 2) {
         // ================= weight producer (constants: no dependency wait) =================
         int g = 0;
@@ -658,14 +692,19 @@ conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_const
     } else if (warp == 1) {
         // ================= MMA issuer =================
         int g = 0, lt = 0;
+        long long w_acc = 0, w_ops = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
             const int b = lt & 1;
+            const long long t0 = dbg ? clock64() : 0;
             mbar_wait(&acc_empty[b], ((lt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+            if (dbg) w_acc += clock64() - t0;
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(b * BN);
             for (int i = 0; i < nsteps; ++i, ++g) {
                 const int s = g % STAGES;
+                const long long t1 = dbg ? clock64() : 0;
                 mbar_wait(&full_bar[s], (g / STAGES) & 1);
+                if (dbg) w_ops += clock64() - t1;
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + s * A_STAGE);
                 const uint32_t b_addr = smem_u32(sB + s * B_STAGE);
@@ -689,24 +728,36 @@ conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
         }
         if (p.pdl_trigger == 1) pdl_launch_dependents();
+        if (dbg && lane == 0) dbg[9] = w_acc, dbg[10] = w_ops, dbg[13] = clock64();
     } else if (warp >= 4) {
-        // ================= epilogue (4 warps = 128 threads, one accumulator row each) =================
+        // ================= epilogue: two groups of 4 warps (128 threads, one accumulator row each) =================
         pdl_wait();
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int grp = (warp - 4) >> 2;  // == accumulator / staging / residual buffer index == parity of the local tile
+        const int q = warp & 3;           // TMEM lane quadrant this warp may access
         const int row = q * 32 + lane;
-        const bool e0 = (threadIdx.x == 128);
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const bool e0 = (threadIdx.x == 128 + grp * 128);
+        uint8_t* const my_out = sOut + grp * TILE_BYTES;
+        const uint8_t* const my_res = sRes + grp * TILE_BYTES;
+        const uint32_t bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
+        int lt = grp;
+        const bool rec = dbg && e0 && grp == 0;
+        long long d_acc = 0, d_res = 0, d_a = 0, d_math = 0, d_b = 0, d_tiles = 0;
+        for (int tile = blockIdx.x + grp * static_cast<int>(gridDim.x); tile < num_tiles; tile += 2 * gridDim.x, lt += 2) {
             const int mt = tile / p.tiles_n;
             const int nt = tile - mt * p.tiles_n;
             const int m0 = mt * 128, n0 = nt * BN;
-            const int b = lt & 1;
-            mbar_wait(&acc_full[b], (lt >> 1) & 1);
+            const uint32_t par = (lt >> 1) & 1;
+            const long long c0 = rec ? clock64() : 0;
+            mbar_wait(&acc_full[grp], par);
             tc_fence_after();
-            if (has_res) mbar_wait(res_full, lt & 1);
-            // (A) the previous tile's TMA store has finished READING the staging tile (e0 waited before arriving)
-            named_bar_sync(1, 128);
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(b * BN);
+            const long long c1 = rec ? clock64() : 0;
+            if (has_res) mbar_wait(&res_full[grp], par);
+            const long long c2 = rec ? clock64() : 0;
+            // (A) this group's previous TMA store has finished READING the staging buffer
+            if (e0) tma_store_wait_read0();
+            named_bar_sync(bar_a, 128);
+            const long long c3 = rec ? clock64() : 0;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(grp * BN);
             const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0);
             constexpr int GP = NG >= 2 ? 2 : 1;
 #pragma unroll
@@ -734,7 +785,7 @@ conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         v[6] = __uint_as_float(acc[j][qq * 8 + 6]) + b1.z;
                         v[7] = __uint_as_float(acc[j][qq * 8 + 7]) + b1.w;
                         if (has_res) {
-                            const uint4 rv = *reinterpret_cast<const uint4*>(sRes + so);
+                            const uint4 rv = *reinterpret_cast<const uint4*>(my_res + so);
                             const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -751,22 +802,29 @@ conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-                        *reinterpret_cast<uint4*>(sOut + so) = o;
+                        *reinterpret_cast<uint4*>(my_out + so) = o;
                     }
                 }
             }
             tc_fence_before();
             fence_proxy_async();
-            // (B) every epilogue thread has drained its TMEM rows, read its residual row and staged its output row
-            named_bar_sync(2, 128);
+            const long long c4 = rec ? clock64() : 0;
+            // (B) every thread of the group has drained its TMEM rows, read its residual row and staged its output row
+            named_bar_sync(bar_b, 128);
             if (e0) {
-                mbar_arrive(&acc_empty[b]);        // accumulator b may be overwritten by tile lt+2
-                if (has_res) mbar_arrive(res_empty);  // residual buffer may be refilled
+                mbar_arrive(&acc_empty[grp]);              // the accumulator may be overwritten by tile lt+2
+                if (has_res) mbar_arrive(&res_empty[grp]);  // the residual buffer may be refilled
 #pragma unroll
-                for (int bx = 0; bx < NBOX; ++bx) tma_store_2d(&mapOut, sOut + bx * (128 * OROWB), n0 + bx * OW, m0);
-                tma_store_commit_and_wait_read();  // before (A) of the next tile lets anyone overwrite sOut
+                for (int bx = 0; bx < NBOX; ++bx) tma_store_2d(&mapOut, my_out + bx * (128 * OROWB), n0 + bx * OW, m0);
+                tma_store_commit();  // awaited at (A) of this group's next tile, or below before the CTA retires
+            }
+            if (rec) {
+                const long long c5 = clock64();
+                d_acc += c1 - c0, d_res += c2 - c1, d_a += c3 - c2, d_math += c4 - c3, d_b += c5 - c4, ++d_tiles;
             }
         }
+        if (e0) tma_store_wait_read0();  // shared memory must outlive the last bulk store's read
+        if (rec) dbg[2] = clock64(), dbg[3] = d_tiles, dbg[4] = d_acc, dbg[5] = d_res, dbg[6] = d_a, dbg[7] = d_math, dbg[8] = d_b;
     }
     tc_fence_before();
     __syncthreads();
@@ -1112,7 +1170,7 @@ int launch_conv_f16_tcgen05(const ConvLaunch& L, cudaStream_t stream) {
 template <int BN, int STAGES, int SPS>
 static int launch_one_ws(const ConvLaunch& L, cudaStream_t stream) {
     const size_t smem = size_t(conv_ws_smem_bytes(BN, STAGES, SPS, L.args.residual != nullptr));
-    return launch_kernel(conv_f16_tcgen05_ws<BN, STAGES, SPS>, dim3(L.ws_ctas), dim3(256), smem, stream, true, L.mapA, L.mapOut,
+    return launch_kernel(conv_f16_tcgen05_ws<BN, STAGES, SPS>, dim3(L.ws_ctas), dim3(384), smem, stream, true, L.mapA, L.mapOut,
                          L.mapRes, L.args);
 }
 
@@ -1266,13 +1324,14 @@ __global__ void input_cast_kernel(const S* __restrict__ src, T* __restrict__ dst
                                   int C_phys) {
     pdl_launch_dependents();
     pdl_wait();
-    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (idx >= static_cast<long long>(N) * HW) return;
-    const int n = static_cast<int>(idx / HW);
-    const int px = static_cast<int>(idx - static_cast<long long>(n) * HW);
-    const S* s = src + static_cast<size_t>(n) * C * HW + px;
-    T* d = dst + static_cast<size_t>(idx) * C_phys;
-    for (int c = 0; c < C_phys; ++c) d[c] = from_f<T>(c < C ? ld_in(s + static_cast<size_t>(c) * HW) : 0.0f);
+    const long long total = static_cast<long long>(N) * HW, step = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += step) {
+        const int n = static_cast<int>(idx / HW);
+        const int px = static_cast<int>(idx - static_cast<long long>(n) * HW);
+        const S* s = src + static_cast<size_t>(n) * C * HW + px;
+        T* d = dst + static_cast<size_t>(idx) * C_phys;
+        for (int c = 0; c < C_phys; ++c) d[c] = from_f<T>(c < C ? ld_in(s + static_cast<size_t>(c) * HW) : 0.0f);
+    }
 }
 
 // specialisation used by the fp16 path when C_phys == 8: one 16-byte store per pixel
@@ -1280,27 +1339,29 @@ template <typename S>
 __global__ void input_cast_c8_kernel(const S* __restrict__ src, uint4* __restrict__ dst, int N, int C, int HW) {
     pdl_launch_dependents();
     pdl_wait();
-    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (idx >= static_cast<long long>(N) * HW) return;
-    const int n = static_cast<int>(idx / HW);
-    const int px = static_cast<int>(idx - static_cast<long long>(n) * HW);
-    const S* s = src + static_cast<size_t>(n) * C * HW + px;
-    float f[8];
+    const long long total = static_cast<long long>(N) * HW, step = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += step) {
+        const int n = static_cast<int>(idx / HW);
+        const int px = static_cast<int>(idx - static_cast<long long>(n) * HW);
+        const S* s = src + static_cast<size_t>(n) * C * HW + px;
+        float f[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) f[c] = c < C ? ld_in(s + static_cast<size_t>(c) * HW) : 0.0f;
-    uint4 o;
-    __half2* o2 = reinterpret_cast<__half2*>(&o);
+        for (int c = 0; c < 8; ++c) f[c] = c < C ? ld_in(s + static_cast<size_t>(c) * HW) : 0.0f;
+        uint4 o;
+        __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-    dst[idx] = o;
+        for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+        dst[idx] = o;
+    }
 }
 
 template <typename S>
 static int launch_input_cast_t(const S* src, void* dst, int N, int C, int H, int W, int C_phys, bool half_storage,
-                               cudaStream_t stream) {
+                               int max_blocks, cudaStream_t stream) {
     const long long total = static_cast<long long>(N) * H * W;
     const int threads = 256;
-    const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+    unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+    if (max_blocks > 0 && blocks > static_cast<unsigned>(max_blocks)) blocks = static_cast<unsigned>(max_blocks);  // grid-stride
     if (half_storage && C_phys == 8 && C <= 8)
         B2_LAUNCH_RC = launch_kernel(input_cast_c8_kernel<S>, dim3(blocks), dim3(threads), 0, stream, false, src, reinterpret_cast<uint4*>(dst), N, C, H * W);
     else if (half_storage)
@@ -1310,9 +1371,9 @@ static int launch_input_cast_t(const S* src, void* dst, int N, int C, int H, int
     return B2_LAUNCH_RC;
 }
 int launch_input_cast(const void* src, bool src_half, void* dst, int N, int C, int H, int W, int C_phys, bool half_storage,
-                      cudaStream_t stream) {
-    if (src_half) return launch_input_cast_t(static_cast<const __half*>(src), dst, N, C, H, W, C_phys, half_storage, stream);
-    return launch_input_cast_t(static_cast<const float*>(src), dst, N, C, H, W, C_phys, half_storage, stream);
+                      int max_blocks, cudaStream_t stream) {
+    if (src_half) return launch_input_cast_t(static_cast<const __half*>(src), dst, N, C, H, W, C_phys, half_storage, max_blocks, stream);
+    return launch_input_cast_t(static_cast<const float*>(src), dst, N, C, H, W, C_phys, half_storage, max_blocks, stream);
 }
 
 // fp32 NCHW -> fp16 [N, H, pad_l + W/2 + pad_r, 8], channel = dw*4 + c: one 16-byte store per PAIR of input pixels;
@@ -1324,36 +1385,38 @@ __global__ void input_cast_s2d_kernel(const S* __restrict__ src, uint4* __restri
     pdl_wait();
     const int W2 = W >> 1;
     const int Wp = W2 + pad_l + pad_r;
-    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (idx >= static_cast<long long>(N) * H * Wp) return;
-    const int wp = static_cast<int>(idx % Wp);
-    const long long t = idx / Wp;
-    const int h = static_cast<int>(t % H);
-    const int n = static_cast<int>(t / H);
-    const int w2 = wp - pad_l;
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (w2 >= 0 && w2 < W2) {
-        const S* s = src + (static_cast<size_t>(n) * C * H + h) * W + 2 * w2;
-        float f[8];
+    const long long total = static_cast<long long>(N) * H * Wp, step = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += step) {
+        const int wp = static_cast<int>(idx % Wp);
+        const long long t = idx / Wp;
+        const int h = static_cast<int>(t % H);
+        const int n = static_cast<int>(t / H);
+        const int w2 = wp - pad_l;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (w2 >= 0 && w2 < W2) {
+            const S* s = src + (static_cast<size_t>(n) * C * H + h) * W + 2 * w2;
+            float f[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float2 v = make_float2(0.f, 0.f);
-            if (c < C) v = ld_in2(s + static_cast<size_t>(c) * H * W);
-            f[c] = v.x;
-            f[4 + c] = v.y;
+            for (int c = 0; c < 4; ++c) {
+                float2 v = make_float2(0.f, 0.f);
+                if (c < C) v = ld_in2(s + static_cast<size_t>(c) * H * W);
+                f[c] = v.x;
+                f[4 + c] = v.y;
+            }
+            __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
         }
-        __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+        dst[idx] = o;
     }
-    dst[idx] = o;
 }
 
 int launch_input_cast_s2d(const void* src, bool src_half, void* dst, int N, int C, int H, int W, int pad_l, int pad_r,
-                          cudaStream_t stream) {
+                          int max_blocks, cudaStream_t stream) {
     const long long total = static_cast<long long>(N) * H * (W / 2 + pad_l + pad_r);
     const int threads = 256;
-    const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+    unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+    if (max_blocks > 0 && blocks > static_cast<unsigned>(max_blocks)) blocks = static_cast<unsigned>(max_blocks);  // grid-stride
     if (src_half)
         B2_LAUNCH_RC = launch_kernel(input_cast_s2d_kernel<__half>, dim3(blocks), dim3(threads), 0, stream, false,
                                      static_cast<const __half*>(src), reinterpret_cast<uint4*>(dst), N, C, H, W, pad_l, pad_r);

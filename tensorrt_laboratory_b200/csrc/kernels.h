@@ -172,12 +172,14 @@ int launch_conv_simt(const SimtConvArgs& a, bool half_storage, cudaStream_t stre
 
 // fp32 NCHW binding -> NHWC activations (zero-filled channel padding)
 // (`src_half`: the binding holds fp16 instead of fp32 -- plans built with input_dtype="f16")
+// max_blocks > 0 caps the grid (the kernels are grid-stride loops): a cast that reads its source over PCIe (zero-copy
+// pinned input) lives for the length of the transfer and must not occupy every thread slot of the machine meanwhile
 int launch_input_cast(const void* src, bool src_half, void* dst, int N, int C, int H, int W, int C_phys,
-                      bool half_storage, cudaStream_t stream);
+                      bool half_storage, int max_blocks, cudaStream_t stream);
 // fp32 NCHW binding -> fp16 [N, H, pad_l + W/2 + pad_r, 8] with channel = dw*4 + c (horizontal space-to-depth, C <= 4;
 // border pixels zero)
 int launch_input_cast_s2d(const void* src, bool src_half, void* dst, int N, int C, int H, int W, int pad_l, int pad_r,
-                          cudaStream_t stream);
+                          int max_blocks, cudaStream_t stream);
 // NHWC activations -> fp32 NCHW binding
 int launch_output_cast(const void* src, float* dst, int N, int C, int H, int W, int C_phys,
                        bool half_storage, cudaStream_t stream);

@@ -245,7 +245,17 @@ void* Bindings::DeviceAddress(uint32_t binding_id) {
 }
 void** Bindings::DeviceAddresses() { return (void**)m_DeviceAddresses.data(); }
 
-void Bindings::CopyToDevice(uint32_t id) { CopyToDevice(id, HostAddress(id), BindingSize(id)); }  // bindings.cc:121-126
+void Bindings::CopyToDevice(uint32_t id) {  // bindings.cc:121-126
+    if (InferenceManager::ZeroCopyInput() && m_Model->GetBinding(id).isInput) {
+        // the pinned host buffer is mapped into the device's address space: the forward pass's first kernel (the input
+        // cast) reads it over PCIe itself -- the host->device transfer still happens inside the request, without the
+        // copy engine and without the HBM round trip of a staged copy
+        if (!m_StagedDevice.count(id)) m_StagedDevice[id] = m_DeviceAddresses[id];
+        m_DeviceAddresses[id] = HostAddress(id);
+        return;
+    }
+    CopyToDevice(id, HostAddress(id), BindingSize(id));
+}
 void Bindings::CopyToDevice(const std::vector<uint32_t>& ids) {
     for (auto id : ids) CopyToDevice(id);
 }
@@ -307,6 +317,9 @@ void ExecutionContext::Infer(const std::shared_ptr<Bindings>& bindings) {
 }
 double ExecutionContext::Synchronize() {
     TRT_CHECK_CUDA(cudaEventSynchronize(m_Done));
+    return ElapsedSeconds();
+}
+double ExecutionContext::ElapsedSeconds() const {
     float ms = 0.f;
     TRT_CHECK_CUDA(cudaEventElapsedTime(&ms, m_Start, m_Done));
     return double(ms) * 1e-3;
@@ -348,6 +361,20 @@ void InferenceManager::ActivateDevice() const {
     }
 }
 
+bool InferenceManager::ZeroCopyInput() {
+    static const bool v = [] {
+        const char* e = getenv("TRTLAB_ZERO_COPY_INPUT");
+        return e && atoi(e) != 0;
+    }();
+    return v;
+}
+bool InferenceManager::YieldingSync() {
+    static const bool v = [] {
+        const char* e = getenv("TRTLAB_SYNC");
+        return e && (!strcmp(e, "yield") || !strcmp(e, "userspace") || !strcmp(e, "poll"));
+    }();
+    return v;
+}
 void InferenceManager::RecordComputeTime(double seconds) {
     m_ComputeNs.fetch_add(uint64_t(seconds * 1e9), std::memory_order_relaxed);
     m_ComputeCount.fetch_add(1, std::memory_order_relaxed);
@@ -433,6 +460,10 @@ void InferenceManager::PrepareModel(const Model* model) {
         for (auto& ctx : held) {
             TRT_CHECK_B2(b2_context_set_device_memory(ctx->handle, m_Lanes[lane]->workspace));
             if (!getenv("B2_NET_CTAS")) b2_context_set_option(ctx->handle, "net_ctas", std::max(1, 296 / std::max(1, m_MaxExecutions)));
+            if (ZeroCopyInput() && !getenv("B2_INPUT_CTAS")) {  // a PCIe-paced cast must not hold every thread slot of the GPU
+                const char* v = getenv("TRTLAB_ZERO_COPY_CTAS");
+                b2_context_set_option(ctx->handle, "input_ctas", v ? atoi(v) : 74);
+            }
             for (int b = (mode == "max" || max_batch > 64) ? max_batch : 1; b <= max_batch; b++)
                 TRT_CHECK_B2(b2_context_prepare(ctx->handle, b, nullptr));
         }

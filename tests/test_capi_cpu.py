@@ -180,6 +180,16 @@ def test_cpp_core_unit_tests(tmp_path):
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stderr
 
 
+def test_cuda_sync_policies_against_a_fake_device(tmp_path):
+    """cuda_sync<standard_threads | userspace_threads> (include/trtlab/cuda/sync.h; reference trtlab/cuda/sync.h:13-62):
+    the polling flavour yields once per not-ready answer through the installable hook and throws on a device error."""
+    exe = tmp_path / "test_sync"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "test_sync.cc"), "-o", str(exe), "-lpthread"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "test_sync OK" in out.stdout, out.stderr
+
+
 def test_fp16_input_binding_is_recorded_in_the_plan():
     """Secondary mode of SURVEY.md 8(d): the input binding of an fp16 engine may be declared fp16."""
     import struct

@@ -237,3 +237,43 @@ def test_fused_tail_is_one_launch_and_bit_identical(gpu, rn50):
     out = helpers.run_engine(rn50["low"], rn50["x"][:2], builder.PREC_FP16, outputs=taps)
     assert helpers.rel_err(out["pool5"].reshape(2, -1), snaps["pool5"].reshape(2, -1)) <= 4e-3
     np.testing.assert_allclose(out["prob"], rn50["direct"][:2], rtol=0, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# process-level modes of the host pipeline: cuda_sync<userspace_threads> in the post stage, zero-copy input
+# ------------------------------------------------------------------------------------------------------------------
+_MODE_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from tensorrt_laboratory_b200 import builder, capi, weights
+blob = builder.build_resnet_plan(50, builder.PREC_FP16, 8, seed=0)
+x = weights.synthetic_input(8)
+mgr = capi.InferenceManager(max_exec_concurrency=2, max_copy_concurrency=4)
+mgr.register_model("rn50", blob)
+mgr.update_resources()
+outs = [mgr.infer("rn50", x[:b]) for b in (8, 3, 8, 1)]
+res, lats = mgr.bench("rn50", 8, seconds=30.0, max_batches=24)
+assert res["kBatchesComputed"] == 24
+np.savez(sys.argv[2], *outs)
+mgr.close()
+"""
+
+
+@pytest.mark.parametrize("mode", [{"TRTLAB_SYNC": "yield"}, {"TRTLAB_ZERO_COPY_INPUT": "1"},
+                                  {"TRTLAB_ZERO_COPY_INPUT": "1", "TRTLAB_ZERO_COPY_CTAS": "8", "TRTLAB_SYNC": "yield"}],
+                         ids=["yielding_sync", "zero_copy_input", "both_small_grid"])
+def test_pipeline_modes_change_no_bit(gpu, rn50, tmp_path, mode):
+    """TRTLAB_SYNC=yield (post stage polls through cuda_sync<userspace_threads>, reference trtlab/cuda/sync.h:16-48) and
+    TRTLAB_ZERO_COPY_INPUT=1 (the input cast reads the mapped pinned buffer over PCIe; CopyToDevice stages nothing) are
+    read once per process: run the manager pipeline in a child under each mode and compare with this process's direct path."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "out.npz"
+    env = dict(os.environ, **mode)
+    r = subprocess.run([sys.executable, "-c", _MODE_SCRIPT, root, str(out)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = np.load(out)
+    for arr, b in zip([got[k] for k in got.files], (8, 3, 8, 1)):
+        np.testing.assert_array_equal(arr, rn50["direct"][:b])
