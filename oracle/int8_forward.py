@@ -12,10 +12,10 @@ requantisation with round-half-to-even (the arithmetic of TensorRT's / ONNX's QL
 reference holds no INT8 golden vector in-tree; what this oracle pins is the repository's own scheme (quantize.py), and
 the accuracy claim is oracle-int8 vs oracle-fp32 on the synthetic inputs (tests/test_int8.py).
 
-Rounding contract (every ``fl`` is one IEEE fp32 operation, round-to-nearest-even; numpy float32 arithmetic):
+Rounding contract (every ``fl`` / ``fma`` is one IEEE fp32 operation, round-to-nearest-even):
     quantize   q = clip(rint(fl(h * inv_s)), -127, 127)                          h: the fp16 value as fp32
-    conv       t = fl(fl(float(acc) * m[c]) + b[c]);  t = fl(t + fl(float(q_res) * r));  t = max(t, 0);
-               q = clip(rint(t), -127, 127)
+    conv       t = fma(float(acc), m[c], b[c]);  t = fma(float(q_res), r, t);  t = max(t, 0);
+               q = clip(rint(t), -127, 127)            (fused multiply-adds: ``fma32`` below restates them exactly)
     avg pool   h = fp16(fl(float(sum q) * k))
     output     y = fl(float(q) * fl(s))                                          (INT8 tensor exposed as fp32 binding)
 """
@@ -32,15 +32,45 @@ from oracle.caffe_forward import _pool_out
 f32 = np.float32
 
 
+def fma32(a: np.ndarray, b: np.ndarray, c: np.ndarray) -> np.ndarray:
+    """IEEE fp32 fused multiply-add, round(a*b + c) with ONE rounding, for float32 arrays -- exact, not approximately:
+    the product of two 24-bit significands is exact in float64; the float64 sum p + c may round, so its error is recovered
+    with TwoSum, and the only case in which rounding the float64 sum to float32 differs from rounding the true value -- the
+    float64 sum lands exactly on a float32 tie while the true value is off the tie -- is resolved by the sign of that error."""
+    shape = np.broadcast_shapes(np.shape(a), np.shape(b), np.shape(c))
+    ta, tb, tc = (torch.broadcast_to(torch.from_numpy(np.array(v, dtype=np.float32)).double(), shape).reshape(-1)
+                  for v in (a, b, c))                # torch: the same IEEE float64 operations, on all host cores
+    p = ta * tb                                    # exact
+    s = p + tc                                     # rounded to float64
+    r = s.float()                                  # round-to-nearest-even of s
+    # a float64 is a float32 tie iff its low 29 significand bits are 1000...0 (float32-normal magnitudes); everything
+    # else -- subnormal float32 results, overflow -- goes through the generic neighbour comparison below
+    mag = s.abs()
+    normal = (mag >= 2.0 ** -126) & (mag < 2.0 ** 127)
+    suspect = (((s.view(torch.int64) & 0x1FFFFFFF) == 0x10000000) & normal) | (~normal & torch.isfinite(s) & (mag > 0))
+    out = r.numpy()
+    cand = torch.nonzero(suspect).reshape(-1).numpy()
+    if cand.size:
+        sc, pc, cc = s.numpy()[cand], p.numpy()[cand], tc.numpy()[cand]
+        bb = sc - pc
+        err = (pc - (sc - bb)) + (cc - bb)         # TwoSum: the true value is sc + err, exactly
+        rc = out[cand]
+        rc64 = rc.astype(np.float64)
+        other = np.where(rc64 > sc, np.nextafter(rc, np.float32(-np.inf)), np.nextafter(rc, np.float32(np.inf)))
+        o64 = other.astype(np.float64)
+        tie = (rc64 != sc) & (np.abs(rc64 - sc) == np.abs(o64 - sc)) & (err != 0)
+        flip = tie & (np.sign(err) == np.sign(o64 - sc))  # float() went to the even neighbour; the truth lies on err's side
+        out[cand[flip]] = other[flip]
+    return out.reshape(shape)
+
+
 def _requant(acc: np.ndarray, op: dict, res_q: Optional[np.ndarray]) -> np.ndarray:
     """acc [N, C, H, W] int64 (exact) -> int8 values as int32 array."""
-    m = op["m"].astype(f32).reshape(1, -1, 1, 1)
-    b = op["b"].astype(f32).reshape(1, -1, 1, 1)
-    t = acc.astype(f32)          # int -> fp32, round-to-nearest-even (|acc| can exceed 2^24)
-    t = t * m                    # fl(float(acc) * m[c])
-    t = t + b                    # fl(... + b[c])
+    m = np.broadcast_to(op["m"].astype(f32).reshape(1, -1, 1, 1), acc.shape)
+    b = np.broadcast_to(op["b"].astype(f32).reshape(1, -1, 1, 1), acc.shape)
+    t = fma32(acc.astype(f32), m, b)   # int -> fp32 rounds to nearest even (|acc| can exceed 2^24); fma(float(acc), m[c], b[c])
     if res_q is not None:
-        t = t + res_q.astype(f32) * f32(op["r"])
+        t = fma32(res_q.astype(f32), np.broadcast_to(f32(op["r"]), acc.shape), t)
     if op["relu"]:
         t = np.maximum(t, f32(0))
     return np.clip(np.rint(t), -127, 127).astype(np.int32)

@@ -3,8 +3,8 @@
 //
 //  * conv_i8_tcgen05<BN> -- implicit-GEMM convolution on the INT8 tensor path: TMA (tiled or im2col mode, 1-byte elements,
 //    one 128-byte swizzle row = 128 channels) -> tcgen05.mma.kind::i8 (UMMA 128 x BN x 32, s8 x s8 -> s32 in TMEM, exact)
-//    -> requantising epilogue in fp32 with explicit rounding steps (quantize.py: the CPU oracle reproduces it bit for bit)
-//        t = fl(fl(float(acc) * m[c]) + b[c]);  t = fl(t + fl(float(q_res) * r));  t = max(t, 0);  q = clip(rint(t), +-127)
+//    -> requantising epilogue in fp32, two fused multiply-adds (quantize.py: the CPU oracle reproduces it bit for bit)
+//        t = fma(float(acc), m[c], b[c]);  t = fma(float(q_res), r, t);  t = max(t, 0);  q = clip(rint(t), +-127)
 //    -> int8 -> 128-byte-swizzled staging tile -> TMA store.  Same warp roles as conv_f16_tcgen05 (warp 0 activation
 //    producer, warp 1 MMA issuer, warp 2 TMEM owner, warp 3 weight producer, all four = epilogue), PDL throughout.
 //  * quantize_h_to_i8_kernel -- fp16 NHWC -> int8 NHWC (channels zero-padded to the 128-channel rows of the INT8 layout)
@@ -215,8 +215,8 @@ conv_i8_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int c = col + i;
-                float t = __fadd_rn(__fmul_rn(__int2float_rn(static_cast<int>(acc[h * 16 + i])), s_m[c]), s_b[c]);
-                if (has_res) t = __fadd_rn(t, __fmul_rn(__int2float_rn(static_cast<int>(rq[i])), r));
+                float t = __fmaf_rn(__int2float_rn(static_cast<int>(acc[h * 16 + i])), s_m[c], s_b[c]);
+                if (has_res) t = __fmaf_rn(__int2float_rn(static_cast<int>(rq[i])), r, t);
                 q[i] = __float2int_rn(fmaxf(t, lo));  // > 127 (up to INT_MAX for huge t) saturates in the pack
             }
             uint4 o;

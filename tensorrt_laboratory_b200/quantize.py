@@ -5,9 +5,9 @@ scales to the engine builder).
 Scheme (what the INT8 kernels of this repository implement, bit for bit):
   * activations: symmetric per-tensor scale ``s = max|x| / 127`` from max-abs calibration over the calibration inputs;
   * weights: symmetric per-OUTPUT-CHANNEL scale ``s_w[c] = max|W[c]| / 127``, ``Wq = clip(rint(W / s_w), -127, 127)``;
-  * convolution: ``acc = sum(q_in * Wq)`` exact in int32; epilogue in fp32 with explicit rounding steps
-        t = fl(fl(float(acc) * m[c]) + b[c])          m[c] = fl(s_in * s_w[c] / s_out),  b[c] = fl(bias[c] / s_out)
-        t = fl(t + fl(float(q_res) * r))              r = fl(s_res / s_out)                      (fused residual)
+  * convolution: ``acc = sum(q_in * Wq)`` exact in int32; epilogue in fp32, two fused multiply-adds (one rounding each)
+        t = fma(float(acc), m[c], b[c])               m[c] = fl(s_in * s_w[c] / s_out),  b[c] = fl(bias[c] / s_out)
+        t = fma(float(q_res), r, t)                   r = fl(s_res / s_out)                      (fused residual)
         t = max(t, 0)                                                                           (fused ReLU)
         q_out = clip(rint(t), -127, 127)              round-half-even
   * the thin-input stem convolution, the max pool behind it, the classifier (FC) and the softmax stay fp16: a
