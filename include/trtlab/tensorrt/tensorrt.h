@@ -618,9 +618,11 @@ class BatchedInferRunner {
             release();
         };
         // every request carries one batch item, so "max requests per batch" == the model's max batch size
-        // a worker stays with its merged batch until the results are scattered: one per execution lane (+1 to overlap
-        // the host copies of the next batch) keeps every lane fed
-        if (workers == 0) workers = size_t(m_Resources->MaxExecConcurrency()) + 1;
+        // a worker stays with its merged batch until the results are scattered, and gathering 32 single-image requests
+        // into the pinned batch is ~2 ms of memcpy on one core -- as long as a forward pass takes on a lane.  One worker
+        // per pooled Buffers (never fewer than lanes + 1) lets every Buffers be in SOME stage: gather, H2D, forward, scatter.
+        if (workers == 0)
+            workers = std::max(size_t(m_Resources->MaxExecConcurrency()) + 1, size_t(m_Resources->MaxCopyConcurrency()));
         m_Dispatcher = std::make_unique<DispatcherType>(StandardBatcher<Request, standard_threads>(size_t(m_Model->GetMaxBatchSize())),
                                                         window, std::make_shared<ThreadPool>(workers),
                                                         std::make_shared<DeferredShortTaskPool>(), execute);

@@ -30,6 +30,11 @@ int trt_manager_infer(trt_manager* m, const char* model, int batch, const void* 
  * contiguous [n][item]; *batches_executed = number of merged forward passes it took */
 int trt_manager_infer_batched(trt_manager* m, const char* model, int n, const void* inputs, void* outputs, int window_us,
                               int* batches_executed);
+/* the same path as one flood of `n` single-image requests cycling through `ring` (ring_items images); *window_seconds spans
+ * the completions of requests [warm, n - cool) -- steady state, free of the pipeline's fill and drain; outputs: n items */
+int trt_manager_bench_batched(trt_manager* m, const char* model, int n, const void* ring, int ring_items, void* outputs,
+                              int window_us, int warm, int cool, double* window_seconds, double* total_seconds,
+                              int* batches_executed);
 /* Prometheus text exposition of the manager's metrics (request/compute summaries per model, load-ratio histogram,
  * GPU power gauge sampled now through NVML); returns the text length (excluding the NUL) or a negative B2_E* code;
  * at most cap-1 bytes are written */

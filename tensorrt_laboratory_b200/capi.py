@@ -93,6 +93,7 @@ SYMBOLS = [
     ("trt_manager_allocate", _I, [_VP]),
     ("trt_manager_infer", _I, [_VP, _S, _I, _VP, _SZ, _VP, _SZ, C.POINTER(_D)]),
     ("trt_manager_infer_batched", _I, [_VP, _S, _I, _VP, _VP, _I, C.POINTER(_I)]),
+    ("trt_manager_bench_batched", _I, [_VP, _S, _I, _VP, _I, _VP, _I, _I, _I, C.POINTER(_D), C.POINTER(_D), C.POINTER(_I)]),
     ("trt_manager_metrics_text", _I, [_VP, C.c_char_p, _SZ]),
     ("trt_manager_serve_metrics", _I, [_VP, _I, C.POINTER(_I)]),
     ("trt_manager_prefill_inputs", _I, [_VP, _S, _VP, _SZ]),
@@ -505,6 +506,18 @@ class InferenceManager:
         check(self._lib.trt_manager_infer_batched(self.handle, name.encode(), x.shape[0], x.ctypes.data, out.ctypes.data,
                                                   window_us, C.byref(nb)))
         return out, nb.value
+
+    def bench_batched(self, name: str, ring: np.ndarray, n: int, warm: int, cool: int, window_us: int = 2000):
+        """One flood of ``n`` single-image requests (inputs cycle through ``ring``) through BatchedInferRunner ->
+        (outputs [n, ...], seconds spanned by the completions of requests [warm, n - cool), total seconds, merged batches)."""
+        meta = self.models[name]
+        ring = np.ascontiguousarray(ring, dtype=[b["np_dtype"] for b in meta.bindings if b["is_input"]][0])
+        ob = [b for b in meta.bindings if not b["is_input"]][0]
+        out = np.empty((n,) + ob["shape"], dtype=np.float32)
+        win, tot, nb = _D(), _D(), _I(0)
+        check(self._lib.trt_manager_bench_batched(self.handle, name.encode(), n, ring.ctypes.data, ring.shape[0], out.ctypes.data,
+                                                  window_us, warm, cool, C.byref(win), C.byref(tot), C.byref(nb)))
+        return out, win.value, tot.value, nb.value
 
     def metrics_text(self) -> str:
         """Prometheus text exposition (request/compute summaries, load-ratio histogram, GPU power gauge)."""

@@ -122,6 +122,39 @@ int trt_manager_infer_batched(trt_manager* m, const char* model_name, int n, con
     TRT_CATCH
 }
 
+// The same path as one continuous flood of `n` single-image requests whose inputs cycle through `ring` (ring_items
+// images); *window_seconds spans the completions of requests [warm, n - cool): the batcher, every lane and every Buffers
+// are busy on both sides of the window, so the rate is free of the pipeline's fill and drain.
+int trt_manager_bench_batched(trt_manager* m, const char* model_name, int n, const void* ring, int ring_items, void* outputs,
+                              int window_us, int warm, int cool, double* window_seconds, double* total_seconds, int* batches_executed) {
+    if (!m || !model_name || n < 1 || !ring || ring_items < 1 || !outputs || warm < 0 || cool < 0 || warm + cool >= n || !window_seconds)
+        return fail(B2_EINVAL, "bad arguments");
+    TRT_TRY
+    auto model = m->mgr->GetModel(model_name);
+    const size_t in_item = model->GetBinding(model->GetInputBindingIds()[0]).bytesPerBatchItem;
+    const size_t out_item = model->GetBinding(model->GetOutputBindingIds()[0]).bytesPerBatchItem;
+    BatchedInferRunner runner(model, m->mgr, std::chrono::microseconds(window_us > 0 ? window_us : 2000));
+    std::vector<BatchedInferRunner::future_type> futures;
+    futures.reserve(size_t(n));
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n; ++i)
+        futures.push_back(runner.Infer(static_cast<const char*>(ring) + size_t(i % ring_items) * in_item,
+                                       static_cast<char*>(outputs) + size_t(i) * out_item));
+    std::chrono::steady_clock::time_point t_lo = t0, t_hi = t0;
+    for (int i = 0; i < n; ++i) {
+        futures[size_t(i)].get();
+        if (i == warm - 1) t_lo = std::chrono::steady_clock::now();  // request `warm` starts counting after its predecessor is out
+        if (i == n - cool - 1) t_hi = std::chrono::steady_clock::now();
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    runner.Shutdown();
+    *window_seconds = std::chrono::duration<double>(t_hi - t_lo).count();
+    if (total_seconds) *total_seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (batches_executed) *batches_executed = int(runner.BatchesExecuted());
+    return B2_OK;
+    TRT_CATCH
+}
+
 int trt_manager_metrics_text(trt_manager* m, char* buf, size_t cap) {
     if (!m || !buf || cap == 0) return -fail(B2_EINVAL, "bad arguments");
     try {
