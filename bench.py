@@ -379,6 +379,22 @@ def run_b200(args):
         "hbm_view": {"algorithmic_bytes_per_step": ALGO_BYTES_PER_STEP,
                      "achieved_gbs": ALGO_BYTES_PER_STEP / (ms_per_step * 1e-3) / 1e9, "peak_gbs": peak_hbm},
     }
+    try:
+        # every convolution against the roof that binds IT: the tensor peak, or -- for the wide short-K layers whose
+        # activations live in L2 -- the read / write bandwidth of L2 for unique streaming data (tensorrt_laboratory_b200/roofs.py)
+        from tensorrt_laboratory_b200 import graph, roofs, weights
+        net = graph.resnet_caffe(50)
+        floors = roofs.conv_floors(graph.lower(net, weights.random_weights(net, 0)), BATCH, peak_tf)
+        floor_us = sum(f["floor_us"] for f in floors)
+        roofline["per_layer_roofs"] = {
+            "floor_us_per_step": floor_us, "frac": floor_us / (conv_ms_per_step * 1e3),
+            "tensor_bound_layers": sum(f["roof"] == "tensor" for f in floors), "memory_bound_layers": sum(f["roof"] == "memory" for f in floors),
+            "tensor_floor_us": sum(f["tensor_floor_us"] for f in floors), "memory_floor_us": sum(f["memory_floor_us"] for f in floors),
+            "l2_read_tbs": roofs.L2_READ_BPS / 1e12, "l2_write_tbs": roofs.L2_WRITE_BPS / 1e12,
+            "source": "per layer max(2MNK / tensor peak, reads / L2 read bw + writes / L2 write bw); L2 figures: tools/micro/l2_stream.cu, "
+                      "profiles/l2_stream_r2.log; per-layer table: profiles/roofline_r2_saturated.md"}
+    except Exception as ex:  # an explanatory view must never take the line down
+        roofline["per_layer_roofs"] = {"error": f"{type(ex).__name__}: {ex}"}
 
     config2 = None
     if world == 1 and not args.no_config2:

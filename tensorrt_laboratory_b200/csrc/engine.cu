@@ -918,6 +918,7 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, int 
         if (!halo_cands.empty() && (c->force_halo > 0 || fixed_halo > 0)) candidates.clear();
         candidates.insert(candidates.end(), halo_cands.begin(), halo_cands.end());
     }
+    std::vector<std::pair<ConvConfig, double>> timed;
     for (const ConvConfig& cand : candidates) {
         {
             const int bn = cand.bn, st = cand.stages, sp = cand.splits;
@@ -967,12 +968,23 @@ int autotune_conv(b2_context* c, const Op& op, int batch, int fixed_splits, int 
             if (verbose > 1)
                 fprintf(stderr, "[b2 tune]   %s b=%d cand bn=%d st=%d sp=%d sps=%d ws=%d cn=%d halo=%d : %.3f us/launch\n", op.name.c_str(),
                         batch, cand.bn, cand.stages, cand.splits, cand.sps, cand.ws, cand.cn, cand.halo, ms * 1e3 / (iters * ns));
+            timed.push_back({cand, double(ms)});
             if (ms < best_ms) best_ms = ms, best = cand;
         }
         if (status) break;
     }
     cleanup();
     if (status) return status;
+    // B2_TUNE_TIE_PERMILLE = t > 0: among the one-tile tactics within t/1000 of the fastest, take the WIDEST N tile (fewest
+    // CTAs, least L2->SM traffic per MAC): with several copies of one layer the timing cannot see the SMs a wide tile
+    // leaves to the other contexts' layers.  0 (default) = fastest wins; measured neutral-to-negative, DESIGN.md.
+    const int tie = env_int("B2_TUNE_TIE_PERMILLE", 0);
+    if (tie > 0 && !best.ws && !best.halo && best.splits == 1) {
+        for (const auto& t : timed)
+            if (!t.first.ws && !t.first.halo && t.first.splits == 1 && t.first.cn == best.cn && t.second <= best_ms * (1.0 + tie / 1000.0) &&
+                (t.first.bn > best.bn || (t.first.bn == best.bn && t.second < best_ms)))
+                best = t.first, best_ms = std::min(best_ms, t.second);
+    }
     best.est_us = best_ms * 1e3 / (iters * ns);
     if (verbose)
         fprintf(stderr, "[b2 tune] %s b=%d M=%d N=%d K=%d best bn=%d st=%d sp=%d sps=%d ws=%d cn=%d halo=%d : %.3f us/launch (%d streams)\n",
