@@ -225,3 +225,18 @@ def test_prometheus_http_endpoint(lib):
         assert ei.value.code == 404
     finally:
         mgr.close()
+
+
+def test_per_layer_roofs_of_resnet50():
+    """roofs.conv_floors: pure shape arithmetic -- 53 convolutions at batch 8, FLOPs add up to the network's conv FLOPs, the
+    wide short-K layers with a residual are memory-bound and the 3x3 layers tensor-bound."""
+    from tensorrt_laboratory_b200 import graph, roofs, weights
+    net = graph.resnet_caffe(50)
+    fl = roofs.conv_floors(graph.lower(net, weights.random_weights(net, 0)), 8, 1429.0)
+    assert len(fl) == 53
+    by = {f["name"]: f for f in fl}
+    assert abs(sum(f["flops"] for f in fl) / 61.69e9 - 1) < 0.01
+    assert by["res2b_branch2c"]["roof"] == "memory" and by["res4b_branch2b"]["roof"] == "tensor"
+    assert abs(by["res2b_branch2c"]["read_bytes"] + by["res2b_branch2c"]["write_bytes"] - 28.9e6) < 0.2e6
+    assert all(f["floor_us"] == max(f["tensor_floor_us"], f["memory_floor_us"]) for f in fl)
+    assert 55 < sum(f["floor_us"] for f in fl) < 62
