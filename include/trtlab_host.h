@@ -51,6 +51,10 @@ int trt_manager_bench(trt_manager* m, const char* model, int batch, double secon
  * (pipeline full on both sides), latencies[] = those requests' latencies */
 int trt_manager_bench_window(trt_manager* m, const char* model, int batch, size_t warm, size_t steps, size_t cool,
                              double* window_seconds, double* latencies, size_t lat_cap, size_t* lat_count);
+/* ... `windows` back-to-back windows of `steps` completions each inside the same loop (window_seconds[windows]): a single
+ * scheduling hiccup then costs one window, not the measurement; latencies[] covers all windows */
+int trt_manager_bench_windows(trt_manager* m, const char* model, int batch, size_t warm, size_t steps, size_t windows, size_t cool,
+                              double* window_seconds, double* latencies, size_t lat_cap, size_t* lat_count);
 /* TimedBenchmarkWorkspace::enqueue_pipeline averaged over iters */
 int trt_timed_pipeline(const void* blob, size_t nbytes, int iters, float* h2d_ms, float* compute_ms, float* d2h_ms);
 /* v2 surface: BenchmarkWorkspace (caller-captured graph of the forward pass, reference workspace.cc:21-124) at max batch:

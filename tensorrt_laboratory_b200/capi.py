@@ -99,6 +99,7 @@ SYMBOLS = [
     ("trt_manager_prefill_inputs", _I, [_VP, _S, _VP, _SZ]),
     ("trt_manager_bench", _I, [_VP, _S, _I, _D, _SZ, C.POINTER(_D), C.POINTER(_D), _SZ, C.POINTER(_SZ)]),
     ("trt_manager_bench_window", _I, [_VP, _S, _I, _SZ, _SZ, _SZ, C.POINTER(_D), C.POINTER(_D), _SZ, C.POINTER(_SZ)]),
+    ("trt_manager_bench_windows", _I, [_VP, _S, _I, _SZ, _SZ, _SZ, _SZ, C.POINTER(_D), C.POINTER(_D), _SZ, C.POINTER(_SZ)]),
     ("trt_timed_pipeline", _I, [_VP, _SZ, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("trt_device_throughput", _I, [_VP, _SZ, _I, _I, _I, _I, _VP, _I, C.POINTER(_D), C.POINTER(_I)]),
     ("trt_workspace_infer", _I, [_VP, _SZ, _VP, _SZ, _VP, _SZ, _I, _I]),
@@ -555,6 +556,16 @@ class InferenceManager:
         n = _SZ()
         check(self._lib.trt_manager_bench_window(self.handle, name.encode(), batch, warm, steps, cool, C.byref(win), lat, steps, C.byref(n)))
         return win.value, np.array(lat[: n.value])
+
+    def bench_windows(self, name: str, batch: int, warm: int, steps: int, windows: int, cool: int):
+        """One continuous closed loop of warm + windows * steps + cool requests; -> (seconds spanned by each of the `windows`
+        consecutive groups of `steps` completions [windows], latencies of all their requests)."""
+        win = (C.c_double * windows)()
+        lat = (C.c_double * (steps * windows))()
+        n = _SZ()
+        check(self._lib.trt_manager_bench_windows(self.handle, name.encode(), batch, warm, steps, windows, cool, win, lat,
+                                                  steps * windows, C.byref(n)))
+        return np.array(win[:]), np.array(lat[: n.value])
 
     def close(self):
         if self.handle and self.handle.value:

@@ -226,26 +226,34 @@ int trt_manager_bench(trt_manager* m, const char* model_name, int batch, double 
 // middle: *window_seconds = time from the warm-th completion to the (warm + steps)-th, latencies[] = those requests'
 // latencies.  The pipeline (8 Buffers, 4 lanes) is full on both sides of the window, so a short window measures the
 // steady state instead of the fill / drain transients a bracketed run of the same length is dominated by.
-int trt_manager_bench_window(trt_manager* m, const char* model_name, int batch, size_t warm, size_t steps, size_t cool,
-                             double* window_seconds, double* latencies, size_t lat_cap, size_t* lat_count) {
-    if (!m || !model_name || !window_seconds || steps < 1) return fail(B2_EINVAL, "bad arguments");
+int trt_manager_bench_windows(trt_manager* m, const char* model_name, int batch, size_t warm, size_t steps, size_t windows, size_t cool,
+                              double* window_seconds, double* latencies, size_t lat_cap, size_t* lat_count) {
+    if (!m || !model_name || !window_seconds || steps < 1 || windows < 1) return fail(B2_EINVAL, "bad arguments");
     TRT_TRY
     auto model = m->mgr->GetModel(model_name);
     InferBench bench(m->mgr);
     std::vector<double> lat, done;
     InferBench::ModelsList models = {model};
-    bench.Run(models, uint32_t(batch), 3600.0, warm + steps + cool, &lat, &done);
-    if (done.size() != warm + steps + cool) return fail(B2_EINVAL, "bench loop ended early (%zu of %zu requests)", done.size(), warm + steps + cool);
+    const size_t total = warm + steps * windows + cool;
+    bench.Run(models, uint32_t(batch), 3600.0, total, &lat, &done);
+    if (done.size() != total) return fail(B2_EINVAL, "bench loop ended early (%zu of %zu requests)", done.size(), total);
     std::vector<size_t> order(done.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = i;
     std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return done[a] < done[b]; });
-    const double t_begin = warm ? done[order[warm - 1]] : 0.0;
-    *window_seconds = done[order[warm + steps - 1]] - t_begin;
+    for (size_t w = 0; w < windows; ++w) {  // window w = completions warm + w*steps + 1 .. warm + (w+1)*steps
+        const size_t first = warm + w * steps;
+        const double t_begin = first ? done[order[first - 1]] : 0.0;
+        window_seconds[w] = done[order[first + steps - 1]] - t_begin;
+    }
     size_t n = 0;
-    for (size_t k = warm; k < warm + steps && latencies && n < lat_cap; ++k) latencies[n++] = lat[order[k]];
+    for (size_t k = warm; k < warm + steps * windows && latencies && n < lat_cap; ++k) latencies[n++] = lat[order[k]];
     if (lat_count) *lat_count = n;
     return B2_OK;
     TRT_CATCH
+}
+int trt_manager_bench_window(trt_manager* m, const char* model_name, int batch, size_t warm, size_t steps, size_t cool,
+                             double* window_seconds, double* latencies, size_t lat_cap, size_t* lat_count) {
+    return trt_manager_bench_windows(m, model_name, batch, warm, steps, 1, cool, window_seconds, latencies, lat_cap, lat_count);
 }
 
 // H2D / compute / D2H breakdown of the v2 single-stream pipeline (TimedBenchmarkWorkspace)
