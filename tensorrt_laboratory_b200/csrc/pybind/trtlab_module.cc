@@ -5,8 +5,9 @@
 //     mnist  = models.register_tensorrt_engine("mnist", "mnist.plan")      # a B2ENGINE plan instead of a TensorRT one
 //     models.update_resources()
 //     results = [mnist.infer(Input3=x) for x in inputs];  results = [r.get() for r in results]
-// (examples/30_PyTensorRT/server.py:19-31).  Not provided: serve() / RemoteInferenceManager -- they speak the TRTIS gRPC
-// protocol, which needs gRPC C++ (the grpcio service of tensorrt_laboratory_b200/rpc.py covers the RPC roles).
+// (examples/30_PyTensorRT/server.py:19-31).  serve() and RemoteInferenceManager speak the TRTIS gRPC protocol, which is
+// C++ over nvrpc / gRPC C++ in the reference (infer.cc:124-260, 430-642); gRPC C++ is not in this image, so both delegate to
+// the grpcio restatement of that protocol in tensorrt_laboratory_b200/trtis.py (same wire format, same Python-visible API).
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -156,7 +157,6 @@ class PyInferenceManager : public InferenceManager {
         });
         return out;
     }
-    void Serve(int) { throw std::runtime_error("serve(): the TRTIS gRPC front end needs gRPC C++; see tensorrt_laboratory_b200/rpc.py"); }
 };
 
 }  // namespace
@@ -171,7 +171,15 @@ PYBIND11_MODULE(trtlab, m) {
         .def("infer_runner", &PyInferenceManager::MakeRunner)
         .def("get_models", &PyInferenceManager::Models)
         .def("metrics_text", [](PyInferenceManager& self) { return self.GetMetrics().Expose(); })
-        .def("serve", &PyInferenceManager::Serve, py::arg("port") = 50052);
+        // infer.cc:411-417: TRTIS GRPCService (Status / Health / Infer) in front of this manager; blocks like the reference's
+        // server.Run() unless block=False, in which case the running server object is returned (shutdown() stops it)
+        .def("serve", [](std::shared_ptr<PyInferenceManager> self, int port, bool block) {
+            return py::module_::import("tensorrt_laboratory_b200.trtis").attr("serve_pybind")(self, port, block);
+        }, py::arg("port") = 50052, py::arg("block") = true);
+    // infer.cc:547-642: client of a served manager; get_models() / infer_runner(name).infer(**inputs).get()
+    m.def("RemoteInferenceManager", [](const std::string& hostname) {
+        return py::module_::import("tensorrt_laboratory_b200.trtis").attr("RemoteInferenceManager")(hostname);
+    }, py::arg("hostname") = "localhost:50052");
     py::class_<PyInferRunner, std::shared_ptr<PyInferRunner>>(m, "InferRunner")
         .def("infer", &PyInferRunner::Infer)
         .def("input_bindings", &PyInferRunner::InputBindings)

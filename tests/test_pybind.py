@@ -20,7 +20,7 @@ def _module():
 
 def test_module_surface_matches_the_reference():
     trtlab = _module()
-    assert {"InferenceManager", "InferRunner", "InferFuture"} <= set(dir(trtlab))
+    assert {"InferenceManager", "InferRunner", "InferFuture", "RemoteInferenceManager"} <= set(dir(trtlab))
     mgr = trtlab.InferenceManager(max_exec_concurrency=2)  # keywords of infer.cc:686-688
     for name in ("register_tensorrt_engine", "update_resources", "infer_runner", "get_models", "serve"):
         assert hasattr(mgr, name)
@@ -30,8 +30,13 @@ def test_module_surface_matches_the_reference():
     assert mgr.get_models() == {}
     with pytest.raises(RuntimeError):  # missing engine file: std::runtime_error, as runtime.cc:83-86
         mgr.register_tensorrt_engine("nope", "/nonexistent/engine.plan")
-    with pytest.raises(RuntimeError):
-        mgr.serve()
+    srv = mgr.serve(port=0, block=False)     # TRTIS GRPCService in front of the manager (grpcio restatement, trtis.py)
+    try:
+        remote = trtlab.RemoteInferenceManager(hostname=f"127.0.0.1:{srv.port}")
+        assert remote.is_healthy() and remote.get_models() == []   # nothing registered yet
+        remote.close()
+    finally:
+        srv.shutdown()
 
 
 @pytest.mark.gpu
@@ -65,3 +70,35 @@ def test_mnist_known_answer_through_the_python_surface(gpu, tmp_path):
     del futs[::2]
     for i, f in zip(range(1, 24, 2), futs):
         assert int(f.get()[list(outs)[0]].argmax()) == (2, 0, 9)[i % 3]
+
+
+@pytest.mark.gpu
+def test_serve_and_remote_inference_manager_replay_the_golden_vectors(gpu, tmp_path):
+    """examples/30_PyTensorRT: server.py serves the manager (`models.serve()`), client.py reaches it through
+    `trtlab.RemoteInferenceManager(hostname=...)`, `get_models()`, `infer_runner("mnist").infer(Input3=x).get()` -- here over
+    the TRTIS GRPCService protocol on a loopback port, against the reference's golden vectors."""
+    from tensorrt_laboratory_b200 import builder, graph
+    trtlab = _module()
+    net, w, xs, ys = helpers.load_mnist_golden()
+    plan = tmp_path / "mnist-v1.3.plan"
+    plan.write_bytes(builder.build_plan(graph.lower(net, w), builder.PREC_FP32, 1))
+    models = trtlab.InferenceManager(max_exec_concurrency=2)
+    local = models.register_tensorrt_engine("mnist", str(plan))
+    models.update_resources()
+    srv = models.serve(port=0, block=False)
+    try:
+        remote = trtlab.RemoteInferenceManager(hostname=f"127.0.0.1:{srv.port}")
+        assert remote.get_models() == ["mnist"]
+        mnist = remote.infer_runner("mnist")
+        assert mnist.input_bindings() == {"Input3": {"shape": [1, 28, 28], "dtype": np.dtype(np.float32)}}
+        assert mnist.max_batch_size() == 1
+        futures = [mnist.infer(Input3=x) for x in xs]
+        for f, x, e, want in zip(futures, xs, ys, (2, 0, 9)):
+            (val,) = f.get().values()
+            np.testing.assert_almost_equal(val.reshape((1, 10)), e.reshape((1, 10)), decimal=3)
+            assert int(val.argmax()) == want
+            (direct,) = local.infer(Input3=x).get().values()
+            np.testing.assert_array_equal(val.reshape(-1), np.asarray(direct).reshape(-1))   # the wire changes no bit
+        remote.close()
+    finally:
+        srv.shutdown()
