@@ -5,8 +5,11 @@ executor,context}.h; examples/01_Basic_GRPC/src/server.cpp:89-181; examples/02_T
 gRPC C++ and protoc are not in this image; grpcio (Python) and the protobuf runtime are, so the same roles are
 restated here in Python over grpcio:
 
-  Server / AsyncService / register_rpc / Executor / Context.execute_rpc / Resources      <- nvrpc
+  Server / AsyncService / register_rpc / Executor / Context.execute_rpc / Resources      <- nvrpc (unary life cycle)
+  BatchingContext.execute_rpc(requests, responses)   all-in / all-out on one stream      <- nvrpc/life_cycle_batching.h
+  StreamingContext.request_received(request, stream) + ServerStream                      <- nvrpc/life_cycle_streaming.h
   ClientUnary.enqueue(request, on_complete, headers) -> future                          <- nvrpc/client/client_unary.h
+  ClientStreaming.write(request) / done() -> future of the status                       <- nvrpc/client/client_streaming.h
   simple.Inference/Compute  (Input{batch_id, raw_bytes|sysv} -> Output{batch_id})        <- examples/11_Protos/echo/echo.proto
   ssd.Inference/Compute     (BatchInput -> BatchPredictions)                             <- examples/11_Protos/demo/inference.proto
 
@@ -51,6 +54,18 @@ def _build_pool():
     _field(m, "batch_id", 1, _F.TYPE_UINT64)
     _field(m, "raw_bytes", 2, _F.TYPE_BYTES, oneof=0)
     _field(m, "sysv", 3, _F.TYPE_MESSAGE, type_name=".simple.SystemV", oneof=0)
+    m = fd.message_type.add(name="Output")
+    _field(m, "batch_id", 1, _F.TYPE_UINT64)
+    pool.Add(fd)
+    # ---- package nvrpc.testing (trtlab/nvrpc/tests/testing.proto: TestService{Unary, Streaming}) ----
+    fd = descriptor_pb2.FileDescriptorProto(name="b2/nvrpc_testing.proto", package="nvrpc.testing", syntax="proto3")
+    m = fd.message_type.add(name="SystemV")
+    _field(m, "shm_id", 1, _F.TYPE_UINT64), _field(m, "offset", 2, _F.TYPE_UINT64), _field(m, "size", 3, _F.TYPE_UINT64)
+    m = fd.message_type.add(name="Input")
+    m.oneof_decl.add(name="data")
+    _field(m, "batch_id", 1, _F.TYPE_UINT64)
+    _field(m, "raw_bytes", 2, _F.TYPE_BYTES, oneof=0)
+    _field(m, "sysv", 3, _F.TYPE_MESSAGE, type_name=".nvrpc.testing.SystemV", oneof=0)
     m = fd.message_type.add(name="Output")
     _field(m, "batch_id", 1, _F.TYPE_UINT64)
     pool.Add(fd)
@@ -101,6 +116,78 @@ class Context:
         raise NotImplementedError
 
 
+class BatchingContext(Context):
+    """All-in, then all-out batching on one bidirectional stream (nvrpc LifeCycleBatching, life_cycle_batching.h:64-255): the
+    client writes requests until it half-closes, ``execute_rpc(requests, responses)`` then runs ONCE on all of them and must
+    append exactly one response per request; they go back on the stream in request order.  ``on_request_received`` is the
+    per-message hook (called as each request arrives, before the batch runs)."""
+
+    life_cycle = "batching"
+
+    def on_request_received(self, request) -> None:
+        pass
+
+    def execute_rpc(self, requests, responses) -> None:  # pragma: no cover - interface
+        raise NotImplementedError
+
+
+class ServerStream:
+    """Write side of a streaming RPC handed to the context's callbacks (LifeCycleStreaming::ServerStream,
+    life_cycle_streaming.h:80-170).  May be kept and written from any thread until finished or cancelled."""
+
+    _FINISH, _CANCEL = object(), object()
+
+    def __init__(self):
+        self._out: "queue.Queue" = queue.Queue()
+        self._lock = threading.Lock()
+        self._open = True
+
+    def is_connected(self) -> bool:
+        return self._open
+
+    def write_response(self, response) -> bool:
+        with self._lock:
+            if not self._open:
+                return False
+            self._out.put(response)
+            return True
+
+    def finish_stream(self) -> bool:
+        with self._lock:
+            if not self._open:
+                return False
+            self._open = False
+            self._out.put(self._FINISH)
+            return True
+
+    def cancel_stream(self) -> bool:
+        with self._lock:
+            if not self._open:
+                return False
+            self._open = False
+            self._out.put(self._CANCEL)
+            return True
+
+
+class StreamingContext(Context):
+    """Bidirectional streaming (nvrpc LifeCycleStreaming, life_cycle_streaming.h:40-420): ``request_received(request, stream)``
+    for every message of the client, with ``stream_initialized`` before the first and ``requests_finished`` after the client
+    half-closes; responses are written through the ``ServerStream`` at any time -- zero, one or many per request -- and the
+    RPC ends when the context calls ``finish_stream()`` (OK) or ``cancel_stream()`` (CANCELLED).  A context that has not
+    ended the stream by the time ``requests_finished`` returns is finished for it (the reference warns and cancels)."""
+
+    life_cycle = "streaming"
+
+    def stream_initialized(self, stream: ServerStream) -> None:
+        pass
+
+    def request_received(self, request, stream: ServerStream) -> None:  # pragma: no cover - interface
+        raise NotImplementedError
+
+    def requests_finished(self, stream: ServerStream) -> None:
+        pass
+
+
 class RPC:
     def __init__(self, service: "AsyncService", method: str, request_cls, response_cls, context_cls):
         self.service, self.method = service, method
@@ -120,6 +207,62 @@ class RPC:
         finally:
             self.contexts.put(ctx)
 
+    def _handle_batching(self, request_iterator, grpc_ctx):
+        if self.contexts is None:
+            grpc_ctx.abort(grpc.StatusCode.UNAVAILABLE, "no execution contexts registered for " + self.method)
+        ctx = self.contexts.get()
+        try:
+            ctx.metadata = {k: v for k, v in grpc_ctx.invocation_metadata()}
+            requests = []
+            for request in request_iterator:  # ends when the client half-closes (WritesDone)
+                ctx.on_request_received(request)
+                requests.append(request)
+            responses = []
+            ctx.execute_rpc(requests, responses)
+            if len(responses) != len(requests):
+                grpc_ctx.abort(grpc.StatusCode.INTERNAL, f"{self.method}: {len(responses)} responses for {len(requests)} requests")
+            for response in responses:
+                yield response
+        finally:
+            self.contexts.put(ctx)
+
+    def _handle_streaming(self, request_iterator, grpc_ctx):
+        if self.contexts is None:
+            grpc_ctx.abort(grpc.StatusCode.UNAVAILABLE, "no execution contexts registered for " + self.method)
+        ctx = self.contexts.get()
+        stream = ServerStream()
+        failure = []
+
+        def reader():  # the client's messages arrive on their own thread so that responses can flow meanwhile
+            try:
+                ctx.stream_initialized(stream)
+                for request in request_iterator:
+                    if not stream.is_connected():
+                        break  # finished or cancelled early: further requests are dropped, as the reference does
+                    ctx.request_received(request, stream)
+                ctx.requests_finished(stream)
+                stream.finish_stream()  # no-op when the context already ended the stream
+            except Exception as exc:  # a failing callback ends the RPC with an error instead of hanging it
+                failure.append(exc)
+                stream.cancel_stream()
+
+        try:
+            ctx.metadata = {k: v for k, v in grpc_ctx.invocation_metadata()}
+            t = threading.Thread(target=reader, daemon=True)
+            t.start()
+            while True:
+                item = stream._out.get()
+                if item is ServerStream._FINISH:
+                    break
+                if item is ServerStream._CANCEL:
+                    if failure:
+                        grpc_ctx.abort(grpc.StatusCode.INTERNAL, f"{type(failure[0]).__name__}: {failure[0]}")
+                    grpc_ctx.abort(grpc.StatusCode.CANCELLED, "stream cancelled by the service")
+                yield item
+        finally:
+            stream._open = False
+            self.contexts.put(ctx)
+
 
 class AsyncService:
     def __init__(self, name: str):
@@ -132,10 +275,18 @@ class AsyncService:
         return rpc
 
     def _generic_handler(self):
-        handlers = {
-            name: grpc.unary_unary_rpc_method_handler(rpc._handle, request_deserializer=rpc.request_cls.FromString,
-                                                      response_serializer=lambda m: m.SerializeToString())
-            for name, rpc in self.rpcs.items()}
+        handlers = {}
+        for name, rpc in self.rpcs.items():
+            kind = getattr(rpc.context_cls, "life_cycle", "unary")  # the context class names its life cycle, as in nvrpc
+            kw = dict(request_deserializer=rpc.request_cls.FromString, response_serializer=lambda m: m.SerializeToString())
+            if kind == "unary":
+                handlers[name] = grpc.unary_unary_rpc_method_handler(rpc._handle, **kw)
+            elif kind == "batching":
+                handlers[name] = grpc.stream_stream_rpc_method_handler(rpc._handle_batching, **kw)
+            elif kind == "streaming":
+                handlers[name] = grpc.stream_stream_rpc_method_handler(rpc._handle_streaming, **kw)
+            else:
+                raise ValueError(f"unknown life cycle '{kind}' on {rpc.context_cls.__name__}")
         return grpc.method_handlers_generic_handler(self.name, handlers)
 
 
@@ -217,6 +368,60 @@ class ClientUnary:
         return result
 
     def close(self):
+        self._channel.close()
+
+
+class ClientStreaming:
+    """Bidirectional streaming client (nvrpc/client/client_streaming.h): ``write(request)`` any number of times, ``done()``
+    half-closes and returns a future of the final ``grpc.StatusCode``; every response is handed to ``on_response`` on the
+    reader thread (and collected in ``responses`` when no callback is given)."""
+
+    def __init__(self, target: str, method: str, request_cls, response_cls, on_response: Optional[Callable] = None,
+                 headers: Optional[Dict[str, str]] = None):
+        self._channel = grpc.insecure_channel(target, options=[("grpc.max_receive_message_length", 64 << 20),
+                                                                ("grpc.max_send_message_length", 64 << 20)])
+        self._requests: "queue.Queue" = queue.Queue()
+        self.responses = []
+        self._status: "futures.Future" = futures.Future()
+        call = self._channel.stream_stream(method, request_serializer=lambda m: m.SerializeToString(),
+                                           response_deserializer=response_cls.FromString)
+
+        def feed():
+            while True:
+                item = self._requests.get()
+                if item is None:
+                    return
+                yield item
+
+        self._call = call(feed(), metadata=tuple((headers or {}).items()))
+
+        def reader():
+            try:
+                for response in self._call:
+                    (on_response or self.responses.append)(response)
+                self._status.set_result(grpc.StatusCode.OK)
+            except grpc.RpcError as e:
+                self._status.set_result(e.code())
+
+        self._reader = threading.Thread(target=reader, daemon=True)
+        self._reader.start()
+        self._closed = False
+
+    def write(self, request) -> bool:
+        if self._closed:
+            return False
+        self._requests.put(request)
+        return True
+
+    def done(self) -> "futures.Future":
+        if not self._closed:
+            self._closed = True
+            self._requests.put(None)
+        return self._status
+
+    def close(self):
+        self.done()
+        self._reader.join(timeout=5)
         self._channel.close()
 
 
@@ -323,6 +528,50 @@ class InferenceContext(Context):
         response.compute_time = float(compute_s)  # device time of the forward pass, as server.cc:169 (ctx->Synchronize())
 
 
+class BatchedInferenceContext(BatchingContext):
+    """ssd.Inference/BatchedCompute -- the batching life cycle on the inference path: every message of the stream is one
+    request (its own ``batch_size`` images), the whole stream is merged into as few forward passes as the model's max batch
+    allows (requests are never split), and each request gets its own BatchPredictions back, in order."""
+
+    def execute_rpc(self, requests, responses):
+        t0 = time.perf_counter()
+        res: InferenceResources = self.get_resources()
+        b = res.in_binding
+        item = int(np.prod(b["shape"]))
+        tensors = []
+        for r in requests:
+            n = int(r.batch_size)
+            x = np.frombuffer(r.data, dtype=b["np_dtype"])
+            if n < 1 or n > res.max_batch or x.size != n * item:
+                raise ValueError(f"request {r.batch_id}: batch_size {n} / {x.size} elements do not fit the input binding")
+            tensors.append(x.reshape((n,) + b["shape"]))
+        groups, cur, cur_n = [], [], 0          # greedy, order-preserving packing into forward passes
+        for i, x in enumerate(tensors):
+            if cur and cur_n + x.shape[0] > res.max_batch:
+                groups.append(cur)
+                cur, cur_n = [], 0
+            cur.append(i)
+            cur_n += x.shape[0]
+        if cur:
+            groups.append(cur)
+        probs, compute = [None] * len(tensors), [0.0] * len(tensors)
+        for g in groups:
+            y, sec = res.manager.infer_timed(res.model_name, np.concatenate([tensors[i] for i in g], 0))
+            at = 0
+            for i in g:
+                n = tensors[i].shape[0]
+                probs[i], compute[i] = y[at:at + n].reshape(n, -1), sec
+                at += n
+        self.forward_passes = len(groups)
+        for r, prob, sec in zip(requests, probs, compute):
+            out = message("ssd.BatchPredictions")()
+            for row in prob:
+                p = out.elements.add().predictions.add()
+                p.class_id, p.score = int(row.argmax()), float(row.max())
+            out.batch_id, out.compute_time, out.total_time = r.batch_id, float(sec), float(time.perf_counter() - t0)
+            responses.append(out)
+
+
 def build_echo_server(address: str = "127.0.0.1:0", contexts: int = 10, executor_threads: int = 4,
                       resources: Optional[EchoResources] = None) -> Server:
     """The reference's simpleServer (examples/01_Basic_GRPC/src/server.cpp:137-181)."""
@@ -339,8 +588,11 @@ def build_inference_server(manager, model_name: str, address: str = "127.0.0.1:0
     server = Server(address)
     svc = server.register_async_service("ssd.Inference")
     rpc = svc.register_rpc("Compute", message("ssd.BatchInput"), message("ssd.BatchPredictions"), InferenceContext)
+    batched = svc.register_rpc("BatchedCompute", message("ssd.BatchInput"), message("ssd.BatchPredictions"), BatchedInferenceContext)
     executor = server.register_executor(Executor(executor_threads))
-    executor.register_contexts(rpc, InferenceResources(manager, model_name), contexts)
+    resources = InferenceResources(manager, model_name)
+    executor.register_contexts(rpc, resources, contexts)
+    executor.register_contexts(batched, resources, max(1, contexts // 2))
     return server
 
 

@@ -1,6 +1,7 @@
 """nvrpc-role unary service (BASELINE.json configs[0]: unary echo + host pinned-pool round trip; runs without a GPU).
 Cases follow trtlab/nvrpc/tests/test_pingpong.cc:182-228 (UnaryTest)."""
 import threading
+import time
 
 import grpc
 import numpy as np
@@ -138,6 +139,152 @@ def test_inference_service_matches_direct_path(gpu):
             assert [e.predictions[0].class_id for e in out.elements] == list(direct[:n].argmax(axis=1))
             np.testing.assert_allclose([e.predictions[0].score for e in out.elements], direct[:n].max(axis=1), rtol=1e-6)
         client.close()
+        # the batching life cycle on the same path: 11 single-image requests and a 3-image one on ONE stream come back as
+        # their own BatchPredictions, computed in ceil(14 / 8) = 2 merged forward passes
+        got = []
+        stream = rpc.ClientStreaming(f"127.0.0.1:{server.port}", "/ssd.Inference/BatchedCompute", rpc.message("ssd.BatchInput"),
+                                     rpc.message("ssd.BatchPredictions"), on_response=got.append)
+        picks = [(i, [i % 8]) for i in range(5)] + [(5, [1, 2, 3])] + [(i, [i % 8]) for i in range(6, 12)]
+        for bid, rows in picks:
+            stream.write(rpc.message("ssd.BatchInput")(batch_id=bid, batch_size=len(rows), data=x[rows].tobytes()))
+        assert stream.done().result(120) == grpc.StatusCode.OK
+        assert [o.batch_id for o in got] == [bid for bid, _ in picks]
+        for o, (bid, rows) in zip(got, picks):
+            assert [e.predictions[0].class_id for e in o.elements] == list(direct[rows].argmax(axis=1))
+            np.testing.assert_allclose([e.predictions[0].score for e in o.elements], direct[rows].max(axis=1), rtol=1e-6)
+        stream.close()
         server.shutdown()
     finally:
         mgr.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# streaming and batching life cycles (trtlab/nvrpc/tests/test_pingpong.{h,cc}: PingPongStreaming, ...EarlyFinish, ...EarlyCancel)
+# ------------------------------------------------------------------------------------------------------------------
+def _testing_service(contexts):
+    In, Out = rpc.message("nvrpc.testing.Input"), rpc.message("nvrpc.testing.Output")
+    server = rpc.Server()
+    svc = server.register_async_service("nvrpc.testing.TestService")
+    ex = server.register_executor(rpc.Executor(4))
+    for method, ctx in contexts.items():
+        ex.register_contexts(svc.register_rpc(method, In, Out, ctx), None, 2)
+    return server.async_start(), In, Out
+
+
+def test_streaming_life_cycle_pingpong_early_finish_and_early_cancel():
+    import grpc
+
+    class PingPong(rpc.StreamingContext):          # one response per request, the context never ends the stream itself
+        def stream_initialized(self, stream):
+            self.count = 0
+
+        def request_received(self, request, stream):
+            self.count += 1
+            assert stream.write_response(rpc.message("nvrpc.testing.Output")(batch_id=request.batch_id))
+
+    class EarlyFinish(rpc.StreamingContext):       # finishes after the 3rd request: later requests are dropped, status OK
+        def stream_initialized(self, stream):
+            self.count = 0
+
+        def request_received(self, request, stream):
+            self.count += 1
+            stream.write_response(rpc.message("nvrpc.testing.Output")(batch_id=request.batch_id))
+            if self.count == 3:
+                assert stream.finish_stream() and not stream.is_connected()
+                assert not stream.write_response(rpc.message("nvrpc.testing.Output")(batch_id=99))
+
+    class EarlyCancel(EarlyFinish):                # cancels instead: the client sees CANCELLED
+        def request_received(self, request, stream):
+            self.count += 1
+            stream.write_response(rpc.message("nvrpc.testing.Output")(batch_id=request.batch_id))
+            if self.count == 3:
+                stream.cancel_stream()
+
+    class Fanout(rpc.StreamingContext):            # zero-to-many responses per request, some written after the client is done
+        def stream_initialized(self, stream):
+            self.seen = []
+
+        def request_received(self, request, stream):
+            self.seen.append(request.batch_id)
+            for _ in range(request.batch_id % 3):
+                stream.write_response(rpc.message("nvrpc.testing.Output")(batch_id=request.batch_id))
+
+        def requests_finished(self, stream):
+            stream.write_response(rpc.message("nvrpc.testing.Output")(batch_id=1000 + len(self.seen)))
+
+    class Broken(rpc.StreamingContext):
+        def request_received(self, request, stream):
+            raise RuntimeError("callback failed")
+
+    server, In, Out = _testing_service({"Streaming": PingPong, "EarlyFinish": EarlyFinish, "EarlyCancel": EarlyCancel,
+                                        "Fanout": Fanout, "Broken": Broken})
+    try:
+        def run(method, n):
+            c = rpc.ClientStreaming(f"127.0.0.1:{server.port}", f"/nvrpc.testing.TestService/{method}", In, Out)
+            for i in range(n):
+                c.write(In(batch_id=i))
+            status = c.done().result(20)
+            ids = [r.batch_id for r in c.responses]
+            c.close()
+            return status, ids
+
+        assert run("Streaming", 10) == (grpc.StatusCode.OK, list(range(10)))
+        assert run("Streaming", 0) == (grpc.StatusCode.OK, [])
+        assert run("EarlyFinish", 10) == (grpc.StatusCode.OK, [0, 1, 2])
+        status, ids = run("EarlyCancel", 10)
+        assert status == grpc.StatusCode.CANCELLED and ids[:3] == [0, 1, 2][:len(ids)]
+        assert run("Fanout", 6) == (grpc.StatusCode.OK, [1, 2, 2, 4, 5, 5, 1006])
+        assert run("Broken", 2)[0] == grpc.StatusCode.INTERNAL
+        assert run("Streaming", 3) == (grpc.StatusCode.OK, [0, 1, 2])      # the contexts went back to their pools
+        # responses can be consumed while requests are still being written (true bidirectional streaming)
+        got = []
+        c = rpc.ClientStreaming(f"127.0.0.1:{server.port}", "/nvrpc.testing.TestService/Streaming", In, Out, on_response=got.append)
+        c.write(In(batch_id=7))
+        deadline = time.time() + 10
+        while not got and time.time() < deadline:
+            time.sleep(0.01)
+        assert [r.batch_id for r in got] == [7]
+        c.write(In(batch_id=8))
+        assert c.done().result(20) == grpc.StatusCode.OK and [r.batch_id for r in got] == [7, 8]
+        c.close()
+    finally:
+        server.shutdown()
+
+
+def test_batching_life_cycle_all_in_then_all_out():
+    import grpc
+    received = []
+
+    class Batch(rpc.BatchingContext):
+        def on_request_received(self, request):
+            received.append(request.batch_id)
+
+        def execute_rpc(self, requests, responses):
+            assert [r.batch_id for r in requests] == received[-len(requests):] if requests else True
+            total = sum(r.batch_id for r in requests)                   # something only the WHOLE batch can know
+            for r in requests:
+                responses.append(rpc.message("nvrpc.testing.Output")(batch_id=total * 100 + r.batch_id))
+
+    class Short(rpc.BatchingContext):
+        def execute_rpc(self, requests, responses):
+            responses.extend(rpc.message("nvrpc.testing.Output")(batch_id=r.batch_id) for r in requests[:-1])
+
+    server, In, Out = _testing_service({"Batching": Batch, "Short": Short})
+    try:
+        c = rpc.ClientStreaming(f"127.0.0.1:{server.port}", "/nvrpc.testing.TestService/Batching", In, Out)
+        for i in (1, 2, 3, 4):
+            c.write(In(batch_id=i))
+        time.sleep(0.2)
+        assert c.responses == []                                         # nothing comes back before the client is done
+        assert c.done().result(20) == grpc.StatusCode.OK
+        assert [r.batch_id for r in c.responses] == [1001, 1002, 1003, 1004] and received == [1, 2, 3, 4]
+        c.close()
+        c = rpc.ClientStreaming(f"127.0.0.1:{server.port}", "/nvrpc.testing.TestService/Batching", In, Out)
+        assert c.done().result(20) == grpc.StatusCode.OK and c.responses == []   # an empty batch is a valid batch
+        c.close()
+        c = rpc.ClientStreaming(f"127.0.0.1:{server.port}", "/nvrpc.testing.TestService/Short", In, Out)
+        c.write(In(batch_id=1)), c.write(In(batch_id=2))
+        assert c.done().result(20) == grpc.StatusCode.INTERNAL           # one response per request is the contract
+        c.close()
+    finally:
+        server.shutdown()
