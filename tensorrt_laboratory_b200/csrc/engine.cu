@@ -793,6 +793,8 @@ int make_i8_conv_launch(b2_context* c, const Op& op, int batch, int bn, int stag
     a.relu = int(r.relu & 1);
     a.M = M, a.Cout = int(r.cout_phys);
     a.cblocks = int(r.cin_phys) / 128;
+    a.last_cb_mmas = (int(r.cin) % 128) ? (int(r.cin) % 128 + 31) / 32 : 4;
+    a.cout_real = int(r.cout);
     a.num_kblocks = int(r.taps) * a.cblocks;
     a.kw = op.kw(), a.HoWo = int(to.h * to.w), a.Wo = int(to.w);
     a.stride_h = op.sh(), a.stride_w = op.sw(), a.pad_h = op.ph(), a.pad_w = op.pw_lo();

@@ -58,7 +58,6 @@ conv_i8_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     constexpr int TILE_BYTES = 128 * BN;     // int8 output / residual tile
     constexpr int NBOX = BN / 128;           // 128-column TMA boxes per tile row
     constexpr int NG = BN / 32;
-    constexpr uint32_t IDESC = make_idesc_i8(128, BN);
     static_assert(TILE_BYTES <= PIPE_BYTES, "the output staging tile reuses the pipeline buffers");
 
     extern __shared__ uint8_t smem_raw[];
@@ -82,6 +81,11 @@ conv_i8_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int n0 = blockIdx.x * BN;
     const int m0 = blockIdx.y * 128;
     const int nk = p.num_kblocks;
+    // real output channels of this N tile, rounded up to the MMA's granularity: the instruction is issued N = nv wide, only
+    // nv weight rows are fetched, and the epilogue writes zeros for the rest (what the padded weights would have produced)
+    int nv = p.cout_real - n0;
+    nv = nv >= BN ? BN : (nv <= 0 ? 32 : ((nv + 31) / 32) * 32);
+    const uint32_t b_bytes = static_cast<uint32_t>(nv) * 128u;
 
     // ---------------- prologue: nothing here depends on the previous kernel's output ----------------
     if (threadIdx.x == 0) {
@@ -133,7 +137,7 @@ conv_i8_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const int s = i % STAGES;
             if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
             if (elect_one_sync()) {
-                mbar_expect_tx(&full_bar[s], A_STAGE + B_STAGE);
+                mbar_expect_tx(&full_bar[s], A_STAGE + b_bytes);
                 if (tiled)
                     tma_load_2d(&mapA, &full_bar[s], sA + s * A_STAGE, cur_cb * 128, m0);
                 else
@@ -151,22 +155,29 @@ conv_i8_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
+        const uint32_t idesc = make_idesc_i8(128, nv);
+        int cur_cb = 0;
         for (int i = 0; i < nk; ++i) {
             const int s = i % STAGES;
             mbar_wait(&full_bar[s], (i / STAGES) & 1);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(sA + s * A_STAGE);
             const uint32_t b_addr = smem_u32(sB + s * B_STAGE);
+            // all-zero 32-byte slices at the end of a tap's last channel block contribute nothing: not issued
+            const int nj = (cur_cb == p.cblocks - 1) ? p.last_cb_mmas : 4;
             if (elect_one_sync()) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {  // 4 x (K = 32 bytes) inside one 128-byte swizzle row
-                    const uint64_t ad = make_smem_desc(a_addr + j * 32, 16, 1024, 2);
-                    const uint64_t bd = make_smem_desc(b_addr + j * 32, 16, 1024, 2);
-                    umma_i8(tmem_base, ad, bd, IDESC, (i > 0 || j > 0) ? 1u : 0u);
+                    if (j < nj) {
+                        const uint64_t ad = make_smem_desc(a_addr + j * 32, 16, 1024, 2);
+                        const uint64_t bd = make_smem_desc(b_addr + j * 32, 16, 1024, 2);
+                        umma_i8(tmem_base, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+                    }
                 }
                 umma_commit(&empty_bar[s]);
             }
             __syncwarp();
+            if (++cur_cb == p.cblocks) cur_cb = 0;
         }
         if (elect_one_sync()) umma_commit(accum_bar);
         __syncwarp();
@@ -177,7 +188,7 @@ conv_i8_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int i = 0; i < nk; ++i) {
             const int s = i % STAGES;
             if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
-            if (elect_one_sync()) bulk_load_1d(&full_bar[s], sB + s * B_STAGE, src + i * kstride, B_STAGE);
+            if (elect_one_sync()) bulk_load_1d(&full_bar[s], sB + s * B_STAGE, src + i * kstride, b_bytes);
             __syncwarp();
         }
     }
@@ -195,6 +206,15 @@ conv_i8_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const bool relu = p.relu != 0;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
+        if (g * 32 >= nv) {  // padding channels (CTA-uniform): the result is zero by construction, nothing to read or compute
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = g * 32 + h * 16;
+                *reinterpret_cast<uint4*>(sOut + static_cast<uint32_t>((col >> 7) * (128 * 128)) + swz_off<128>(row, (col & 127) >> 4)) =
+                    make_uint4(0u, 0u, 0u, 0u);
+            }
+            continue;
+        }
         uint32_t acc[32];
         tmem_ld32(taddr + g * 32, acc);
         tmem_wait_ld();

@@ -135,6 +135,9 @@ struct I8ConvArgs {
     int has_res, relu;
     int M, Cout, num_kblocks, cblocks;  // cblocks = Cin_phys / 128
     int kw, HoWo, Wo, stride_h, stride_w, pad_h, pad_w, a_mode;
+    // padding that need not be computed: the LAST 128-channel block of every tap holds `last_cb_mmas` (1..4) 32-byte MMA
+    // slices of real input channels (the rest is zero), and output channels >= cout_real are padding whose result is zero
+    int last_cb_mmas, cout_real;
 };
 struct I8ConvLaunch {
     CUtensorMap mapA;    // int8 activations: 2-D tiled [M, Cin] (box 128 rows x 128 B) or 4-D im2col
