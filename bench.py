@@ -218,6 +218,8 @@ def run_config2(capi, builder, peaks_int8_tops: float = 4500.0):
         "roofline": {"bound": "tensor", "kernel": "conv_i8_tcgen05 (the 154 INT8 convolutions of one forward pass)",
                      "achieved": ops * steps / (ms * 1e-3) / 1e12, "peak": peaks_int8_tops, "unit": "TOP/s",
                      "frac": ops * steps / (ms * 1e-3) / 1e12 / peaks_int8_tops,
+                     # DRAM bytes (read + write) of the 155 conv launches of one batch-32 forward pass, committed ncu pass
+                     "traffic": 1171.1e6, "traffic_source": "profiles/ncu_metrics_r2_int8.csv",
                      "peak_source": "NOMINAL dense int8 4.5 POP/s (B200_PROFILING.md table; MEASURED_PEAKS.json has no int8 entry)"},
     }
 
@@ -371,8 +373,8 @@ def run_b200(args):
         "bound": "tensor", "kernel": "conv_f16_tcgen05 (all %d conv launches of one forward pass)" % n_conv,
         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
         # DRAM bytes (read+write) of the 53 conv launches of ONE forward pass = one step, from the committed ncu pass
-        # profiles/ncu_metrics_r1i.csv (cold L2; outputs stay L2-resident inside each kernel)
-        "traffic": 267.2e6, "traffic_source": "profiles/ncu_metrics_r1i.csv",
+        # profiles/ncu_metrics_r2l.csv (cold L2; outputs stay L2-resident inside each kernel)
+        "traffic": 267.3e6, "traffic_source": "profiles/ncu_metrics_r2l.csv",
         "peak_source": peak_src,
         "flops_per_step": conv_flops, "conv_share_of_step": conv_share,
         # aggregate over 4 overlapping contexts (above) vs the kernels in isolation on ONE stream: conv FLOPs / (single-
