@@ -604,11 +604,9 @@ conv_f16_tcgen05_ws(const __grid_constant__ CUtensorMap mapA, const __grid_const
         pdl_wait();
         long long w_stage = 0;
         int g = 0;   // global pipeline step counter of this CTA (across tiles)
-        int lt = 0;  // local tile counter
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int mt = tile / p.tiles_n;
-            const int nt = tile - mt * p.tiles_n;
-            const int m0 = mt * 128, n0 = nt * BN;
+            const int m0 = mt * 128;
             int img0 = 0, p0 = 0, q0 = 0;
             if (p.a_mode == A_IM2COL) {
                 img0 = m0 / p.HoWo;
