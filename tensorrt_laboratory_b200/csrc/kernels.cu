@@ -1781,7 +1781,7 @@ __device__ __forceinline__ void tail_wait_counter(const int* p, int need) {
     uint32_t spins = 0;
     long long t0 = 0;
     while (tail_ld_relaxed(p) < need) {
-        __nanosleep(200);
+        __nanosleep(64);
         if ((++spins & 0xFFFu) == 0) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
@@ -1791,7 +1791,11 @@ __device__ __forceinline__ void tail_wait_counter(const int* p, int need) {
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(256) tail_f16_kernel(const TailArgs a) {
+// (256, 2): at most 128 registers per thread.  Unbounded the kernel took 154, i.e. 39 K registers per CTA -- more than an SM
+// that already hosts three conv CTAs of OTHER contexts has left, so the tail's CTAs queued for emptier SMs and a forward pass
+// at 4 contexts paid ~24 us for it (fused 51.1 k img/s against 53.1 k unfused; 52.4 k with the cap, 50.2 k at 80 registers where
+// the spills cost more than the residency wins).
+__global__ void __launch_bounds__(256, 2) tail_f16_kernel(const TailArgs a) {
     extern __shared__ uint4 s_dyn[];  // FC: [8][K/8] staged pooled rows
     __shared__ float part[8][32][8];
     __shared__ float red[32];
@@ -1801,17 +1805,37 @@ __global__ void __launch_bounds__(256) tail_f16_kernel(const TailArgs a) {
     const int groups_per_img = (C8 + 31) / 32;
     const int n_pool = a.N * groups_per_img;
     const int n_fc = (a.Cout + 7) / 8;
-    const int total = n_pool + n_fc + a.N;
+    // counters: [0] FC tickets  [1] pool items done  [2] FC items done  [3] CTAs gone  [4] pool tickets  [5] softmax tickets
+    // Order of work in a CTA: take an FC item and pull its weight rows into registers (constants: no dependency), THEN help
+    // with the pooling until no pool ticket is left, then wait for the pooling, compute, and finally take softmax rows.
+    // With one CTA per FC item (the default grid) the 4 MB of weights stream in while the pooling runs and the FC phase is a
+    // single wave.  Deadlock-free for any grid: a CTA only ever waits for items whose tickets are held by RUNNING CTAs, and
+    // those wait on nothing (pool) or on pool items only (FC).
+    auto take = [&](int* counter, int limit) -> int {
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = tail_ld_relaxed(counter) < limit ? atomicAdd(counter, 1) : limit;
+        __syncthreads();
+        return s_ticket;
+    };
     pdl_launch_dependents();
     bool waited = false;  // griddepcontrol.wait executed (before the first read of the previous kernel's output)
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_ticket = atomicAdd(a.ctrl, 1);
-        __syncthreads();
-        const int t = s_ticket;
-        if (t >= total) break;
-        if (t < n_pool) {
-            // ---------------- global average pool: one (image, 256-channel group) ----------------
+        const int f = take(a.ctrl + 0, n_fc);
+        const bool have_fc = f < n_fc;
+        const int j = f * 8 + warp;
+        const int K = a.C;
+        const int kv = K / 8, per_lane = kv / 32;  // uint4 per row / per lane (<= 8)
+        uint4 wreg[8];
+        if (have_fc && j < a.Cout) {  // constants: fetched before the dependency wait, in flight during the pooling
+            const uint4* wr = reinterpret_cast<const uint4*>(a.w + static_cast<size_t>(j) * K);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < per_lane) wreg[i] = __ldg(wr + lane + 32 * i);
+        }
+        // ---------------- global average pool: (image, 256-channel group) items until none is left ----------------
+        for (;;) {
+            const int t = take(a.ctrl + 4, n_pool);
+            if (t >= n_pool) break;
             if (!waited) pdl_wait(), waited = true;
             const int n = t / groups_per_img;
             const int cg = (t - n * groups_per_img) * 32 + lane;
@@ -1821,14 +1845,24 @@ __global__ void __launch_bounds__(256) tail_f16_kernel(const TailArgs a) {
             for (int i = 0; i < 8; ++i) acc[i] = 0.f;
             if (cg < C8) {
                 const uint4* base = reinterpret_cast<const uint4*>(a.in) + static_cast<size_t>(n) * a.HW * C8 + cg;
-                for (int px = slice; px < a.HW; px += 8) {
-                    const uint4 v = __ldg(base + static_cast<size_t>(px) * C8);
-                    const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+                // up to 8 of this slice's pixels are requested before the first is consumed (the loop was one L2 round trip
+                // per pixel); they are still ADDED in ascending pixel order, so the sums keep their bits
+                for (int px0 = slice; px0 < a.HW; px0 += 64) {
+                    uint4 v[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 f = __half22float2(h2[i]);
-                        acc[2 * i] += f.x;
-                        acc[2 * i + 1] += f.y;
+                    for (int k = 0; k < 8; ++k)
+                        if (px0 + 8 * k < a.HW) v[k] = __ldg(base + static_cast<size_t>(px0 + 8 * k) * C8);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (px0 + 8 * k < a.HW) {
+                            const __half2* h2 = reinterpret_cast<const __half2*>(&v[k]);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 f = __half22float2(h2[i]);
+                                acc[2 * i] += f.x;
+                                acc[2 * i + 1] += f.y;
+                            }
+                        }
                     }
                 }
             }
@@ -1856,18 +1890,9 @@ __global__ void __launch_bounds__(256) tail_f16_kernel(const TailArgs a) {
                 __threadfence();
                 atomicAdd(a.ctrl + 1, 1);
             }
-        } else if (t < n_pool + n_fc) {
+        }
+        if (have_fc) {
             // ---------------- fully connected: 8 neurons (one per warp) x all images ----------------
-            const int j = (t - n_pool) * 8 + warp;
-            const int K = a.C;
-            const int kv = K / 8, per_lane = kv / 32;  // uint4 per row / per lane (<= 8)
-            uint4 wreg[8];
-            if (j < a.Cout) {  // constants: fetched before the dependency wait
-                const uint4* wr = reinterpret_cast<const uint4*>(a.w + static_cast<size_t>(j) * K);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (i < per_lane) wreg[i] = __ldg(wr + lane + 32 * i);
-            }
             if (!waited) pdl_wait(), waited = true;
             if (threadIdx.x == 0) tail_wait_counter(a.ctrl + 1, n_pool);
             __syncthreads();
@@ -1916,17 +1941,35 @@ __global__ void __launch_bounds__(256) tail_f16_kernel(const TailArgs a) {
                 __threadfence();
                 atomicAdd(a.ctrl + 2, 1);
             }
-        } else {
-            // ---------------- softmax: one image ----------------
-            const int n = t - n_pool - n_fc;
+            continue;  // another FC item, if the grid is smaller than the item list
+        }
+        // ---------------- softmax: one image per ticket, once every FC item is in ----------------
+        for (;;) {
+            const int n = take(a.ctrl + 5, a.N);
+            if (n >= a.N) break;
             if (!waited) pdl_wait(), waited = true;
             if (threadIdx.x == 0) tail_wait_counter(a.ctrl + 2, n_fc);
             __syncthreads();
             const float* x = a.logits + static_cast<size_t>(n) * a.Cout;
             float* y = a.out + static_cast<size_t>(n) * a.Cout;
             const int nwarp = blockDim.x >> 5;
+            // the row is read ONCE (<= 8 logits per thread stay in registers through max, sum and normalisation: three L2 round
+            // trips became one); rows wider than 8 x blockDim fall back to re-reading.  Same operations in the same order.
+            constexpr int kKeep = 8;
+            const bool keep = a.Cout <= kKeep * static_cast<int>(blockDim.x);
+            float xv[kKeep];
             float m = -INFINITY;
-            for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) m = fmaxf(m, __ldcg(x + i));
+            if (keep) {
+#pragma unroll
+                for (int k = 0; k < kKeep; ++k) {
+                    const int i = threadIdx.x + k * blockDim.x;
+                    xv[k] = i < a.Cout ? __ldcg(x + i) : -INFINITY;
+                }
+#pragma unroll
+                for (int k = 0; k < kKeep; ++k) m = fmaxf(m, xv[k]);
+            } else {
+                for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) m = fmaxf(m, __ldcg(x + i));
+            }
             for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             if (lane == 0) red[warp] = m;
             __syncthreads();
@@ -1934,21 +1977,43 @@ __global__ void __launch_bounds__(256) tail_f16_kernel(const TailArgs a) {
             for (int i = 1; i < nwarp; ++i) m = fmaxf(m, red[i]);
             __syncthreads();
             float sum = 0.f;
-            for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) sum += expf(__ldcg(x + i) - m);
+            if (keep) {
+#pragma unroll
+                for (int k = 0; k < kKeep; ++k) {
+                    const int i = threadIdx.x + k * blockDim.x;
+                    if (i < a.Cout) {
+                        xv[k] = expf(xv[k] - m);
+                        sum += xv[k];
+                    }
+                }
+            } else {
+                for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) sum += expf(__ldcg(x + i) - m);
+            }
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             if (lane == 0) red[warp] = sum;
             __syncthreads();
             sum = 0.f;
             for (int i = 0; i < nwarp; ++i) sum += red[i];
             const float inv = 1.0f / sum;
-            for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) y[i] = expf(__ldcg(x + i) - m) * inv;
+            if (keep) {
+#pragma unroll
+                for (int k = 0; k < kKeep; ++k) {
+                    const int i = threadIdx.x + k * blockDim.x;
+                    if (i < a.Cout) y[i] = xv[k] * inv;
+                }
+            } else {
+                for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) y[i] = expf(__ldcg(x + i) - m) * inv;
+            }
         }
+        break;
     }
     // the last CTA to leave re-arms the counters for the next launch
     if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(a.ctrl + 3, 1) == static_cast<int>(gridDim.x) - 1) {
-            a.ctrl[0] = 0, a.ctrl[1] = 0, a.ctrl[2] = 0, a.ctrl[3] = 0;
+            a.ctrl[0] = 0, a.ctrl[1] = 0, a.ctrl[2] = 0, a.ctrl[4] = 0, a.ctrl[5] = 0;
+            __threadfence();
+            a.ctrl[3] = 0;
         }
     }
 }
