@@ -145,20 +145,37 @@ struct Resources : public std::enable_shared_from_this<Resources> {
 
 // ---- ThreadPool --------------------------------------------------------------------------------
 class ThreadPool {
+    // queue, lock and stop flag are shared with the workers, so a worker outlives the ThreadPool object safely -- which
+    // happens when the LAST owner of the pool's owner is a task: InferRunner's stages capture shared_ptr<InferenceManager>,
+    // and if the caller drops its reference while the post stage is still unwinding, the manager (and this pool) is
+    // destroyed ON a pool thread.  Joining oneself is EDEADLK (std::system_error -> terminate): that worker is detached
+    // instead, finds the stop flag in the shared state when its task returns, and leaves.
+    struct State {
+        std::deque<std::function<void()>> tasks;
+        std::mutex mutex;
+        std::condition_variable cv;
+        bool stop = false;
+    };
+
   public:
-    explicit ThreadPool(size_t nthreads) {
+    explicit ThreadPool(size_t nthreads) : m_State(std::make_shared<State>()) {
         if (nthreads == 0) nthreads = 1;
-        for (size_t i = 0; i < nthreads; ++i) m_Workers.emplace_back([this] { Loop(); });
+        for (size_t i = 0; i < nthreads; ++i) m_Workers.emplace_back([st = m_State] { Loop(*st); });
     }
     ThreadPool(const ThreadPool&) = delete;
     ThreadPool& operator=(const ThreadPool&) = delete;
     ~ThreadPool() {
         {
-            std::lock_guard<std::mutex> l(m_Mutex);
-            m_Stop = true;
+            std::lock_guard<std::mutex> l(m_State->mutex);
+            m_State->stop = true;
         }
-        m_Cv.notify_all();
-        for (auto& t : m_Workers) t.join();
+        m_State->cv.notify_all();
+        for (auto& t : m_Workers) {
+            if (t.get_id() == std::this_thread::get_id())
+                t.detach();  // destroyed from one of our own tasks: see above
+            else
+                t.join();
+        }
     }
 
     template <class F, class... Args>
@@ -172,34 +189,32 @@ class ThreadPool {
 
     void enqueue(std::function<void()> task) {
         {
-            std::lock_guard<std::mutex> l(m_Mutex);
-            if (m_Stop) throw std::runtime_error("enqueue on stopped ThreadPool");
-            m_Tasks.push_back(std::move(task));
+            std::lock_guard<std::mutex> l(m_State->mutex);
+            if (m_State->stop) throw std::runtime_error("enqueue on stopped ThreadPool");
+            m_State->tasks.push_back(std::move(task));
         }
-        m_Cv.notify_one();
+        m_State->cv.notify_one();
     }
 
     int Size() const { return int(m_Workers.size()); }
 
   private:
-    void Loop() {
+    static void Loop(State& st) {
         for (;;) {
             std::function<void()> task;
             {
-                std::unique_lock<std::mutex> l(m_Mutex);
-                m_Cv.wait(l, [this] { return m_Stop || !m_Tasks.empty(); });
-                if (m_Tasks.empty()) return;  // stop requested and drained
-                task = std::move(m_Tasks.front());
-                m_Tasks.pop_front();
+                std::unique_lock<std::mutex> l(st.mutex);
+                st.cv.wait(l, [&st] { return st.stop || !st.tasks.empty(); });
+                if (st.tasks.empty()) return;  // stop requested and drained
+                task = std::move(st.tasks.front());
+                st.tasks.pop_front();
             }
             task();
+            task = nullptr;  // the task's captures die HERE, not at the top of the next iteration under the lock
         }
     }
+    std::shared_ptr<State> m_State;
     std::vector<std::thread> m_Workers;
-    std::deque<std::function<void()>> m_Tasks;
-    std::mutex m_Mutex;
-    std::condition_variable m_Cv;
-    bool m_Stop = false;
 };
 
 // ---- Pool<T>: blocking pool of shared resources; Pop() hands out a shared_ptr whose deleter returns

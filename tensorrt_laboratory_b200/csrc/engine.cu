@@ -1152,8 +1152,15 @@ int tune_engine_batch(b2_context* c, int batch) {
         const Tensor& to = e->tensors[r.out];
         const int kbsz = conv_kb(c, op), nkb = conv_num_kblocks(c, op);
         const bool side = op.side_join >= 0;
-        int splits = side ? 1 : 0;
-        if (batch != e->max_batch && !side) {
+        // Split-K is the ONE tactic that changes the fp32 summation order (every other one -- N tile, ring depth, halo,
+        // persistent -- adds the same products in the same order), so letting the timing pick it would make the BITS of a
+        // model depend on the load-time measurement of that process: seen once as a 4e-3 relative difference between a tuned
+        // manager and an untuned session of the same plan.  It never won a serving-regime timing anyway (the closest
+        // candidate is 40 % behind, profiles/tune_dump_r2_rn50_b8_4streams.log), so the tuner leaves it alone unless
+        // B2_TUNE_SPLITK=1; `splits` stays available as an explicit option.
+        static const bool tune_splitk = env_int("B2_TUNE_SPLITK", 0) != 0;
+        int splits = (side || !tune_splitk) ? 1 : 0;
+        if (batch != e->max_batch && !side && tune_splitk) {
             std::lock_guard<std::mutex> lock(e->tune_mutex);
             auto it = e->tuned.find({int(i), e->max_batch});
             if (it != e->tuned.end()) splits = it->second.splits;
@@ -2193,7 +2200,7 @@ int b2_engine_refine_tactics(b2_engine* e, int streams, int passes, double* gain
             // of SMs; splitting K shortens the link and puts more SMs on it.  The per-layer tuner rejects it (more total
             // work), the chain-bound whole-network rate is where it can pay.  (The split factor fixes the fp32 summation
             // order; it is chosen here, at max batch, and shared by every batch size.)
-            if (!(op.side_join >= 0) && cur.splits == 1 && !cur.halo) {
+            if (env_int("B2_TUNE_SPLITK", 0) != 0 && !(op.side_join >= 0) && cur.splits == 1 && !cur.halo) {  // opt-in: changes bits
                 const int m_tiles = (batch * int(e->tensors[r.out].h * e->tensors[r.out].w) + 127) / 128;
                 for (int sp : {2, 4}) {
                     const int tiles = m_tiles * (int(r.cout_phys) / cur.bn);

@@ -93,6 +93,28 @@ static void test_thread_pool() {
     EXPECT(n == 10);
 }
 
+// The last owner of a pool's owner may be one of the pool's own tasks (InferRunner's post stage holds the manager): the pool
+// is then destroyed ON its own thread.  Joining oneself throws EDEADLK and terminates the process; the worker must be let go.
+static void test_thread_pool_destroyed_from_its_own_task() {
+    struct Owner {
+        explicit Owner(std::atomic<int>* d) : pool(2), destroyed(d) {}
+        ~Owner() { destroyed->fetch_add(1); }
+        ThreadPool pool;
+        std::atomic<int>* destroyed;
+    };
+    for (int round = 0; round < 50; ++round) {
+        std::atomic<int> destroyed{0};
+        std::promise<void> go;
+        std::shared_future<void> gate = go.get_future().share();
+        auto owner = std::make_shared<Owner>(&destroyed);
+        owner->pool.enqueue(std::function<void()>([owner, gate] { gate.wait(); }));  // this task keeps the owner alive ...
+        owner.reset();                                                               // ... and becomes its LAST owner
+        go.set_value();
+        for (int i = 0; i < 2000 && destroyed.load() == 0; ++i) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        EXPECT(destroyed.load() == 1);
+    }
+}
+
 static void test_async_compute() {
     using Wrapper = AsyncComputeWrapper<void(std::shared_ptr<int>&)>;
     auto compute = Wrapper::Wrap([](std::shared_ptr<int>& p) { return *p + 1; });
@@ -320,6 +342,7 @@ int main() {
     test_pool_blocks_until_available();
     test_pool_outlives_handle();
     test_thread_pool();
+    test_thread_pool_destroyed_from_its_own_task();
     test_async_compute();
     test_bytes();
     test_cyclic_allocator();
