@@ -1,3 +1,8 @@
+"""Invariant check: a TUNED engine, an untuned (cost-model) engine and the InferenceManager pipeline (tuned at registration,
+two lanes, dynamic batcher) of the same plan must agree bit for bit, whatever tactics the load-time tuner picked in this
+process.  Loops `n_tuned` engines and `n_managers` managers and prints the unusual tactics (split-K / persistent / halo) of
+each.  Written to chase a once-seen 4e-3 difference that turned out to be split-K being chosen by the timing.
+  python tools/gpu_tactic_invariance.py [n_tuned=12] [n_managers=6]"""
 import os, sys, numpy as np
 sys.path.insert(0, os.getcwd())
 from tensorrt_laboratory_b200 import builder, capi, weights
