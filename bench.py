@@ -259,22 +259,13 @@ def run_b200(args):
         if dist is not None:
             dist.barrier()
 
+    from tensorrt_laboratory_b200 import replicas  # the N > 1 host logic (MAX / gather over ranks; gloo-tested on CPU)
+
     def gather_over_ranks(x: float):
-        if dist is None:
-            return [x]
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        out = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(out, t)
-        return [float(o.item()) for o in out]
+        return replicas.gather_over_ranks(x, dist)
 
     def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return replicas.max_over_ranks(x, dist)
 
     # ---- value: device-resident inputs, CONTEXTS streams, CUDA events ---------------------------------------
     sampler = ClockSampler(local)

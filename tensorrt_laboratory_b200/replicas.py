@@ -25,17 +25,33 @@ def least_outstanding(outstanding: List[int]) -> int:
     return min(range(len(outstanding)), key=lambda i: (outstanding[i], i))
 
 
+def _tensor(x: float, dist):
+    import torch
+    t = torch.tensor([float(x)], dtype=torch.float64)
+    return t.cuda() if dist.get_backend() == "nccl" else t
+
+
+def max_over_ranks(x: float, dist=None) -> float:
+    """MAX of one scalar over the replicas (the job's elapsed time is its slowest rank's); identity without a process group."""
+    if dist is None or not dist.is_initialized():
+        return float(x)
+    t = _tensor(x, dist)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_over_ranks(x: float, dist=None) -> List[float]:
+    """Every rank's value of one scalar, in rank order (per-replica rates in the N-GPU bench line)."""
+    if dist is None or not dist.is_initialized():
+        return [float(x)]
+    t = _tensor(x, dist)
+    out = [t.clone() for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(o.item()) for o in out]
+
+
 def aggregate_throughput(local_elapsed_s: float, steps_per_rank: int, batch: int, dist=None) -> float:
     """Whole-job inferences/s for weak scaling: every rank runs ``steps_per_rank`` steps; the job time is
     the MAX over ranks.  ``dist``: an initialised ``torch.distributed`` module or None (single process)."""
-    world = 1
-    elapsed = float(local_elapsed_s)
-    if dist is not None and dist.is_initialized():
-        import torch
-        world = dist.get_world_size()
-        t = torch.tensor([elapsed], dtype=torch.float64)
-        if dist.get_backend() == "nccl":
-            t = t.cuda()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
-    return world * steps_per_rank * batch / elapsed
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    return world * steps_per_rank * batch / max_over_ranks(local_elapsed_s, dist)

@@ -26,6 +26,7 @@ def test_round_robin_sharding_covers_every_request_once():
 def test_least_outstanding():
     assert replicas.least_outstanding([3, 1, 1, 5]) == 1
     assert replicas.least_outstanding([0]) == 0
+    assert replicas.max_over_ranks(3.5) == 3.5 and replicas.gather_over_ranks(2.0) == [2.0]   # no process group: identity
 
 
 def _worker(rank, world, port, q):
@@ -34,6 +35,8 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     # rank r pretends its K steps took (1 + r) seconds: the job time is the max, the work is the sum
     v = replicas.aggregate_throughput(1.0 + rank, steps_per_rank=100, batch=8, dist=dist)
+    assert replicas.max_over_ranks(10.0 * (rank + 1), dist) == 10.0 * world
+    assert replicas.gather_over_ranks(float(rank), dist) == [float(r) for r in range(world)]
     mine = replicas.shard_requests(10, world, rank)
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
