@@ -287,7 +287,9 @@ def run_b200(args):
     steady = []    # per leg: the mid-stream window measurement
 
     def e2e_run(plan_blob):
-        mgr = capi.InferenceManager(CONTEXTS, BUFFERS, pre_threads=1, cuda_threads=1, post_threads=3)
+        # thread counts of examples/00_TensorRT/infer.cc:100-102 (1 / 1 / 3); B2_BENCH_THREADS="pre,cuda,post" for experiments
+        pre_t, cuda_t, post_t = (int(v) for v in os.environ.get("B2_BENCH_THREADS", "1,1,3").split(","))
+        mgr = capi.InferenceManager(CONTEXTS, BUFFERS, pre_threads=pre_t, cuda_threads=cuda_t, post_threads=post_t)
         mgr.register_model("rn50", plan_blob)
         mgr.update_resources()
         mgr.prefill_inputs("rn50", ring[:BUFFERS])
