@@ -1794,12 +1794,13 @@ __device__ __forceinline__ void tail_wait_counter(const int* p, int need) {
 // (256, 2): at most 128 registers per thread.  Unbounded the kernel took 154, i.e. 39 K registers per CTA -- more than an SM
 // that already hosts three conv CTAs of OTHER contexts has left, so the tail's CTAs queued for emptier SMs and a forward pass
 // at 4 contexts paid ~24 us for it (fused 51.1 k img/s against 53.1 k unfused; 52.4 k with the cap, 50.2 k at 80 registers where
-// the spills cost more than the residency wins).
+// the spills cost more than the residency wins).  With the weight rows in shared memory the kernel needs 116 and spills nothing.
 __global__ void __launch_bounds__(256, 2) tail_f16_kernel(const TailArgs a) {
     extern __shared__ uint4 s_dyn[];  // FC: [8][K/8] staged pooled rows
     __shared__ float part[8][32][8];
     __shared__ float red[32];
     __shared__ int s_ticket;
+    __shared__ __align__(8) uint64_t wbar;  // the FC item's weight rows have landed in s_w (one bulk copy per item)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C8 = a.C / 8;
     const int groups_per_img = (C8 + 31) / 32;
@@ -1817,20 +1818,28 @@ __global__ void __launch_bounds__(256, 2) tail_f16_kernel(const TailArgs a) {
         __syncthreads();
         return s_ticket;
     };
+    const int K = a.C;
+    const int kv = K / 8, per_lane = kv / 32;  // uint4 per row / per lane (<= 8)
+    uint4* const s_w = s_dyn + 8 * kv;         // [8 neurons][K/8]: this item's weight rows
+    if (threadIdx.x == 0) {
+        mbar_init(&wbar, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    uint32_t wphase = 0;
     pdl_launch_dependents();
     bool waited = false;  // griddepcontrol.wait executed (before the first read of the previous kernel's output)
     for (;;) {
-        const int f = take(a.ctrl + 0, n_fc);
+        const int f = take(a.ctrl + 0, n_fc);  // (its barriers also publish wbar's initialisation and retire the previous item)
         const bool have_fc = f < n_fc;
         const int j = f * 8 + warp;
-        const int K = a.C;
-        const int kv = K / 8, per_lane = kv / 32;  // uint4 per row / per lane (<= 8)
-        uint4 wreg[8];
-        if (have_fc && j < a.Cout) {  // constants: fetched before the dependency wait, in flight during the pooling
-            const uint4* wr = reinterpret_cast<const uint4*>(a.w + static_cast<size_t>(j) * K);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (i < per_lane) wreg[i] = __ldg(wr + lane + 32 * i);
+        if (have_fc && threadIdx.x == 0) {
+            // constants: ONE bulk copy (<= 8 consecutive rows = 32 KB) started before the dependency wait, in flight during the
+            // pooling -- no registers held meanwhile (the kernel used to park the rows in 32 registers per thread)
+            const int rows_w = min(8, a.Cout - f * 8);
+            const uint32_t bytes = static_cast<uint32_t>(rows_w) * static_cast<uint32_t>(K) * 2u;
+            mbar_expect_tx(&wbar, bytes);
+            bulk_load_1d(&wbar, s_w, a.w + static_cast<size_t>(f) * 8 * K, bytes);
         }
         // ---------------- global average pool: (image, 256-channel group) items until none is left ----------------
         for (;;) {
@@ -1896,6 +1905,8 @@ __global__ void __launch_bounds__(256, 2) tail_f16_kernel(const TailArgs a) {
             if (!waited) pdl_wait(), waited = true;
             if (threadIdx.x == 0) tail_wait_counter(a.ctrl + 1, n_pool);
             __syncthreads();
+            mbar_wait(&wbar, wphase);
+            wphase ^= 1u;
             for (int nb = 0; nb < a.N; nb += 8) {
                 const int rows = min(8, a.N - nb);
                 __syncthreads();
@@ -1909,7 +1920,8 @@ __global__ void __launch_bounds__(256, 2) tail_f16_kernel(const TailArgs a) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         if (i < per_lane) {
-                            const __half2* w2 = reinterpret_cast<const __half2*>(&wreg[i]);
+                            const uint4 wv = s_w[warp * kv + lane + 32 * i];
+                            const __half2* w2 = reinterpret_cast<const __half2*>(&wv);
                             float2 wf[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) wf[q] = __half22float2(w2[q]);
@@ -2032,7 +2044,7 @@ int launch_tail_f16(const TailArgs& a, cudaStream_t stream) {
         use_pdl = v ? atoi(v) : 1;
     }
     const unsigned blocks = static_cast<unsigned>(items < cap ? items : cap);
-    const size_t smem = static_cast<size_t>(a.C) * 2 * 8;
+    const size_t smem = static_cast<size_t>(a.C) * 2 * 8 * 2;  // pooled rows of 8 images + the weight rows of 8 neurons
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(tail_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
