@@ -58,7 +58,17 @@ def _blob(buf: bytes) -> np.ndarray:
 
 
 def read_layers(buf: bytes) -> List[dict]:
-    """-> [{name, type, blobs: [ndarray]}] in file order."""
+    """-> [{name, type, blobs: [ndarray]}] in file order.  A truncated or corrupt file is a ValueError, whatever the
+    low-level symptom (a varint running off the end, a length past the buffer, bytes that are not UTF-8 ...)."""
+    try:
+        return _read_layers(buf)
+    except ValueError:
+        raise
+    except (IndexError, struct.error, OverflowError, MemoryError) as ex:
+        raise ValueError(f"caffemodel: truncated or corrupt NetParameter ({type(ex).__name__}: {ex})") from ex
+
+
+def _read_layers(buf: bytes) -> List[dict]:
     layers = []
     for field, wt, v in _fields(buf):
         if field == 2 and wt == 2:

@@ -175,7 +175,18 @@ def _value_info_shape(buf: bytes) -> List[int]:
 
 
 def parse_model(buf: bytes) -> dict:
-    """-> {nodes: [...], initializers: {name: ndarray}, inputs: [names], outputs: [names], input_shapes: {name: dims}}"""
+    """-> {nodes: [...], initializers: {name: ndarray}, inputs: [names], outputs: [names], input_shapes: {name: dims}}
+    A truncated or corrupt file is a ValueError, whatever the low-level symptom."""
+    import struct
+    try:
+        return _parse_model(buf)
+    except ValueError:
+        raise
+    except (IndexError, struct.error, OverflowError, MemoryError, KeyError, TypeError) as ex:
+        raise ValueError(f"onnx: truncated or corrupt ModelProto ({type(ex).__name__}: {ex})") from ex
+
+
+def _parse_model(buf: bytes) -> dict:
     graph = None
     for fno, _, v in _fields(buf):
         if fno == 7:

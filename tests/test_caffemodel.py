@@ -87,3 +87,40 @@ def test_plan_from_caffemodel_is_identical(tmp_path):
     assert r.returncode == 0, r.stderr
     want = builder.build_plan(graph.lower(net, w), builder.PREC_FP16, 2)
     assert out.read_bytes() == want
+
+
+def test_corrupt_files_are_value_errors_never_crashes():
+    """Random truncations and byte flips of a valid file either load (payload bytes changed) or raise ValueError."""
+    import random
+    net = _mini_net()
+    buf = caffemodel.save_caffemodel(net, weights.random_weights(net, 1))
+    rnd = random.Random(0)
+    outcomes = {"ok": 0, "ValueError": 0}
+    for t in range(400):
+        b = bytearray(buf)
+        if t % 2:
+            b = b[:rnd.randrange(1, len(b))]
+        else:
+            for _ in range(3):
+                b[rnd.randrange(len(b))] = rnd.randrange(256)
+        try:
+            caffemodel.load_caffemodel(bytes(b), net)
+            outcomes["ok"] += 1
+        except ValueError:
+            outcomes["ValueError"] += 1
+    assert outcomes["ValueError"] > 100 and sum(outcomes.values()) == 400
+
+
+def test_build_tool_int8_from_caffemodel(tmp_path):
+    """tools/build_engine.py --caffemodel ... --precision int8: the plan it writes is the INT8 plan of the same weights."""
+    net = graph.resnet_caffe(50)
+    w = weights.random_weights(net, 5)
+    mp = tmp_path / "rn50.caffemodel"
+    mp.write_bytes(caffemodel.save_caffemodel(net, w))
+    out = tmp_path / "rn50_i8.plan"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "build_engine.py"), "--model", "resnet50", "--caffemodel", str(mp),
+                        "--precision", "int8", "--batch", "2", "-o", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    from tensorrt_laboratory_b200 import quantize
+    low = quantize.quantize_lowered(graph.lower(net, w), weights.synthetic_input(8, seed=4321))
+    assert out.read_bytes() == builder.build_plan(low, builder.PREC_INT8, 2)

@@ -69,3 +69,29 @@ def test_unsupported_operators_are_reported():
         onnx_import.import_onnx(model)
     with pytest.raises(ValueError, match="input shape"):
         onnx_import.import_onnx({**model, "nodes": model["nodes"][:-1], "input_shapes": {}})
+
+
+def test_corrupt_onnx_files_are_value_errors_never_crashes():
+    """Random truncations and byte flips of a valid ModelProto either parse (payload bytes changed) or raise ValueError."""
+    import random
+    sys_path_net = builder.single_conv_net(64, 8, 8, 64, 3, 1, 1, residual=True)
+    buf = onnx_import.export_onnx(sys_path_net, weights.random_weights(sys_path_net, 0))
+    rnd = random.Random(2)
+    outcomes = {"ok": 0, "ValueError": 0}
+    for t in range(400):
+        b = bytearray(buf)
+        if t % 2:
+            b = b[:rnd.randrange(1, len(b))]
+        else:
+            for _ in range(3):
+                b[rnd.randrange(len(b))] = rnd.randrange(256)
+        try:
+            model = onnx_lite.parse_model(bytes(b))
+            try:
+                onnx_import.import_onnx(model)
+            except (ValueError, KeyError, NotImplementedError):
+                pass  # a well-formed protobuf that no longer describes a supported CNN
+            outcomes["ok"] += 1
+        except ValueError:
+            outcomes["ValueError"] += 1
+    assert outcomes["ValueError"] > 100 and sum(outcomes.values()) == 400
