@@ -278,7 +278,7 @@ class Engine:
         else:
             check(lib.b2_runtime_create(C.byref(self._rt)))
             check(lib.b2_engine_deserialize(self._rt, blob, len(blob), C.byref(self.handle)))
-        self.name = lib.b2_engine_name(self.handle).decode()
+        self.name = lib.b2_engine_name(self.handle).decode(errors="replace")
         self.max_batch = lib.b2_engine_max_batch(self.handle)
         self.precision = lib.b2_engine_precision(self.handle)
         self.bindings: List[dict] = []
@@ -288,7 +288,7 @@ class Engine:
             check(lib.b2_engine_binding_dims(self.handle, i, dims, C.byref(nd)))
             shape = tuple(int(dims[d]) for d in range(nd.value))
             self.bindings.append(dict(
-                name=lib.b2_engine_binding_name(self.handle, i).decode(),
+                name=lib.b2_engine_binding_name(self.handle, i).decode(errors="replace"),
                 is_input=bool(lib.b2_engine_binding_is_input(self.handle, i)),
                 dtype=lib.b2_engine_binding_dtype(self.handle, i),
                 shape=shape,

@@ -5,6 +5,7 @@ import os
 import re
 import struct
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -240,3 +241,38 @@ def test_per_layer_roofs_of_resnet50():
     assert abs(by["res2b_branch2c"]["read_bytes"] + by["res2b_branch2c"]["write_bytes"] - 28.9e6) < 0.2e6
     assert all(f["floor_us"] == max(f["tensor_floor_us"], f["memory_floor_us"]) for f in fl)
     assert 55 < sum(f["floor_us"] for f in fl) < 62
+
+
+_PLAN_FUZZ = r"""
+import random, sys
+sys.path.insert(0, sys.argv[1])
+from tensorrt_laboratory_b200 import builder, capi, graph, weights
+net = builder.single_conv_net(64, 8, 8, 64, 3, 1, 1, residual=True)
+blob = builder.build_plan(graph.lower(net, weights.random_weights(net, 0)), builder.PREC_FP16, 2)
+rnd = random.Random(int(sys.argv[2]))
+ok = err = 0
+for t in range(int(sys.argv[3])):
+    b = bytearray(blob)
+    mode = t % 3
+    if mode == 0:
+        b = b[:rnd.randrange(1, len(b))]
+    else:
+        for _ in range(rnd.randrange(1, 4)):
+            i = rnd.randrange(4096) if mode == 1 else rnd.randrange(len(b))   # mostly the header and the records
+            b[i] = rnd.randrange(256)
+    try:
+        capi.Engine(bytes(b), inspect_only=True).destroy()
+        ok += 1
+    except capi.B2Error:
+        err += 1
+print("ok", ok, "rejected", err)
+"""
+
+
+def test_plan_parser_survives_random_corruption():
+    """b2_engine_deserialize on 900 randomly truncated / byte-flipped plans (in a child process, so that a crash of the C
+    parser is a test failure and not the end of the test run): every one is either accepted or rejected with a B2 error."""
+    out = subprocess.run([sys.executable, "-c", _PLAN_FUZZ, ROOT, "7", "900"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, (out.returncode, out.stderr[-1500:])
+    ok, rejected = int(out.stdout.split()[1]), int(out.stdout.split()[3])
+    assert ok + rejected == 900 and rejected > 200
